@@ -1,0 +1,174 @@
+/*
+ * treegp_b200 -- C ABI of the B200-native GP hot path.
+ *
+ * The reference (PFLeget/treegp v1.4.1) is pure Python and has no FFI layer; its operator boundary
+ * is what `GPInterpolation`, `log_likelihood` and `two_pcf` call into numpy/scipy/TreeCorr.  Each
+ * entry point below replaces one of those call sites (cited per function, paths relative to
+ * /root/reference).  A maintainer binds them with ctypes.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer owned by the caller (e.g. torch.Tensor.data_ptr()),
+ *    FP64 / int64 / int32, C-contiguous row-major, unless a parameter says "host";
+ *  - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and never
+ *    synchronise, except where stated;
+ *  - return value: 0 on success, negative tgp_status on a usage / CUDA error
+ *    (tgp_last_error() gives the text).  There is no CPU fallback anywhere;
+ *  - factorisation status follows LAPACK: *info == 0 ok, *info == j > 0 means the leading minor
+ *    of order j is not positive definite (host maps this to logL = -inf exactly where
+ *    treegp/log_likelihood.py:38-39 does).
+ */
+#ifndef TREEGP_B200_H
+#define TREEGP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TGP_ABI_VERSION 1
+
+typedef enum {
+  TGP_OK = 0,
+  TGP_ERR_INVALID = -1,   /* bad argument */
+  TGP_ERR_CUDA = -2,      /* CUDA runtime error, see tgp_last_error() */
+  TGP_ERR_UNSUPPORTED = -3
+} tgp_status;
+
+/* Stationary correlation families: K = amp * f(q), q = delta^T M delta (M = inverse metric). */
+typedef enum {
+  TGP_FAM_RBF = 0,        /* exp(-q/2): sklearn RBF, treegp AnisotropicRBF  (kernels.py:114-126)          */
+  TGP_FAM_VONKARMAN = 1,  /* q^(5/12) K_{5/6}(2 pi sqrt q)/lim0: VonKarman / AnisotropicVonKarman
+                             (kernels.py:251-277, :358-381)                                               */
+  TGP_FAM_MATERN12 = 2,   /* exp(-sqrt q)                           sklearn Matern(nu=0.5)                */
+  TGP_FAM_MATERN32 = 3,   /* (1+sqrt(3q)) exp(-sqrt(3q))            sklearn Matern(nu=1.5)                */
+  TGP_FAM_MATERN52 = 4    /* (1+sqrt(5q)+5q/3) exp(-sqrt(5q))       sklearn Matern(nu=2.5)                */
+} tgp_family;
+
+/* POD lowering of `const * Kernel` trees produced by treegp.kernels.eval_kernel (kernels.py:17-59). */
+typedef struct {
+  int32_t family;   /* tgp_family */
+  int32_t ndim;     /* 1 or 2 */
+  double amp;       /* ConstantKernel value (sigma^2); 1.0 if absent */
+  double m00, m01, m11; /* symmetric inverse metric; ndim==1 uses m00 only */
+} tgp_kernel;
+
+int tgp_abi_version(void);
+const char* tgp_last_error(void);
+
+/* ---- (1) covariance construction --------------------------------------------------------- */
+
+/* K(X,X) [+ diag(diag_add)] -> out (N x N, leading dimension ld >= N).
+ * Replaces kernel.__call__(X) + eye*y_err**2  (gp_interp.py:180, log_likelihood.py:29).
+ * X: (N, ndim).  diag_add: N values or NULL.  lower_only != 0 writes only j <= i (what
+ * tgp_potrf reads); otherwise the full symmetric matrix. */
+int tgp_kmat_sym(const double* X, int64_t N, const tgp_kernel* k /*host*/, const double* diag_add,
+                 double* out, int64_t ld, int lower_only, void* stream);
+
+/* K(Xs, X) -> out (M x N, ld >= N).  Replaces kernel.__call__(X2, Y=X1) (gp_interp.py:177). */
+int tgp_kmat_cross(const double* Xs, int64_t M, const double* X, int64_t N,
+                   const tgp_kernel* k /*host*/, double* out, int64_t ld, void* stream);
+
+/* ---- (2) dense linear algebra -------------------------------------------------------------- */
+
+/* In-place lower Cholesky A = L L^T of the row-major N x N matrix (only j <= i is read or
+ * written).  Replaces scipy.linalg.cholesky (gp_interp.py:181,187; log_likelihood.py:30).
+ * info: device int32, see header comment. */
+int tgp_potrf(double* A, int64_t N, int64_t ld, int32_t* info, void* stream);
+
+/* Solve L L^T x = b in place for one right-hand side (b: N).  Replaces cho_solve
+ * (gp_interp.py:182, log_likelihood.py:31). */
+int tgp_potrs_vec(const double* L, int64_t N, int64_t ld, double* b, void* stream);
+
+/* B <- B L^-T for an (M x N) row-major B (each ROW of B is one right-hand side; afterwards row m
+ * holds L^-1 b_m).  The building block of cho_solve with many right-hand sides
+ * (gp_interp.py:190). */
+int tgp_trsm_rows(const double* L, int64_t N, int64_t ld, double* B, int64_t M, int64_t ldb,
+                  void* stream);
+
+/* C (M x Nc, ldc) <- C - A (M x Kd, lda) * B^T (B: Nc x Kd, ldb).  Used for HT.dot(v)
+ * (gp_interp.py:191) in factored form.  lower_only != 0 updates only tiles with j <= i. */
+int tgp_gemm_nt_sub(double* C, int64_t M, int64_t Nc, int64_t ldc, const double* A, int64_t lda,
+                    const double* B, int64_t ldb, int64_t Kd, int lower_only, void* stream);
+
+/* out[0] = sum_i 2 log L_ii   (log_likelihood.py:33);  out[1] = y . alpha (log_likelihood.py:32) when
+ * y and alpha are non-NULL. out: device double[2]. */
+int tgp_logdet_chi2(const double* L, int64_t N, int64_t ld, const double* y, const double* alpha,
+                    double* out, void* stream);
+
+/* Whole marginal log-likelihood evaluation (log_likelihood.py:29-37) in one call:
+ * work (N x N, ld) receives K (lower) then L; out: device double[3] = {logL, chi2, logdet}; info as
+ * tgp_potrf.  When *info != 0 out[0] is -inf (log_likelihood.py:38-39).
+ * want_alpha != 0: alpha (N) receives K^-1 y (both triangular sweeps) and chi2 = y . alpha;
+ * want_alpha == 0: alpha receives L^-1 y (forward sweep only) and chi2 = ||L^-1 y||^2 -- the same
+ * number without the backward sweep; this is what the hyper-parameter search loop uses. */
+int tgp_loglike(const double* X, const double* y, const double* yerr2, int64_t N,
+                const tgp_kernel* k /*host*/, double* work, int64_t ld, double* alpha, int want_alpha,
+                double* out, int32_t* info, void* stream);
+
+/* ---- (4) predict ----------------------------------------------------------------------------- */
+
+/* mean[m] = sum_n K(Xs_m, X_n) alpha_n without materialising K(Xs, X).
+ * Replaces HT = kernel(X2, Y=X1); np.dot(HT, alpha)  (gp_interp.py:177,183). */
+int tgp_predict_mean(const double* Xs, int64_t M, const double* X, int64_t N,
+                     const tgp_kernel* k /*host*/, const double* alpha, double* mean, void* stream);
+
+/* var[m] = amp - || L^-1 K(X, Xs_m) ||^2, the diagonal of gp_interp.py:190-191.
+ * work: 16-byte aligned device buffer of at least chunk*(N+1) doubles; `chunk` test points are
+ * processed at a time (K(Xs_chunk, X) is materialised there, then solved in place on the DMMA pipe). */
+int tgp_predict_var(const double* Xs, int64_t M, const double* X, int64_t N,
+                    const tgp_kernel* k /*host*/, const double* L, int64_t ld, double* work,
+                    int64_t chunk, double* var, void* stream);
+
+/* ---- (3) two-point correlation function ------------------------------------------------------ */
+
+typedef enum {
+  TGP_BIN_TWOD = 0, /* treecorr bin_type="TwoD", bin_slop=0 (two_pcf.py:297-305) */
+  TGP_BIN_LOG = 1   /* treecorr default Log binning in the bin_slop -> 0 limit (two_pcf.py:330-334) */
+} tgp_bintype;
+
+/* Brute-force pair binning of one or several catalogues (a bootstrap batch is ncat > 1).
+ *
+ *  px, py, pk, pw : concatenated point arrays (total = cat_off[ncat]); pk is the scalar field k,
+ *                   pw the weights w or NULL (unit weights).
+ *  cat_off        : device int64[ncat+1]; catalogue c owns points [cat_off[c], cat_off[c+1]).
+ *  max_cat_len    : host upper bound on the catalogue lengths (sizes the launch).
+ *  edges          : device double[nbins+1] of decision THRESHOLDS: edges[k] (1 <= k < nbins) is the
+ *                   smallest double that the binning formula sends to bin >= k, so that
+ *                   bin(v) = #{k in 1..nbins-1 : v >= edges[k]} reproduces the formula bit for bit.
+ *                   TwoD additionally needs edges[0] = -inf and edges[nbins] = +inf.
+ *  TGP_BIN_TWOD   : with (dx,dy) = p_j - p_i and r2 = dx*dx + dy*dy (un-fused), a pair is kept iff
+ *                   r2 != 0, r2 >= min_sep2 and max(|dx|,|dy|) < max_sep; column = bin(dx),
+ *                   row = bin(dy), flat index row*nbins + column (nb = nbins^2).  Every unordered
+ *                   pair is entered twice, at (dx,dy) and at (-dx,-dy).
+ *  TGP_BIN_LOG    : kept iff min_sep2 <= r2 < max_sep^2; index = bin(r2) (nb = nbins); every
+ *                   unordered pair entered once.
+ *  tile_rank, tile_nranks : multi-GPU sharding -- runs of pair tiles are dealt round-robin; rank
+ *                   r of n computes a disjoint subset and the per-rank outputs add up to the
+ *                   single-GPU result (counts exactly; FP64 sums up to summation order).
+ *  npairs         : device int64[ncat*nb]   pair counts
+ *  sumw           : device double[ncat*nb]  sum w_i w_j
+ *  sumwkk         : device double[ncat*nb]  sum w_i k_i w_j k_j
+ *  sumwr          : device double[ncat*nb]  sum w_i w_j r   (LOG only; may be NULL)
+ * Outputs are ACCUMULATED into (the caller zeroes them).  xi = sumwkk / sumw is left to the caller
+ * so that multi-GPU partial sums can be all-reduced first.
+ */
+int tgp_pairbin(const double* px, const double* py, const double* pk, const double* pw,
+                const int64_t* cat_off, int32_t ncat, int64_t max_cat_len, int32_t bin_type,
+                const double* edges, int32_t nbins, double min_sep2, double max_sep,
+                int32_t tile_rank, int32_t tile_nranks, int64_t* npairs, double* sumw,
+                double* sumwkk, double* sumwr, void* stream);
+
+/* Points per pair tile (informational). */
+int tgp_pairbin_tile(void);
+
+/* ---- measurement helpers --------------------------------------------------------------------- */
+
+/* FP64 micro-peaks used as roofline denominators.  kind 0: DFMA (FP64 FMA pipe), 1: DMMA
+ * (mma.sync m8n8k4 f64).  Synchronous.  Writes achieved TFLOP/s to *tflops (host). */
+int tgp_microbench_fp64(int kind, int iters, double* tflops /*host*/);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TREEGP_B200_H */

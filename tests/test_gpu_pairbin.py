@@ -1,0 +1,109 @@
+"""GPU parity: pair binning (csrc/pairbin.cu) through the C ABI vs the brute-force oracle.
+
+Counts must be bit-exact; FP64 sums agree up to summation order (stated tolerance: 1e-12 relative to
+the sum of |contributions| in the bin)."""
+import numpy as np
+import pytest
+
+from oracle import pairbin_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_pairbin(x, y, k, w, min_sep, max_sep, nbins, bin_type, offsets=None, nranks=1):
+    import torch
+    from treegp_b200 import _cabi, backend, binning
+
+    bt = _cabi.BIN_TWOD if bin_type == "TwoD" else _cabi.BIN_LOG
+    edges = binning.twod_thresholds(max_sep, nbins) if bin_type == "TwoD" else binning.log_thresholds(min_sep, max_sep, nbins)
+    if offsets is None:
+        offsets = np.array([0, len(x)], dtype=np.int64)
+    maxlen = int(np.diff(offsets).max())
+    args = (backend.to_device(x), backend.to_device(y), backend.to_device(k),
+            None if w is None else backend.to_device(w), backend.to_device(offsets, torch.int64), maxlen, bt,
+            backend.to_device(edges), nbins, min_sep, max_sep)
+    tot = None
+    for r in range(nranks):
+        res = backend.pairbin(*args, rank=r, nranks=nranks)
+        res = [None if t is None else t.cpu().numpy() for t in res]
+        tot = res if tot is None else [None if a is None else a + b for a, b in zip(tot, res)]
+    return tot
+
+
+def _check(res, ref, c=0):
+    npairs, sumw, sumwkk, sumwr = res
+    np.testing.assert_array_equal(npairs[c], ref["npairs"])
+    scale = max(1.0, np.abs(ref["weight"]).max())
+    np.testing.assert_allclose(sumw[c], ref["weight"], rtol=1e-12, atol=1e-12 * scale)
+    np.testing.assert_allclose(sumwkk[c], ref["sumwkk"], rtol=0, atol=1e-11 * max(1.0, np.abs(ref["sumwkk"]).max()))
+    if sumwr is not None:
+        np.testing.assert_allclose(sumwr[c], ref["sumwr"], rtol=1e-12, atol=1e-12 * scale)
+
+
+@pytest.mark.parametrize("n", [2, 255, 256, 257, 1000, 3001])
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("cfg", [("TwoD", 0.0, 14.142135623730951, 21), ("TwoD", 0.5, 3.0, 20), ("Log", 0.1, 1.75, 15),
+                                 ("Log", 0.3, 12.0, 20)])
+def test_pairbin_matches_oracle(gpu_ready, n, weighted, cfg):
+    bin_type, mn, mx, nb = cfg
+    rng = np.random.default_rng(n + 17 * nb)
+    x, y = rng.uniform(-10, 10, n), rng.uniform(-10, 10, n)
+    k = rng.normal(size=n)
+    w = rng.uniform(0.5, 2.0, n) if weighted else None
+    if n > 10:  # coincident points must be skipped (r2 == 0), as bootstrap duplicates are
+        x[7], y[7] = x[3], y[3]
+    ref = po.pairbin(x, y, k, w, mn, mx, nb, bin_type)
+    _check(_gpu_pairbin(x, y, k, w, mn, mx, nb, bin_type), ref)
+
+
+def test_pairbin_values_on_bin_edges(gpu_ready):
+    """Lattice points put many displacements exactly on bin edges: the threshold rule must agree with
+    the floor((d+max_sep)/bin_size) rule bit for bit."""
+    g = np.arange(-10, 11, dtype=np.float64)
+    X, Y = np.meshgrid(g, g)
+    x, y = X.ravel() * 0.5, Y.ravel() * 0.5
+    k = np.cos(x) * np.sin(y)
+    for mx, nb in ((5.0, 20), (5.25, 21), (4.0, 16)):
+        ref = po.pairbin(x, y, k, None, 0.0, mx, nb, "TwoD")
+        _check(_gpu_pairbin(x, y, k, None, 0.0, mx, nb, "TwoD"), ref)
+    ref = po.pairbin(x, y, k, None, 0.5, 8.0, 16, "Log")
+    _check(_gpu_pairbin(x, y, k, None, 0.5, 8.0, 16, "Log"), ref)
+
+
+def test_pairbin_twod_is_point_symmetric(gpu_ready):
+    rng = np.random.default_rng(5)
+    n, nb = 4000, 21
+    x, y, k = rng.uniform(0, 30, n), rng.uniform(0, 30, n), rng.normal(size=n)
+    npairs, sumw, sumwkk, _ = _gpu_pairbin(x, y, k, None, 0.0, 10.0, nb, "TwoD")
+    c = npairs[0].reshape(nb, nb)
+    np.testing.assert_array_equal(c, c[::-1, ::-1])
+    assert c.sum() % 2 == 0
+
+
+def test_pairbin_batched_catalogues_and_rank_sharding(gpu_ready):
+    """A bootstrap batch (ragged catalogues) in one launch, and the multi-GPU split: the per-rank
+    partial results must add up to the single-rank answer (counts exactly)."""
+    rng = np.random.default_rng(8)
+    sizes = [700, 1, 513, 0, 1290]
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n = offsets[-1]
+    x, y, k, w = rng.uniform(-10, 10, n), rng.uniform(-10, 10, n), rng.normal(size=n), rng.uniform(0.5, 2, n)
+    for bin_type, mn, mx, nb in (("TwoD", 0.0, 9.0, 21), ("Log", 0.2, 9.0, 12)):
+        one = _gpu_pairbin(x, y, k, w, mn, mx, nb, bin_type, offsets)
+        three = _gpu_pairbin(x, y, k, w, mn, mx, nb, bin_type, offsets, nranks=3)
+        for c, sz in enumerate(sizes):
+            s = slice(offsets[c], offsets[c + 1])
+            ref = po.pairbin(x[s], y[s], k[s], w[s], mn, mx, nb, bin_type)
+            _check(one, ref, c)
+            _check(three, ref, c)
+
+
+def test_pairbin_n20000_vs_oracle(gpu_ready):
+    rng = np.random.default_rng(2)
+    n, nb = 20000, 21
+    x, y, k = rng.uniform(-50, 50, n), rng.uniform(-50, 50, n), rng.normal(size=n)
+    mx = np.sqrt(2) * 100 / 2
+    ref = po.pairbin(x, y, k, None, 0.0, mx, nb, "TwoD")
+    res = _gpu_pairbin(x, y, k, None, 0.0, mx, nb, "TwoD")
+    _check(res, ref)
+    assert res[0].sum() == ref["npairs"].sum()

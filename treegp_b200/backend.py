@@ -1,0 +1,176 @@
+"""Device-side operators of the GP hot path: thin wrappers that hand torch CUDA tensors
+(device memory + current stream: plumbing) to the C ABI in libtreegp_b200.so.
+
+Every function here requires a CUDA device; nothing falls back to the CPU.
+"""
+import ctypes
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import TgpKernel, check
+
+F64 = torch.float64
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _cabi.TgpError("treegp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def to_device(a, dtype=F64):
+    """numpy / tensor -> contiguous CUDA tensor (no copy if already there)."""
+    dev = require_cuda()
+    if isinstance(a, torch.Tensor):
+        return a.to(device=dev, dtype=dtype).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(dev)
+
+
+def as_points(X):
+    """(N,) or (N, d) host/device array -> (N, d) contiguous CUDA tensor, d in {1, 2}."""
+    Xd = to_device(X)
+    if Xd.dim() == 1:
+        Xd = Xd.reshape(-1, 1)
+    if Xd.dim() != 2 or Xd.shape[1] not in (1, 2):
+        raise ValueError("coordinates must have shape (N, 1) or (N, 2); got %r" % (tuple(Xd.shape),))
+    return Xd.contiguous()
+
+
+def even(n):
+    return (int(n) + 1) & ~1
+
+
+def alloc_matrix(rows, cols, device=None):
+    """rows x cols FP64 workspace with an even leading dimension (16-byte rows for the DMMA loads)."""
+    dev = device or require_cuda()
+    return torch.empty((int(rows), even(cols)), dtype=F64, device=dev)
+
+
+def kmat_sym(X, kdesc, diag_add=None, out=None, lower_only=False):
+    """K(X,X) + diag(diag_add).  Returns the (N, ld) workspace; the matrix is out[:, :N]."""
+    X = as_points(X)
+    N = X.shape[0]
+    if out is None:
+        out = alloc_matrix(N, N, X.device)
+    lib = _cabi.load()
+    check(lib.tgp_kmat_sym(_p(X), N, ctypes.byref(kdesc), _p(diag_add), _p(out), out.stride(0),
+                           int(bool(lower_only)), _stream()), "tgp_kmat_sym")
+    return out
+
+
+def kmat_cross(Xs, X, kdesc, out=None):
+    Xs, X = as_points(Xs), as_points(X)
+    M, N = Xs.shape[0], X.shape[0]
+    if out is None:
+        out = alloc_matrix(M, N, X.device)
+    lib = _cabi.load()
+    check(lib.tgp_kmat_cross(_p(Xs), M, _p(X), N, ctypes.byref(kdesc), _p(out), out.stride(0), _stream()),
+          "tgp_kmat_cross")
+    return out
+
+
+def potrf(A, N):
+    """In-place lower Cholesky of the leading N x N block of the workspace A.  Returns info (device int32)."""
+    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    check(_cabi.load().tgp_potrf(_p(A), N, A.stride(0), _p(info), _stream()), "tgp_potrf")
+    return info
+
+
+def potrs_vec(L, N, b):
+    """Solve L L^T x = b in place (b: N-vector on the device)."""
+    check(_cabi.load().tgp_potrs_vec(_p(L), N, L.stride(0), _p(b), _stream()), "tgp_potrs_vec")
+    return b
+
+
+def trsm_rows(L, N, B, M):
+    """B[:M, :N] <- B L^-T in place."""
+    check(_cabi.load().tgp_trsm_rows(_p(L), N, L.stride(0), _p(B), M, B.stride(0), _stream()), "tgp_trsm_rows")
+    return B
+
+
+def gemm_nt_sub(C, M, Nc, A, B, Kd, lower_only=False):
+    """C[:M, :Nc] -= A[:M, :Kd] @ B[:Nc, :Kd].T in place."""
+    check(_cabi.load().tgp_gemm_nt_sub(_p(C), M, Nc, C.stride(0), _p(A), A.stride(0), _p(B), B.stride(0), Kd,
+                                       int(bool(lower_only)), _stream()), "tgp_gemm_nt_sub")
+    return C
+
+
+def logdet_chi2(L, N, y=None, alpha=None):
+    out = torch.zeros(2, dtype=F64, device=L.device)
+    check(_cabi.load().tgp_logdet_chi2(_p(L), N, L.stride(0), _p(y), _p(alpha), _p(out), _stream()),
+          "tgp_logdet_chi2")
+    return out
+
+
+def loglike(X, y, yerr2, kdesc, work=None, want_alpha=False):
+    """One marginal-likelihood evaluation.  Returns (out[3] = logL, chi2, logdet; info; alpha; work)."""
+    X = as_points(X)
+    N = X.shape[0]
+    if work is None:
+        work = alloc_matrix(N, N, X.device)
+    alpha = torch.empty(N, dtype=F64, device=X.device)
+    out = torch.zeros(3, dtype=F64, device=X.device)
+    info = torch.zeros(1, dtype=torch.int32, device=X.device)
+    check(_cabi.load().tgp_loglike(_p(X), _p(y), _p(yerr2), N, ctypes.byref(kdesc), _p(work), work.stride(0),
+                                   _p(alpha), int(bool(want_alpha)), _p(out), _p(info), _stream()), "tgp_loglike")
+    return out, info, alpha, work
+
+
+def predict_mean(Xs, X, kdesc, alpha, out=None):
+    Xs, X = as_points(Xs), as_points(X)
+    M = Xs.shape[0]
+    if out is None:
+        out = torch.empty(M, dtype=F64, device=X.device)
+    check(_cabi.load().tgp_predict_mean(_p(Xs), M, _p(X), X.shape[0], ctypes.byref(kdesc), _p(alpha), _p(out),
+                                        _stream()), "tgp_predict_mean")
+    return out
+
+
+def predict_var(Xs, X, kdesc, L, chunk=None, out=None, work=None):
+    Xs, X = as_points(Xs), as_points(X)
+    M, N = Xs.shape[0], X.shape[0]
+    if chunk is None:
+        # keep the K(Xs_chunk, X) workspace around 2 GiB
+        chunk = max(128, min(M, (1 << 28) // max(N, 1)))
+        chunk = (chunk + 127) // 128 * 128
+    if work is None:
+        work = torch.empty(chunk * (N + 1), dtype=F64, device=X.device)
+    if out is None:
+        out = torch.empty(M, dtype=F64, device=X.device)
+    check(_cabi.load().tgp_predict_var(_p(Xs), M, _p(X), N, ctypes.byref(kdesc), _p(L), L.stride(0), _p(work),
+                                       chunk, _p(out), _stream()), "tgp_predict_var")
+    return out
+
+
+def pairbin(px, py, pk, pw, cat_off, max_cat_len, bin_type, edges, nbins, min_sep, max_sep,
+            rank=0, nranks=1):
+    """Accumulate pair bins for `ncat` catalogues.  Returns (npairs int64, sumw, sumwkk, sumwr|None),
+    each shaped (ncat, nb)."""
+    ncat = int(cat_off.numel()) - 1
+    nb = nbins * nbins if bin_type == _cabi.BIN_TWOD else nbins
+    dev = px.device
+    npairs = torch.zeros((ncat, nb), dtype=torch.int64, device=dev)
+    sumw = torch.zeros((ncat, nb), dtype=F64, device=dev)
+    sumwkk = torch.zeros((ncat, nb), dtype=F64, device=dev)
+    sumwr = torch.zeros((ncat, nb), dtype=F64, device=dev) if bin_type == _cabi.BIN_LOG else None
+    check(_cabi.load().tgp_pairbin(_p(px), _p(py), _p(pk), _p(pw), _p(cat_off), ncat, int(max_cat_len),
+                                   int(bin_type), _p(edges), int(nbins), float(min_sep) ** 2, float(max_sep),
+                                   int(rank), int(nranks), _p(npairs), _p(sumw), _p(sumwkk), _p(sumwr),
+                                   _stream()), "tgp_pairbin")
+    return npairs, sumw, sumwkk, sumwr
+
+
+def microbench_fp64(kind, iters=20000):
+    require_cuda()
+    v = ctypes.c_double(0.0)
+    check(_cabi.load().tgp_microbench_fp64(int(kind), int(iters), ctypes.byref(v)), "tgp_microbench_fp64")
+    return v.value

@@ -1,0 +1,90 @@
+"""Host-side bin geometry for the 2-point correlation function.
+
+The device never divides or takes logarithms to place a pair in a bin: it compares against
+*decision thresholds* computed here once per call.  Threshold k is the smallest binary64 value v for
+which the binning formula, evaluated in IEEE double arithmetic exactly as TreeCorr states it,
+
+    TwoD:  int((v + max_sep) / bin_size)                  bin_size = 2 max_sep / nbins
+    Log :  int((0.5 ln(v) - ln(min_sep)) / bin_size)      bin_size = ln(max_sep / min_sep) / nbins,  v = r^2
+
+returns >= k.  Because both formulas are monotone in v the set {v >= threshold_k} is exactly
+{bin(v) >= k}, so counting thresholds reproduces the formula bit for bit
+(replaces the binning inside treecorr.KKCorrelation used at
+/root/reference/treegp/two_pcf.py:297-305 and :330-334).
+
+Also builds the half-plane mask and bin-centre coordinates of two_pcf.py:306-328.
+"""
+import math
+import struct
+import numpy as np
+
+
+def _key(x):
+    """Monotone map double -> int (total order of the non-NaN doubles)."""
+    (u,) = struct.unpack("<q", struct.pack("<d", x))
+    return u if u >= 0 else -(u & 0x7FFFFFFFFFFFFFFF)
+
+
+def _unkey(k):
+    u = k if k >= 0 else ((-k) | (1 << 63)) - (1 << 64)
+    (x,) = struct.unpack("<d", struct.pack("<q", u))
+    return x
+
+
+def _smallest_true(pred, lo, hi):
+    """Smallest double v in (lo, hi] with pred(v), given pred(lo) False, pred(hi) True, pred monotone."""
+    klo, khi = _key(lo), _key(hi)
+    while khi - klo > 1:
+        mid = (klo + khi) // 2
+        if pred(_unkey(mid)):
+            khi = mid
+        else:
+            klo = mid
+    return _unkey(khi)
+
+
+def twod_thresholds(max_sep, nbins):
+    """edges[0] = -inf, edges[nbins] = +inf, edges[k] = smallest dx with int((dx+max_sep)/bin_size) >= k."""
+    max_sep = float(max_sep)
+    bin_size = 2.0 * max_sep / nbins
+    edges = np.empty(nbins + 1)
+    edges[0], edges[nbins] = -np.inf, np.inf
+    for k in range(1, nbins):
+        edges[k] = _smallest_true(lambda v: int((v + max_sep) / bin_size) >= k, -max_sep, max_sep)
+    return edges
+
+
+def log_thresholds(min_sep, max_sep, nbins):
+    """edges[k] (1 <= k < nbins) = smallest r^2 whose Log bin index is >= k; edges[0], edges[nbins] are
+    min_sep^2 and max_sep^2 (informational: the range test uses those two numbers directly)."""
+    min_sep, max_sep = float(min_sep), float(max_sep)
+    bin_size = math.log(max_sep / min_sep) / nbins
+    logminsep = math.log(min_sep)
+    lo, hi = min_sep * min_sep, max_sep * max_sep
+    edges = np.empty(nbins + 1)
+    edges[0], edges[nbins] = lo, hi
+    for k in range(1, nbins):
+        edges[k] = _smallest_true(lambda v: int((0.5 * math.log(v) - logminsep) / bin_size) >= k,
+                                  lo * 0.5, hi * 2.0)
+    return edges
+
+
+def twod_mask(nbins):
+    """Boolean mask keeping one half-plane of the point-symmetric nbins x nbins grid (flattened,
+    rows = dy).  Same selection as two_pcf.py:309-321: all rows below the centre, plus -- for odd
+    nbins -- the left part of the centre row including the centre pixel."""
+    mask = np.zeros((nbins, nbins), dtype=bool)
+    half = nbins // 2 + nbins % 2
+    mask[:half, :] = True
+    if nbins % 2:
+        mask[half - 1, half:] = False
+    return mask.reshape(-1)
+
+
+def twod_coords(nbins, max_sep):
+    """(nbins^2, 2) array of bin-centre lags (dx, dy), flat index = row(dy) * nbins + column(dx)
+    (two_pcf.py:323-327)."""
+    edges = np.linspace(-float(max_sep), float(max_sep), nbins + 1)
+    centres = (edges[:-1] + edges[1:]) / 2.0
+    dy, dx = np.meshgrid(centres, centres, indexing="ij")
+    return np.stack([dx.reshape(-1), dy.reshape(-1)], axis=1)

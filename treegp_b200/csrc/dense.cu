@@ -1,0 +1,644 @@
+// FP64 dense linear algebra for the GP solve: blocked right-looking Cholesky, triangular solves,
+// log-determinant and the marginal log-likelihood.
+//
+// Replaces scipy.linalg.cholesky / cho_solve / np.dot at
+//   /root/reference/treegp/gp_interp.py:181-191 and /root/reference/treegp/log_likelihood.py:29-37.
+//
+// Layout: row-major, lower triangle (numpy's default layout for K, `lower=True` factor).
+//
+// Everything O(N^3) funnels into ONE contraction kernel, gemm_nt_sub (C -= A * B^T with both
+// operands K-contiguous), which runs on the FP64 tensor pipe via mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4;
+// there is no tcgen05/TMEM path for FP64 -- larger PTX shapes lower to the same DMMA.8x8x4).
+//   * Cholesky trailing update      A22 -= L21 L21^T            (lower tiles only)
+//   * panel / multi-RHS solves      B2  -= B1  L21^T
+//   * predictive covariance         C   -= V   V^T
+// Operand tiles are brought in by a 4-stage cp.async ring into XOR-swizzled shared memory so the
+// fragment loads are conflict-free 16-byte LDS; the K order inside a 16-wide stage is permuted
+// (even k's then odd k's) so one LDS.128 feeds two DMMAs.
+//
+// The O(N^2 nb) parts (64x64 potf2, 64-wide triangular panel solve) are FP64-ALU kernels.
+#include <float.h>
+#include <math.h>
+#include "tgp_common.cuh"
+
+// ============================================================================================
+// gemm_nt_sub
+// ============================================================================================
+constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, GEMM_THREADS = 256;
+constexpr int STAGE_DOUBLES = (BM + BN) * BK;                 // 4096 doubles = 32 KB
+constexpr int GEMM_SMEM = STAGES * STAGE_DOUBLES * 8;          // 128 KB
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem_src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// Load one BK-wide stage of a (rows x BK) operand tile: `rows` = 128, 8 chunks of 16 B per row.
+// Chunk c of row r is stored at physical chunk c ^ ((r & 1) << 2).
+__device__ __forceinline__ void load_operand_stage(double* smem, const double* __restrict__ G,
+                                                   int64_t ldg, int64_t row0, int64_t nrows,
+                                                   int64_t k0, int64_t Kd, int tid) {
+  const int c = tid & 7;
+  const int rbase = tid >> 3;  // 0..31
+  const int64_t k = k0 + 2 * c;
+  int kbytes = (int)((Kd - k) * 8);
+  kbytes = kbytes < 0 ? 0 : (kbytes > 16 ? 16 : kbytes);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = rbase + 32 * i;
+    const int64_t gr = row0 + r;
+    const bool ok = gr < nrows;
+    const double* src = G + (ok ? gr : 0) * ldg + (kbytes ? k : 0);
+    const int pc = c ^ ((r & 1) << 2);
+    cp_async16(smem + (r * 8 + pc) * 2, src, ok ? kbytes : 0);
+  }
+}
+
+// C (M x Nc) -= A (M x Kd) * B^T (Nc x Kd).  lower_only: skip tiles above the diagonal and mask n > m.
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_nt_sub_kernel(double* __restrict__ C, int64_t M, int64_t Nc, int64_t ldc,
+                   const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
+                   int64_t Kd, int lower_only) {
+  extern __shared__ __align__(16) double gsm[];
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  if (lower_only && n0 > m0 + BM - 1) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+  const int g = lane >> 2, t = lane & 3;
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  const int KT_ = (int)((Kd + BK - 1) / BK);
+  auto issue = [&](int kt) {
+    if (kt < KT_) {
+      double* sa = gsm + (kt % STAGES) * STAGE_DOUBLES;
+      double* sb = sa + BM * BK;
+      load_operand_stage(sa, A, lda, m0, M, (int64_t)kt * BK, Kd, tid);
+      load_operand_stage(sb, B, ldb, n0, Nc, (int64_t)kt * BK, Kd, tid);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES - 1; ++s) issue(s);
+
+  const int swz = (g & 1) << 2;
+  for (int kt = 0; kt < KT_; ++kt) {
+    cp_async_wait<STAGES - 2>();
+    __syncthreads();
+    issue(kt + STAGES - 1);
+    const double* sa = gsm + (kt % STAGES) * STAGE_DOUBLES;
+    const double* sb = sa + BM * BK;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int pc = (h * 4 + t) ^ swz;
+      double2 af[8], bf[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        af[i] = *reinterpret_cast<const double2*>(sa + ((wm0 + i * 8 + g) * 8 + pc) * 2);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        bf[j] = *reinterpret_cast<const double2*>(sb + ((wn0 + j * 8 + g) * 8 + pc) * 2);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y);
+    }
+  }
+  cp_async_wait<0>();
+
+  const bool vec = ((ldc & 1) == 0) && ((((uintptr_t)C) & 15) == 0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t r = m0 + wm0 + i * 8 + g;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t c = n0 + wn0 + j * 8 + 2 * t;
+      bool ok0 = c < Nc, ok1 = c + 1 < Nc;
+      if (lower_only) {
+        ok0 = ok0 && (c <= r);
+        ok1 = ok1 && (c + 1 <= r);
+      }
+      double* p = C + r * ldc + c;
+      if (vec && ok0 && ok1) {
+        double2 v = *reinterpret_cast<double2*>(p);
+        v.x -= acc[i][j][0];
+        v.y -= acc[i][j][1];
+        *reinterpret_cast<double2*>(p) = v;
+      } else {
+        if (ok0) p[0] -= acc[i][j][0];
+        if (ok1) p[1] -= acc[i][j][1];
+      }
+    }
+  }
+}
+
+static int gemm_nt_sub_launch(double* C, int64_t M, int64_t Nc, int64_t ldc, const double* A, int64_t lda,
+                              const double* B, int64_t ldb, int64_t Kd, int lower_only, cudaStream_t st) {
+  if (M <= 0 || Nc <= 0 || Kd <= 0) return TGP_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TGP_CUDA(cudaFuncSetAttribute(gemm_nt_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+    attr_set = true;
+  }
+  TGP_CHECK_ARG((lda % 2 == 0) && (ldb % 2 == 0), "leading dimensions must be even (16-byte rows)");
+  TGP_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), "operands must be 16-byte aligned");
+  dim3 grid((unsigned)tgp_cdiv(Nc, BN), (unsigned)tgp_cdiv(M, BM));
+  TGP_CHECK_ARG(grid.y <= 65535u, "M too large for one launch");
+  gemm_nt_sub_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(C, M, Nc, ldc, A, lda, B, ldb, Kd, lower_only);
+  TGP_LAUNCH_CHECK();
+  return TGP_OK;
+}
+
+// ============================================================================================
+// potf2: unblocked Cholesky of an n x n (n <= 64) diagonal block, one CTA.
+// ============================================================================================
+constexpr int NB = 64;           // inner block
+constexpr int NB_PITCH = NB + 1;
+
+__global__ void __launch_bounds__(256)
+potf2_kernel(double* __restrict__ A, int n, int64_t ld, int32_t* __restrict__ info, int64_t global_off) {
+  __shared__ double S[NB * NB_PITCH];
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < n * NB; idx += blockDim.x) {
+    const int i = idx / NB, j = idx % NB;
+    S[i * NB_PITCH + j] = (j <= i && j < n) ? A[(int64_t)i * ld + j] : 0.0;
+  }
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    const double d = S[j * NB_PITCH + j];
+    if (!(d > 0.0) || !isfinite(d)) {  // not positive definite (or NaN upstream)
+      if (tid == 0) atomicCAS(info, 0, (int32_t)(global_off + j + 1));  // keep the first failure
+    }
+    const double piv = sqrt(d);
+    const double rinv = 1.0 / piv;
+    __syncthreads();
+    // scale column j
+    for (int i = j + 1 + tid; i < n; i += blockDim.x) S[i * NB_PITCH + j] *= rinv;
+    if (tid == 0) S[j * NB_PITCH + j] = piv;
+    __syncthreads();
+    // rank-1 update of the trailing lower triangle: (i, c), j < c <= i < n
+    const int m = n - j - 1;
+    for (int idx = tid; idx < m * m; idx += blockDim.x) {
+      const int i = j + 1 + idx / m, c = j + 1 + idx % m;
+      if (c <= i) S[i * NB_PITCH + c] -= S[i * NB_PITCH + j] * S[c * NB_PITCH + j];
+    }
+    __syncthreads();
+  }
+  for (int idx = tid; idx < n * NB; idx += blockDim.x) {
+    const int i = idx / NB, j = idx % NB;
+    if (j <= i && j < n) A[(int64_t)i * ld + j] = S[i * NB_PITCH + j];
+  }
+}
+
+// ============================================================================================
+// trsm panel: B (M x nb) <- B * L^-T for an nb x nb (nb <= 64) lower-triangular L.  Thread per row,
+// right-looking over columns so the FMAs of one step are independent.
+// ============================================================================================
+constexpr int TRSM_ROWS = 128;
+constexpr int TRSM_SMEM = (NB * NB + NB + TRSM_ROWS * NB_PITCH) * 8;
+
+__global__ void __launch_bounds__(TRSM_ROWS)
+trsm_panel_kernel(const double* __restrict__ L, int nb, int64_t ldl, double* __restrict__ B, int64_t M,
+                  int64_t ldb) {
+  extern __shared__ __align__(16) double tsm[];
+  double* LsT = tsm;                 // NB x NB, LsT[j*NB + i] = L[i][j] (column j contiguous), zero padded
+  double* dinv = tsm + NB * NB;      // 1 / L[j][j]
+  double* Bs = dinv + NB;            // TRSM_ROWS x NB_PITCH
+  const int tid = threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.x * TRSM_ROWS;
+  for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
+    const int i = idx / NB, j = idx % NB;  // coalesced along j
+    double v = 0.0;
+    if (i < nb && j < i) v = L[(int64_t)i * ldl + j];
+    LsT[j * NB + i] = v;
+  }
+  if (tid < NB) dinv[tid] = (tid < nb) ? 1.0 / L[(int64_t)tid * ldl + tid] : 1.0;
+  for (int idx = tid; idx < TRSM_ROWS * NB; idx += TRSM_ROWS) {
+    const int r = idx / NB, j = idx % NB;
+    const int64_t gr = r0 + r;
+    Bs[r * NB_PITCH + j] = (gr < M && j < nb) ? B[gr * ldb + j] : 0.0;
+  }
+  __syncthreads();
+  double x[NB];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) x[j] = Bs[tid * NB_PITCH + j];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    x[j] *= dinv[j];
+    const double nx = -x[j];
+#pragma unroll
+    for (int ip = ((j + 1) & ~1); ip < NB; ip += 2) {  // pairs (ip, ip+1); entries with i <= j are zero/skipped
+      const double2 l = *reinterpret_cast<const double2*>(LsT + j * NB + ip);
+      if (ip > j) x[ip] = fma(nx, l.x, x[ip]);
+      x[ip + 1] = fma(nx, l.y, x[ip + 1]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NB; ++j) Bs[tid * NB_PITCH + j] = x[j];
+  __syncthreads();
+  for (int idx = tid; idx < TRSM_ROWS * NB; idx += TRSM_ROWS) {
+    const int r = idx / NB, j = idx % NB;
+    const int64_t gr = r0 + r;
+    if (gr < M && j < nb) B[gr * ldb + j] = Bs[r * NB_PITCH + j];
+  }
+}
+
+static int trsm_panel_launch(const double* L, int nb, int64_t ldl, double* B, int64_t M, int64_t ldb,
+                             cudaStream_t st) {
+  if (M <= 0 || nb <= 0) return TGP_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TGP_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
+    attr_set = true;
+  }
+  trsm_panel_kernel<<<(unsigned)tgp_cdiv(M, TRSM_ROWS), TRSM_ROWS, TRSM_SMEM, st>>>(L, nb, ldl, B, M, ldb);
+  TGP_LAUNCH_CHECK();
+  return TGP_OK;
+}
+
+// ============================================================================================
+// Blocked drivers (two levels: OB-wide outer blocks whose updates run on DMMA with Kd = OB,
+// NB-wide inner blocks handled by the FP64-ALU kernels above).
+// ============================================================================================
+constexpr int OB = 512;
+
+// B (M x n) <- B * L^-T, L n x n lower.  bs = block size of this level.
+static int trsm_rows_rec(const double* L, int64_t n, int64_t ldl, double* B, int64_t M, int64_t ldb, int bs,
+                         cudaStream_t st) {
+  for (int64_t k = 0; k < n; k += bs) {
+    const int64_t w = (n - k < bs) ? (n - k) : bs;
+    const double* Lkk = L + k * ldl + k;
+    double* Bk = B + k;
+    int rc;
+    if (bs == NB) {
+      rc = trsm_panel_launch(Lkk, (int)w, ldl, Bk, M, ldb, st);
+    } else {
+      rc = trsm_rows_rec(Lkk, w, ldl, Bk, M, ldb, NB, st);
+    }
+    if (rc) return rc;
+    const int64_t rest = n - k - w;
+    if (rest > 0) {
+      // B[:, k+w:] -= B[:, k:k+w] * L[k+w:, k:k+w]^T
+      rc = gemm_nt_sub_launch(B + k + w, M, rest, ldb, Bk, ldb, L + (k + w) * ldl + k, ldl, w, 0, st);
+      if (rc) return rc;
+    }
+  }
+  return TGP_OK;
+}
+
+static int potrf_rec(double* A, int64_t n, int64_t ld, int bs, int32_t* info, int64_t goff, cudaStream_t st) {
+  for (int64_t k = 0; k < n; k += bs) {
+    const int64_t w = (n - k < bs) ? (n - k) : bs;
+    double* Akk = A + k * ld + k;
+    int rc;
+    if (bs == NB) {
+      potf2_kernel<<<1, 256, 0, st>>>(Akk, (int)w, ld, info, goff + k);
+      TGP_LAUNCH_CHECK();
+      rc = TGP_OK;
+    } else {
+      rc = potrf_rec(Akk, w, ld, NB, info, goff + k, st);
+    }
+    if (rc) return rc;
+    const int64_t rest = n - k - w;
+    if (rest > 0) {
+      double* Ark = A + (k + w) * ld + k;  // rows below the diagonal block
+      rc = trsm_rows_rec(Akk, w, ld, Ark, rest, ld, NB, st);
+      if (rc) return rc;
+      rc = gemm_nt_sub_launch(A + (k + w) * ld + (k + w), rest, rest, ld, Ark, ld, Ark, ld, w, 1, st);
+      if (rc) return rc;
+    }
+  }
+  return TGP_OK;
+}
+
+static int check_mat(const double* A, int64_t N, int64_t ld) {
+  if (N < 0 || ld < N) return 1;
+  if (N > 0 && (!A || (ld & 1) || ((uintptr_t)A & 15))) return 1;
+  return 0;
+}
+
+extern "C" int tgp_potrf(double* A, int64_t N, int64_t ld, int32_t* info, void* stream) {
+  TGP_CHECK_ARG(!check_mat(A, N, ld), "A must be 16-byte aligned with even ld >= N");
+  TGP_CHECK_ARG(info != nullptr, "info");
+  cudaStream_t st = (cudaStream_t)stream;
+  TGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+  if (N == 0) return TGP_OK;
+  return potrf_rec(A, N, ld, N > OB ? OB : NB, info, 0, st);
+}
+
+extern "C" int tgp_trsm_rows(const double* L, int64_t N, int64_t ld, double* B, int64_t M, int64_t ldb,
+                             void* stream) {
+  TGP_CHECK_ARG(!check_mat(L, N, ld), "L must be 16-byte aligned with even ld >= N");
+  TGP_CHECK_ARG(M >= 0 && ldb >= N, "M/ldb");
+  if (M == 0 || N == 0) return TGP_OK;
+  TGP_CHECK_ARG(B && (ldb % 2 == 0) && ((uintptr_t)B % 16 == 0), "B must be 16-byte aligned with even ldb");
+  return trsm_rows_rec(L, N, ld, B, M, ldb, N > OB ? OB : NB, (cudaStream_t)stream);
+}
+
+extern "C" int tgp_gemm_nt_sub(double* C, int64_t M, int64_t Nc, int64_t ldc, const double* A, int64_t lda,
+                               const double* B, int64_t ldb, int64_t Kd, int lower_only, void* stream) {
+  TGP_CHECK_ARG(M >= 0 && Nc >= 0 && Kd >= 0 && ldc >= Nc && lda >= Kd && ldb >= Kd, "shape");
+  if (M == 0 || Nc == 0 || Kd == 0) return TGP_OK;
+  TGP_CHECK_ARG(C && A && B, "null pointer");
+  return gemm_nt_sub_launch(C, M, Nc, ldc, A, lda, B, ldb, Kd, lower_only, (cudaStream_t)stream);
+}
+
+// ============================================================================================
+// Single right-hand-side solves  L w = b  (forward) and  L^T x = w  (backward).
+// Outer blocks of TV rows: a one-CTA kernel solves the TV x TV diagonal block, then one wide,
+// HBM-bound update kernel touches the rest of the panel exactly once (4 N^2 bytes per sweep).
+// ============================================================================================
+constexpr int TV = 256;
+
+// forward: solve L[k0:k0+w, k0:k0+w] x = b[k0:k0+w] in place; one CTA of TV threads, thread i <-> row i.
+// 32-column chunks: the owning warp solves its 32x32 triangle in registers with shuffles, publishes
+// x, then every later row applies the 32-column update.
+__global__ void __launch_bounds__(TV)
+trsv_diag_fwd_kernel(const double* __restrict__ L, int64_t ld, int64_t k0, int w, double* __restrict__ b) {
+  __shared__ double xs[TV];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double* Lb = L + k0 * ld + k0;
+  double bi = (tid < w) ? b[k0 + tid] : 0.0;
+  for (int c0 = 0; c0 < w; c0 += 32) {
+    if (warp == (c0 >> 5)) {
+      const int i = c0 + lane;
+      const bool valid = i < w;
+      double lrow[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) lrow[j] = (valid && j < lane) ? Lb[(int64_t)i * ld + c0 + j] : 0.0;
+      const double dinv = valid ? 1.0 / Lb[(int64_t)i * ld + i] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (lane == j) bi *= dinv;
+        const double xj = __shfl_sync(0xffffffffu, bi, j);
+        bi = fma(-lrow[j], xj, bi);  // lrow[j] == 0 for lanes <= j
+      }
+      xs[i] = bi;
+    }
+    __syncthreads();
+    if (tid >= c0 + 32 && tid < w) {
+      const double* row = Lb + (int64_t)tid * ld + c0;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 2) {
+        s0 = fma(row[j], xs[c0 + j], s0);
+        s1 = fma(row[j + 1], xs[c0 + j + 1], s1);
+      }
+      bi -= (s0 + s1);
+    }
+    __syncthreads();
+  }
+  if (tid < w) b[k0 + tid] = bi;
+}
+
+// forward update: b[r] -= L[r, k0:k0+w] . x[k0:k0+w] for r >= k0+w.  Warp per row, 8 rows per CTA.
+__global__ void __launch_bounds__(256)
+trsv_update_fwd_kernel(const double* __restrict__ L, int64_t ld, int64_t N, int64_t k0, int w,
+                       double* __restrict__ b) {
+  __shared__ double xs[TV];
+  const int tid = threadIdx.x;
+  if (tid < TV) xs[tid] = (tid < w) ? b[k0 + tid] : 0.0;
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  const int64_t r = k0 + w + (int64_t)blockIdx.x * 8 + warp;
+  if (r >= N) return;
+  const double* row = L + r * ld + k0;
+  double s = 0.0;
+#pragma unroll
+  for (int j = lane; j < TV; j += 32) {
+    if (j < w) s = fma(row[j], xs[j], s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) b[r] -= s;
+}
+
+// backward: solve L[k0:k0+w, k0:k0+w]^T x = b[k0:k0+w] in place; one CTA, thread j <-> unknown j.
+// Chunks of 32 from the bottom: lane j keeps column j of the 32x32 block (L[c0+i][c0+j], i > j) in
+// registers; once x_i is final every j < i subtracts L[i][j] x_i; earlier columns then apply the
+// 32-row update reading rows of L (coalesced across threads).
+__global__ void __launch_bounds__(TV)
+trsv_diag_bwd_kernel(const double* __restrict__ L, int64_t ld, int64_t k0, int w, double* __restrict__ b) {
+  __shared__ double xs[TV];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double* Lb = L + k0 * ld + k0;
+  double bj = (tid < w) ? b[k0 + tid] : 0.0;
+  const int nchunk = (w + 31) >> 5;
+  for (int ch = nchunk - 1; ch >= 0; --ch) {
+    const int c0 = ch << 5;
+    if (warp == ch) {
+      const int j = c0 + lane;
+      const bool valid = j < w;
+      double lcol[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) lcol[i] = (valid && i > lane && c0 + i < w) ? Lb[(int64_t)(c0 + i) * ld + j] : 0.0;
+      const double dinv = valid ? 1.0 / Lb[(int64_t)j * ld + j] : 0.0;
+#pragma unroll
+      for (int i = 31; i >= 0; --i) {
+        if (lane == i) bj *= dinv;
+        const double xi = __shfl_sync(0xffffffffu, bj, i);
+        bj = fma(-lcol[i], xi, bj);  // lcol[i] == 0 for lanes >= i
+      }
+      xs[j] = bj;
+    }
+    __syncthreads();
+    if (tid < c0) {
+      const int rows = (w - c0 < 32) ? (w - c0) : 32;
+      double s0 = 0.0, s1 = 0.0;
+      int i = 0;
+      for (; i + 2 <= rows; i += 2) {
+        s0 = fma(Lb[(int64_t)(c0 + i) * ld + tid], xs[c0 + i], s0);
+        s1 = fma(Lb[(int64_t)(c0 + i + 1) * ld + tid], xs[c0 + i + 1], s1);
+      }
+      if (i < rows) s0 = fma(Lb[(int64_t)(c0 + i) * ld + tid], xs[c0 + i], s0);
+      bj -= (s0 + s1);
+    }
+    __syncthreads();
+  }
+  if (tid < w) b[k0 + tid] = bj;
+}
+
+// backward update: b[j] -= sum_{r in [k0,k0+w)} L[r][j] x[r] for j < k0.  Thread per column j.
+__global__ void __launch_bounds__(256)
+trsv_update_bwd_kernel(const double* __restrict__ L, int64_t ld, int64_t k0, int w, double* __restrict__ b) {
+  __shared__ double xs[TV];
+  const int tid = threadIdx.x;
+  if (tid < TV) xs[tid] = (tid < w) ? b[k0 + tid] : 0.0;
+  __syncthreads();
+  const int64_t j = (int64_t)blockIdx.x * 256 + tid;
+  if (j >= k0) return;
+  const double* col = L + k0 * ld + j;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int r = 0;
+  for (; r + 4 <= w; r += 4) {
+    s0 = fma(col[(int64_t)(r + 0) * ld], xs[r + 0], s0);
+    s1 = fma(col[(int64_t)(r + 1) * ld], xs[r + 1], s1);
+    s2 = fma(col[(int64_t)(r + 2) * ld], xs[r + 2], s2);
+    s3 = fma(col[(int64_t)(r + 3) * ld], xs[r + 3], s3);
+  }
+  for (; r < w; ++r) s0 = fma(col[(int64_t)r * ld], xs[r], s0);
+  b[j] -= (s0 + s1) + (s2 + s3);
+}
+
+static int trsv_forward(const double* L, int64_t N, int64_t ld, double* b, cudaStream_t st) {
+  for (int64_t k0 = 0; k0 < N; k0 += TV) {
+    const int w = (int)((N - k0 < TV) ? (N - k0) : TV);
+    trsv_diag_fwd_kernel<<<1, TV, 0, st>>>(L, ld, k0, w, b);
+    TGP_LAUNCH_CHECK();
+    const int64_t rest = N - k0 - w;
+    if (rest > 0) {
+      trsv_update_fwd_kernel<<<(unsigned)tgp_cdiv(rest, 8), 256, 0, st>>>(L, ld, N, k0, w, b);
+      TGP_LAUNCH_CHECK();
+    }
+  }
+  return TGP_OK;
+}
+
+static int trsv_backward(const double* L, int64_t N, int64_t ld, double* b, cudaStream_t st) {
+  const int64_t nblk = tgp_cdiv(N, TV);
+  for (int64_t kb = nblk - 1; kb >= 0; --kb) {
+    const int64_t k0 = kb * TV;
+    const int w = (int)((N - k0 < TV) ? (N - k0) : TV);
+    trsv_diag_bwd_kernel<<<1, TV, 0, st>>>(L, ld, k0, w, b);
+    TGP_LAUNCH_CHECK();
+    if (k0 > 0) {
+      trsv_update_bwd_kernel<<<(unsigned)tgp_cdiv(k0, 256), 256, 0, st>>>(L, ld, k0, w, b);
+      TGP_LAUNCH_CHECK();
+    }
+  }
+  return TGP_OK;
+}
+
+extern "C" int tgp_potrs_vec(const double* L, int64_t N, int64_t ld, double* b, void* stream) {
+  TGP_CHECK_ARG(N >= 0 && ld >= N, "N/ld");
+  if (N == 0) return TGP_OK;
+  TGP_CHECK_ARG(L && b, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = trsv_forward(L, N, ld, b, st);
+  if (rc) return rc;
+  return trsv_backward(L, N, ld, b, st);
+}
+
+// ============================================================================================
+// Reductions: log-determinant, chi2 = y . alpha, final log-likelihood.
+// ============================================================================================
+// out[0] = sum 2 log L_ii ; out[1] = y . alpha (if given).  Single CTA, deterministic order.
+__global__ void __launch_bounds__(1024)
+logdet_chi2_kernel(const double* __restrict__ L, int64_t N, int64_t ld, const double* __restrict__ y,
+                   const double* __restrict__ alpha, double* __restrict__ out) {
+  __shared__ double s0[32], s1[32];
+  double a = 0.0, c = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+    a += 2.0 * log(L[i * ld + i]);
+    if (y) c = fma(y[i], alpha[i], c);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    c += __shfl_xor_sync(0xffffffffu, c, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s0[warp] = a; s1[warp] = c; }
+  __syncthreads();
+  if (warp == 0) {
+    a = s0[lane];
+    c = s1[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) {
+      out[0] = a;
+      if (y) out[1] = c;
+    }
+  }
+}
+
+extern "C" int tgp_logdet_chi2(const double* L, int64_t N, int64_t ld, const double* y, const double* alpha,
+                               double* out, void* stream) {
+  TGP_CHECK_ARG(N >= 0 && ld >= N && out, "N/ld/out");
+  TGP_CHECK_ARG((y == nullptr) == (alpha == nullptr), "y and alpha go together");
+  logdet_chi2_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(L, N, ld, y, alpha, out);
+  TGP_LAUNCH_CHECK();
+  return TGP_OK;
+}
+
+// out = {logL, chi2, logdet}; tmp = {logdet, chi2}.
+__global__ void loglike_finish_kernel(const double* tmp, int64_t N, const int32_t* __restrict__ info, double* out) {
+  const double logdet = tmp[0], chi2 = tmp[1];
+  double ll = -0.5 * chi2 - 0.5 * (double)N * log(2.0 * TGP_PI) - 0.5 * logdet;
+  if (*info != 0 || isnan(ll)) ll = -INFINITY;
+  out[0] = ll;
+  out[1] = chi2;
+  out[2] = logdet;
+}
+
+// chi2 = ||w||^2 with w = L^-1 y (forward sweep only) -- y^T K^-1 y without the backward solve.
+__global__ void __launch_bounds__(1024)
+sumsq_kernel(const double* __restrict__ w, int64_t N, double* __restrict__ out1) {
+  __shared__ double s0[32];
+  double a = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += blockDim.x) a = fma(w[i], w[i], a);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s0[warp] = a;
+  __syncthreads();
+  if (warp == 0) {
+    a = s0[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) *out1 = a;
+  }
+}
+
+extern "C" int tgp_loglike(const double* X, const double* y, const double* yerr2, int64_t N,
+                           const tgp_kernel* k, double* work, int64_t ld, double* alpha, int want_alpha,
+                           double* out, int32_t* info, void* stream) {
+  TGP_CHECK_ARG(N > 0 && X && y && work && alpha && out && info, "null pointer / N");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = tgp_kmat_sym(X, N, k, yerr2, work, ld, /*lower_only=*/1, stream);
+  if (rc) return rc;
+  rc = tgp_potrf(work, N, ld, info, stream);
+  if (rc) return rc;
+  TGP_CUDA(cudaMemcpyAsync(alpha, y, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  // out[1], out[2] double as scratch {logdet, chi2} until the finishing kernel reorders them
+  double* tmp = out + 1;
+  if (want_alpha) {
+    rc = tgp_potrs_vec(work, N, ld, alpha, stream);
+    if (rc) return rc;
+    logdet_chi2_kernel<<<1, 1024, 0, st>>>(work, N, ld, y, alpha, tmp);  // chi2 = y . alpha
+    TGP_LAUNCH_CHECK();
+  } else {
+    // y^T K^-1 y = ||L^-1 y||^2: the backward sweep is not needed for the likelihood alone
+    rc = trsv_forward(work, N, ld, alpha, st);
+    if (rc) return rc;
+    logdet_chi2_kernel<<<1, 1024, 0, st>>>(work, N, ld, nullptr, nullptr, tmp);
+    TGP_LAUNCH_CHECK();
+    sumsq_kernel<<<1, 1024, 0, st>>>(alpha, N, tmp + 1);
+    TGP_LAUNCH_CHECK();
+  }
+  loglike_finish_kernel<<<1, 1, 0, st>>>(tmp, N, info, out);
+  TGP_LAUNCH_CHECK();
+  return TGP_OK;
+}

@@ -1,0 +1,128 @@
+// GP prediction: fused, never-materialised K(Xs, X) . alpha, and the diagonal predictive variance.
+//
+// Replaces /root/reference/treegp/gp_interp.py:177 + :183 (HT = kernel(X2, Y=X1); HT . alpha) and the
+// diagonal of :187-191 (v = cho_solve(L, HT^T); K** - HT v).  The reference materialises the M x N
+// matrix HT (320 GB at M = 1e6, N = 4e4); here each thread owns one test point, the training
+// coordinates and alpha stream through shared memory, and only M doubles are written.
+#include "tgp_common.cuh"
+
+constexpr int PM_THREADS = 256;   // test points per CTA
+constexpr int PM_TILE = 1024;     // training points per shared-memory tile
+
+// grid: (ceil(M / PM_THREADS), nsplit).  Split s handles training tiles s, s + nsplit, ...
+// nsplit == 1 writes mean directly; otherwise partial sums are added with red.global.add.f64 into a
+// zeroed output (used only when M alone cannot fill the machine).
+template <int FAM>
+__global__ void __launch_bounds__(PM_THREADS)
+predict_mean_kernel(const double* __restrict__ Xs, int64_t M, const double* __restrict__ X, int64_t N,
+                    KDesc kd, const double* __restrict__ alpha, double* __restrict__ mean,
+                    const double* __restrict__ phi_g) {
+  __shared__ double2 pxy[PM_TILE];
+  __shared__ double pa[PM_TILE];
+  __shared__ double phi_s[FAM == TGP_FAM_VONKARMAN ? TGP_VK_PHI_SIZE : 1];
+  const int tid = threadIdx.x;
+  if (FAM == TGP_FAM_VONKARMAN) tgp_stage_phi(phi_s, phi_g);
+  const int64_t m = (int64_t)blockIdx.x * PM_THREADS + tid;
+  const bool live = m < M;
+  const double sx = live ? Xs[m * kd.ndim] : 0.0;
+  const double sy = (live && kd.ndim == 2) ? Xs[m * 2 + 1] : 0.0;
+  const int nsplit = gridDim.y;
+  const int64_t ntile = (N + PM_TILE - 1) / PM_TILE;
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int64_t tl = blockIdx.y; tl < ntile; tl += nsplit) {
+    const int64_t n0 = tl * PM_TILE;
+    __syncthreads();
+    for (int i = tid; i < PM_TILE; i += PM_THREADS) {
+      const int64_t n = n0 + i;
+      const bool ok = n < N;
+      double2 p;
+      p.x = ok ? X[n * kd.ndim] : 0.0;
+      p.y = (ok && kd.ndim == 2) ? X[n * 2 + 1] : 0.0;
+      pxy[i] = p;
+      pa[i] = ok ? kd.amp * alpha[n] : 0.0;  // padded points carry zero weight
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int i = 0; i < PM_TILE; i += 2) {
+      const double2 p0 = pxy[i], p1 = pxy[i + 1];
+      const double q0 = tgp_qform(kd, sx - p0.x, sy - p0.y);
+      const double q1 = tgp_qform(kd, sx - p1.x, sy - p1.y);
+      acc0 = fma(tgp_profile<FAM>(q0, phi_s), pa[i], acc0);
+      acc1 = fma(tgp_profile<FAM>(q1, phi_s), pa[i + 1], acc1);
+    }
+  }
+  if (live) {
+    const double v = acc0 + acc1;
+    if (nsplit == 1) mean[m] = v;
+    else atomicAdd(mean + m, v);
+  }
+}
+
+extern "C" int tgp_predict_mean(const double* Xs, int64_t M, const double* X, int64_t N,
+                                const tgp_kernel* k, const double* alpha, double* mean, void* stream) {
+  TGP_CHECK_ARG(kdesc_ok(k), "kernel descriptor");
+  TGP_CHECK_ARG(M >= 0 && N >= 0, "M/N");
+  if (M == 0) return TGP_OK;
+  TGP_CHECK_ARG(Xs && mean && (N == 0 || (X && alpha)), "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const KDesc kd = make_kdesc(k);
+  const int64_t gx = tgp_cdiv(M, PM_THREADS);
+  const int64_t ntile = tgp_cdiv(N, PM_TILE);
+  int64_t nsplit = 1;
+  const int64_t target = 4ll * tgp_num_sms();
+  if (gx < target) nsplit = tgp_cdiv(target, gx);
+  if (nsplit > ntile) nsplit = ntile > 0 ? ntile : 1;
+  if (nsplit > 65535) nsplit = 65535;
+  if (nsplit > 1 || N == 0) TGP_CUDA(cudaMemsetAsync(mean, 0, M * sizeof(double), st));
+  if (N == 0) return TGP_OK;
+  dim3 grid((unsigned)gx, (unsigned)nsplit);
+  const double* phi = tgp_phi_device();
+  TGP_FAMILY_SWITCH(k->family, (predict_mean_kernel<FAM><<<grid, PM_THREADS, 0, st>>>(Xs, M, X, N, kd, alpha,
+                                                                                     mean, phi)));
+  TGP_LAUNCH_CHECK();
+  return TGP_OK;
+}
+
+// var[m] = amp - sum_n V[m][n]^2, V = K(Xs, X) L^-T (row m = L^-1 k*_m).  Warp per row.
+__global__ void __launch_bounds__(256)
+var_from_rows_kernel(const double* __restrict__ V, int64_t M, int64_t N, int64_t ldv, double amp,
+                     double* __restrict__ var) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  const double* row = V + m * ldv;
+  double s0 = 0.0, s1 = 0.0;
+  int64_t n = lane;
+  for (; n + 32 < N; n += 64) {
+    const double a = row[n], b = row[n + 32];
+    s0 = fma(a, a, s0);
+    s1 = fma(b, b, s1);
+  }
+  if (n < N) { const double a = row[n]; s0 = fma(a, a, s0); }
+  double s = s0 + s1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) var[m] = amp - s;
+}
+
+extern "C" int tgp_predict_var(const double* Xs, int64_t M, const double* X, int64_t N,
+                               const tgp_kernel* k, const double* L, int64_t ld, double* work,
+                               int64_t chunk, double* var, void* stream) {
+  TGP_CHECK_ARG(kdesc_ok(k), "kernel descriptor");
+  TGP_CHECK_ARG(M >= 0 && N > 0 && ld >= N && chunk > 0, "shape");
+  if (M == 0) return TGP_OK;
+  TGP_CHECK_ARG(Xs && X && L && work && var, "null pointer");
+  const int64_t ldw = (N + 1) & ~1ll;  // even row pitch for the DMMA operand loads
+  TGP_CHECK_ARG(((uintptr_t)work % 16) == 0, "work must be 16-byte aligned");
+  for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+    const int64_t mc = (M - m0 < chunk) ? (M - m0) : chunk;
+    int rc = tgp_kmat_cross(Xs + m0 * k->ndim, mc, X, N, k, work, ldw, stream);
+    if (rc) return rc;
+    rc = tgp_trsm_rows(L, N, ld, work, mc, ldw, stream);
+    if (rc) return rc;
+    var_from_rows_kernel<<<(unsigned)tgp_cdiv(mc, 8), 256, 0, (cudaStream_t)stream>>>(work, mc, N, ldw, k->amp,
+                                                                                      var + m0);
+    TGP_LAUNCH_CHECK();
+  }
+  return TGP_OK;
+}
