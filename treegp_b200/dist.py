@@ -1,0 +1,51 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink on the GPU box,
+gloo in the CPU test-suite).
+
+Only two pieces of the hot path shard:
+* pair binning -- every rank holds all points, runs of pair tiles are dealt round-robin by
+  ``tgp_pairbin(tile_rank, tile_nranks)`` and the bin sums are combined by ONE all-reduce
+  (a few KB to ~1 MB): counts are integers, so the result is bit-exact for any number of GPUs;
+* predict -- test points are split into contiguous slabs, X / alpha (/ L) are replicated, no data-path
+  collective; results are gathered.
+The Cholesky itself does not shard at these sizes (12.8 GB at N = 40k fits one GPU): replicas only.
+"""
+import numpy as np
+import torch
+import torch.distributed as tdist
+
+
+def rank_world(group=None):
+    """(rank, world) of `group`; (0, 1) when torch.distributed is not initialised and no group given."""
+    if group is None and not (tdist.is_available() and tdist.is_initialized()):
+        return 0, 1
+    if group is False:  # explicit single-process
+        return 0, 1
+    return tdist.get_rank(group), tdist.get_world_size(group)
+
+
+def allreduce_bins(group, *tensors):
+    """Sum the per-rank bin arrays in place (one collective per array, tiny messages)."""
+    for t in tensors:
+        if t is not None:
+            tdist.all_reduce(t, op=tdist.ReduceOp.SUM, group=group if group not in (None, False) else None)
+
+
+def slab(n, rank, world):
+    """Contiguous [begin, end) share of n items for `rank`; sizes differ by at most one."""
+    base, extra = divmod(int(n), int(world))
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+def gather_slabs(local, n, group=None):
+    """All-gather the per-rank slabs of a length-n device vector back into one vector on every rank."""
+    rank, world = rank_world(group)
+    if world == 1:
+        return local
+    sizes = [slab(n, r, world)[1] - slab(n, r, world)[0] for r in range(world)]
+    pad = max(sizes)
+    buf = torch.zeros(pad, dtype=local.dtype, device=local.device)
+    buf[: local.numel()] = local
+    outs = [torch.empty_like(buf) for _ in range(world)]
+    tdist.all_gather(outs, buf, group=group if group not in (None, False) else None)
+    return torch.cat([o[:s] for o, s in zip(outs, sizes)])

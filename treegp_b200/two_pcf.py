@@ -1,0 +1,429 @@
+"""Hyper-parameter estimation from the 2-point correlation function, pair-binned on the B200.
+
+Host-side mirror of /root/reference/treegp/two_pcf.py: ``get_correlation_length_matrix`` (:12-31),
+``get_kernel_class`` (:34-65), ``robust_2dfit`` (:68-206) and ``two_pcf`` (:209-464) keep their names,
+signatures and the attributes the reference's tests read (``_2pcf``, ``_2pcf_weight``, ``_2pcf_dist``,
+``_2pcf_fit``, ``_2pcf_mask``, ``_kernel``, ``_results_robust``).
+
+What changed:
+* ``comp_2pcf`` -- the TreeCorr ``KKCorrelation.process`` call (:297-305, :330-334) is the
+  brute-force pair-binning kernel of csrc/pairbin.cu behind ``tgp_pairbin``;
+* ``comp_xi_covariance`` -- the loop of ``n_bootstrap`` sequential TreeCorr runs (:342-362) is ONE
+  batched launch over all resampled catalogues.  A resample with replacement is the same catalogue
+  with integer multiplicities m_i: coincident copies are at r = 0 and never pair (TreeCorr skips
+  rsq == 0), copies of i and j contribute m_i m_j w_i w_j, so each distinct drawn point enters once
+  with weight m_i w_i.  Index generation stays on the host with numpy so that the reference's stream
+  (``default_rng(seed).integers(0, N-1, N)``: index N-1 is never drawn, :275) is reproduced;
+* the Minuit minimiser of the robust fit is the in-repo variable-metric ``migrad`` (iminuit is not
+  part of this image); the chi-square machinery around it is unchanged.
+"""
+from __future__ import print_function
+
+import copy
+import warnings
+
+import numpy as np
+import sklearn
+import torch
+from scipy import optimize
+
+from . import _cabi, backend, binning, kernels
+from .migrad import Migrad
+
+
+def get_correlation_length_matrix(size, e1, e2):
+    """
+    Produce correlation matrix to introduce anisotropy in kernel (weak-lensing shear
+    parameterisation: an anisotropic kernel has an elliptical shape).
+
+    :param size:   Correlation lenght of the kernel.
+    :param e1, e2: Shear applied to isotropic kernel.
+    """
+    if abs(e1) > 1 or abs(e2) > 1:
+        raise ValueError("abs value of e1 and e2 must be lower than one")
+    e = np.sqrt(e1 ** 2 + e2 ** 2)
+    q = (1 - e) / (1 + e)
+    phi = 0.5 * np.arctan2(e2, e1)
+    c, s = np.cos(phi), np.sin(phi)
+    rot = np.array([[c, s], [-s, c]])
+    ell = np.array([[size ** 2, 0], [0, (size * q) ** 2]])
+    return np.dot(rot.T, ell.dot(rot))
+
+
+_ANISOTROPIC = (kernels.AnisotropicVonKarman, kernels.AnisotropicRBF)
+
+
+def get_kernel_class(A):
+    """
+    Check that the given kernel is an AnisotropicVonKarman or an AnisotropicRBF kernel (possibly
+    inside a Product) and return that class.
+
+    :param A: sklearn.gaussian_process.kernels
+    """
+    msg = "Work only with treegp.kernels.AnisotropicVonKarman and treegp.kernels.AnisotropicRBF"
+    if isinstance(A, sklearn.gaussian_process.kernels.Product):
+        found = [v.__class__ for v in vars(A).values() if v.__class__ in _ANISOTROPIC]
+        if not found:
+            raise ValueError(msg)
+        return found[-1]
+    if A.__class__ in _ANISOTROPIC:
+        return A.__class__
+    raise ValueError(msg)
+
+
+class robust_2dfit(object):
+    """
+    Fit hyperparameters on 2D two-point correlation when the analytical profil can
+    be discribed as a Radial Basis Function such as a Gaussian kernel or a
+    von Karman kernel.
+
+    :param kernel:    sklearn.gaussian_process.kernels
+    :param x:         x coordinates of the 2D two point correlation function.
+    :param y:         y coordinates of the 2D two point correlation function.
+    :param flat_data: flatten 2D two point correlation function.
+    :param W:         Inverse of the covariance matrix got from Bootstrap.
+    :param mask:      Mask symetric area for Radial basi Function.
+    """
+
+    def __init__(self, kernel, flat_data, x, y, W, mask=None):
+        self.mask = np.ones(len(x), dtype=bool) if mask is None else mask
+        self.kernel_class = get_kernel_class(kernel)
+        self.flat_data = flat_data
+        self.x = x
+        self.y = y
+        self.coord = np.array([x, y]).T
+        self.W = W
+        self.N = int(np.sqrt(len(self.x)))
+        self._origin = np.zeros((1, 2))
+
+    def _model_skl(self, sigma, corr_length, g1, g2):
+        """
+        Analytical two point correlation function of the kernel at the bin lags
+        (two_pcf.py:96-113); None outside |g| <= 1.
+        """
+        if abs(g1) > 1 or abs(g2) > 1:
+            return None
+        invLam = np.linalg.inv(get_correlation_length_matrix(corr_length, g1, g2))
+        kernel_used = sigma ** 2 * self.kernel_class(invLam=invLam)
+        # the reference evaluates the P x P matrix against P zero points and keeps column 0
+        # (two_pcf.py:111); one zero point gives the same column
+        pcf = kernel_used(self.coord, Y=self._origin)[:, 0]
+        self.kernel_fit = kernel_used
+        return pcf
+
+    def chi2(self, param):
+        """
+        Chi2 over the non-linear parameters (correlation length, e1, e2); the amplitude and the
+        constant offset are linear and solved analytically at every call (two_pcf.py:115-148).
+        """
+        if not np.isfinite(np.sum(param)):
+            self.chi2_value = [np.inf]
+            return np.inf
+        model = self._model_skl(1.0, param[0], param[1], param[2])
+        if model is None:
+            self.chi2_value = [np.inf]
+            return np.inf
+        model = model[self.mask]
+        F = np.array([model, np.ones_like(model)]).T
+        FtW = np.dot(F.T, self.W)
+        Y = self.flat_data[self.mask].reshape((len(model), 1))
+        self.alpha = np.linalg.inv(FtW.dot(F)).dot(FtW.dot(Y))
+        self.alpha[0] = abs(self.alpha[0])
+        self.residuals = self.flat_data[self.mask] - ((self.alpha[0] * model) + self.alpha[1])
+        self.chi2_value = self.residuals.dot(self.W).dot(self.residuals.reshape((len(model), 1)))
+        return self.chi2_value[0]
+
+    def _minimize_minuit(self, p0=[3000.0, 0.2, 0.2]):
+        """
+        Launch a single variable-metric (MIGRAD) minimization from a starting point.
+
+        :param p0: List of starting points.
+        """
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.m = Migrad(self.chi2, p0)
+            self.m.migrad()
+            results = list(self.m.values)
+            self._fit_ok = self.m.accurate
+        # leave alpha / kernel_fit consistent with the returned point
+        self.chi2(results)
+        self._minuit_result = results
+        self.result = [np.sqrt(self.alpha[0][0]), results[0], results[1], results[2], self.alpha[1][0]]
+
+    def minimize_minuit(self, p0=[3000.0, 0.2, 0.2]):
+        """
+        Launch the minimization given a starting point; restart on a 3x3x3 grid of starting points
+        if the minimiser did not converge (two_pcf.py:178-206).
+
+        :param p0: List of starting points.
+        """
+        self._minimize_minuit(p0=p0)
+
+        if not self._fit_ok:
+            n = 3
+            g = np.linspace(-0.3, 0.3, n)
+            size = np.linspace(p0[0] - p0[0] / 10.0, 2 * p0[0], n)
+            g1, g2, size = np.meshgrid(g, g, size)
+            for s_, a_, b_ in zip(size.ravel(), g1.ravel(), g2.ravel()):
+                print("restart fit because failure")
+                new_p0 = [s_, a_, b_]
+                print(new_p0)
+                self._minimize_minuit(p0=new_p0)
+                if self._fit_ok:
+                    break
+        _ = self._model_skl(self.result[0], self.result[1], self.result[2], self.result[3])
+
+
+class two_pcf(object):
+    """
+    Fit statistical uncertaintie on two-point correlation function using bootstraping.
+
+    :param X:           Coordinates of the field.  (n_samples, 1 or 2)
+    :param y:           Values of the field. (n_samples)
+    :param y_err:       Error of y. (n_samples)
+    :param min_sep:     Minimum bin separation. (float)
+    :param max_sep:     Maximum bin separation. (float)
+    :param nbins:       Number of bins (1D) or square root of the number of bins (2D). [default: 20]
+    :param anisotropic: 2D 2-point correlation function (Boolean)
+    :param robust_fit:  Used the variable-metric robust fit; only if anisotropic is True. (Boolean)
+    :param p0:          Starting point of the robust fit.
+    :param seed:        Seed to use for random number generator.
+    """
+
+    def __init__(
+        self,
+        X,
+        y,
+        y_err,
+        min_sep,
+        max_sep,
+        nbins=20,
+        anisotropic=False,
+        robust_fit=False,
+        p0=[3000.0, 0.0, 0.0],
+        seed=610639139,
+    ):
+        self.ndim = np.shape(X)[1]
+        if self.ndim not in [1, 2]:
+            raise ValueError(
+                "two-pcf support only 1d and 2d modeling for the moment. curent ndim: %i" % (self.ndim)
+            )
+        if self.ndim == 2:
+            self.X = X
+        else:  # embed a 1-D field as (x, 0)                                  two_pcf.py:250-251
+            self.X = np.column_stack([np.asarray(X)[:, 0], np.zeros(len(X))])
+        self.y = y
+        self.y_err = y_err
+        self.min_sep = min_sep
+        self.max_sep = max_sep
+        self.nbins = nbins
+        self.anisotropic = anisotropic
+        self.robust_fit = robust_fit
+        self.p0_robust_fit = p0
+        self.seed = seed
+        self._rng = None
+        # multi-GPU: pair tiles are dealt to `world` ranks and the bin sums all-reduced (dist.py)
+        self.group = None
+
+    @property
+    def rng(self):
+        if self._rng is None:
+            self._rng = np.random.default_rng(self.seed)
+        return self._rng
+
+    def resample_bootstrap(self):
+        """
+        Make a single bootstrap resampling on data (two_pcf.py:269-281).
+        """
+        npsfs = len(self.y)
+        ind_object = self.rng.integers(0, npsfs - 1, size=npsfs)
+        return (self.X[:, 0][ind_object], self.X[:, 1][ind_object], self.y[ind_object],
+                self.y_err[ind_object])
+
+    # ---- device pair binning ------------------------------------------------------------------
+    def _bin_geometry(self):
+        if self.anisotropic:
+            edges = binning.twod_thresholds(self.max_sep, self.nbins)
+            return _cabi.BIN_TWOD, edges
+        return _cabi.BIN_LOG, binning.log_thresholds(self.min_sep, self.max_sep, self.nbins)
+
+    def _pairbin(self, px, py, pk, pw, offsets, max_len):
+        """Launch tgp_pairbin on (possibly many) catalogues and return xi (ncat, nb) and meanr|None
+        as numpy arrays.  With a process group the pair tiles are sharded and the sums all-reduced."""
+        from . import dist
+
+        bt, edges = self._bin_geometry()
+        rank, world = dist.rank_world(self.group)
+        npairs, sumw, sumwkk, sumwr = backend.pairbin(
+            px, py, pk, pw, offsets, max_len, bt, backend.to_device(edges), self.nbins,
+            self.min_sep, self.max_sep, rank=rank, nranks=world)
+        if world > 1:
+            dist.allreduce_bins(self.group, npairs, sumw, sumwkk, sumwr)
+        sw = sumw.cpu().numpy()
+        with np.errstate(invalid="ignore", divide="ignore"):
+            xi = np.where(sw != 0, sumwkk.cpu().numpy() / sw, 0.0)
+            meanr = None
+            if sumwr is not None:
+                # TreeCorr reports the nominal bin centre exp(ln min_sep + (k + 1/2) bin_size) where a bin is empty
+                bs = np.log(self.max_sep / self.min_sep) / self.nbins
+                rnom = np.exp(np.log(self.min_sep) + (np.arange(self.nbins) + 0.5) * bs)
+                meanr = np.where(sw != 0, sumwr.cpu().numpy() / sw, rnom[None, :])
+        self._last_npairs = npairs.cpu().numpy()
+        return xi, meanr
+
+    def _assemble(self, xi, meanr):
+        if self.anisotropic:
+            mask = binning.twod_mask(self.nbins)
+            coord = binning.twod_coords(self.nbins, self.max_sep)
+            return xi, coord, coord, mask
+        distance = meanr
+        coord = np.array([distance, np.zeros_like(distance)]).T
+        return xi, distance, coord, np.ones_like(xi, dtype=bool)
+
+    def comp_2pcf(self, X, y, y_err):
+        """
+        Estimate 2-point correlation function (two_pcf.py:283-340).
+
+        :param X:  Coordinates of the field. (n_samples, 2)
+        :param y:  Values of the field. (n_samples)
+        :param y_err: Error of y. (n_samples)
+        """
+        X = np.asarray(X, dtype=np.float64)
+        y = np.asarray(y, dtype=np.float64)
+        y_err = np.asarray(y_err, dtype=np.float64)
+        pw = None if np.sum(y_err) == 0 else backend.to_device(1.0 / y_err ** 2)
+        n = len(y)
+        xi, meanr = self._pairbin(
+            backend.to_device(X[:, 0]), backend.to_device(X[:, 1]), backend.to_device(y - np.mean(y)), pw,
+            backend.to_device(np.array([0, n]), torch.int64), n)
+        return self._assemble(xi[0], None if meanr is None else meanr[0])
+
+    def comp_xi_covariance(self, n_bootstrap=1000, mask=None, seed=610639139):
+        """
+        Estimate 2-point correlation function covariance matrix using Bootstrap
+        (two_pcf.py:342-362), all resamples in one batched launch.
+
+        :param seed: seed of the random generator.
+        """
+        self.seed = seed
+        self._rng = None
+        xi_bootstrap = self._bootstrap_xi(int(n_bootstrap))
+        if mask is None:
+            mask = np.ones(xi_bootstrap.shape[1], dtype=bool)
+        xi_bootstrap = xi_bootstrap[:, mask]
+        dxi = xi_bootstrap - np.mean(xi_bootstrap, axis=0)
+        return 1.0 / (len(dxi) - 1.0) * np.dot(dxi.T, dxi)
+
+    def _bootstrap_xi(self, n_bootstrap, batch_points=1 << 26):
+        """xi of `n_bootstrap` resamples, shape (n_bootstrap, nb)."""
+        n = len(self.y)
+        dev = backend.require_cuda()
+        x = backend.to_device(np.asarray(self.X[:, 0], dtype=np.float64))
+        yy = backend.to_device(np.asarray(self.X[:, 1], dtype=np.float64))
+        val = backend.to_device(np.asarray(self.y, dtype=np.float64))
+        err = np.asarray(self.y_err, dtype=np.float64)
+        err_d = backend.to_device(err)
+        out = []
+        per_batch = max(1, int(batch_points // max(n, 1)))
+        done = 0
+        while done < n_bootstrap:
+            b = min(per_batch, n_bootstrap - done)
+            # same stream of draws as `b` successive resample_bootstrap() calls
+            idx = np.stack([self.rng.integers(0, n - 1, size=n) for _ in range(b)])
+            idx_d = torch.as_tensor(idx, device=dev)
+            mult = torch.zeros((b, n), dtype=torch.float64, device=dev)
+            mult.scatter_add_(1, idx_d, torch.ones_like(idx_d, dtype=torch.float64))
+            ybar = (mult * val).sum(dim=1) / n                      # mean of the resampled values
+            # weights: None in the reference iff the resampled errors sum to 0 (two_pcf.py:291-294)
+            esum = (mult * err_d).sum(dim=1)
+            w_all = torch.where(err_d > 0, 1.0 / (err_d * err_d), torch.zeros_like(err_d))
+            rows, cols = torch.nonzero(mult > 0, as_tuple=True)      # row-major: catalogues are contiguous
+            lens = (mult > 0).sum(dim=1)
+            offsets = torch.zeros(b + 1, dtype=torch.int64, device=dev)
+            offsets[1:] = torch.cumsum(lens, 0)
+            m = mult[rows, cols]
+            unit = (esum == 0)[rows]
+            pw = torch.where(unit, m, m * w_all[cols])
+            pk = val[cols] - ybar[rows]
+            xi, _ = self._pairbin(x[cols].contiguous(), yy[cols].contiguous(), pk.contiguous(), pw.contiguous(),
+                                  offsets, int(lens.max().item()))
+            out.append(xi)
+            done += b
+        return np.concatenate(out, axis=0)
+
+    def return_2pcf(self, seed=610639139):
+        """
+        Return 2-point correlation function and its variance using Bootstrap (two_pcf.py:364-391).
+
+        :param seed: seed of the random generator.
+        """
+        xi, distance, coord, mask = self.comp_2pcf(self.X, self.y, self.y_err)
+        if self.anisotropic:
+            # number of resamples from Taylor et al. 2012 (https://doi.org/10.1093/mnras/stt270) eq. 35:
+            # the resample count at which the de-biasing factor of the inverse covariance equals 2
+            npixel = len(xi[mask])
+
+            def f_bias(x):
+                return (x - 1.0) / (x - npixel - 2.0) - 2.0
+
+            n_bootstrap = int(optimize.fsolve(f_bias, npixel + 10)[0])
+            xi_cov = self.comp_xi_covariance(n_bootstrap=n_bootstrap, mask=mask, seed=seed)
+            bias_factor = (n_bootstrap - 1.0) / (n_bootstrap - npixel - 2.0)
+            xi_weight = np.linalg.inv(xi_cov) * bias_factor
+        else:
+            xi_weight = np.eye(len(xi)) * 1.0 / np.var(self.y)
+        return xi, xi_weight, distance, coord, mask
+
+    def optimizer(self, kernel):
+        """
+        Fit hyperparameter using two-point correlation function (two_pcf.py:393-464).
+
+        :param kernel: sklearn.gaussian_process kernel.
+        """
+        size_x = np.max(self.X[:, 0]) - np.min(self.X[:, 0])
+        if self.ndim == 2:
+            size_y = np.max(self.X[:, 1]) - np.min(self.X[:, 1])
+            rho = float(len(self.X[:, 0])) / (size_x * size_y)
+        else:
+            size_y = 0.0
+            rho = float(len(self.X[:, 0])) / size_x
+        # defaults: min_sep = mean inter-point distance (isotropic) or 0 (anisotropic);
+        # max_sep = half of the field diagonal
+        if self.min_sep is None:
+            self.min_sep = 0.0 if self.anisotropic else np.sqrt(1.0 / rho)
+        if self.max_sep is None:
+            self.max_sep = np.sqrt(size_x ** 2 + size_y ** 2) / 2.0
+
+        xi, xi_weight, distance, coord, mask = self.return_2pcf()
+        origin = np.zeros((1, 2))
+
+        def PCF(param, k=kernel):
+            return k.clone_with_theta(param)(coord, Y=origin)[:, 0]
+
+        xi_mask = xi[mask]
+
+        def chi2(param):
+            residual = xi_mask - PCF(param)[mask]
+            return residual.dot(xi_weight.dot(residual))
+
+        if self.robust_fit:
+            robust = robust_2dfit(kernel, xi, coord[:, 0], coord[:, 1], xi_weight, mask=mask)
+            robust.minimize_minuit(p0=self.p0_robust_fit)
+            kernel = copy.deepcopy(robust.kernel_fit)
+            cst = robust.result[-1]
+            self._results_robust = robust.result
+        else:
+            p0 = kernel.theta
+            candidates = [optimize.fmin(chi2, p0, disp=False),
+                          optimize.minimize(chi2, p0, method="L-BFGS-B")["x"]]
+            values = [chi2(c) for c in candidates]
+            kernel = kernel.clone_with_theta(candidates[values.index(min(values))])
+            cst = 0
+
+        self._2pcf = xi
+        self._2pcf_weight = xi_weight
+        self._2pcf_dist = distance
+        self._2pcf_fit = PCF(kernel.theta) + cst
+        self._2pcf_mask = mask
+        self._kernel = copy.deepcopy(kernel)
+        return kernel
