@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the treegp_b200 hot path.
+
+BASELINE.json metric: "GP fit+predict wall-s at N=40k; 2PCF pairs/s at 1/2/4/8 B200".
+
+One JSON line is printed (rank 0).  Its primary metric is the one that is defined at 1/2/4/8 GPUs:
+
+  metric  = "2pcf_pairs_per_s": unordered pairs binned per second by the anisotropic TwoD pair-binning
+            kernel on N = 1,000,000 synthetic points (configs[3]; nbins = 21, min_sep = 0, max_sep = the
+            reference default: half the field diagonal, two_pcf.py:421 -> 84 % of all pairs land in a bin).
+            A "step" is one complete pair count over all N(N-1)/2 pairs.  With --gpus N the pair tiles are
+            dealt to the ranks and the bin sums all-reduced over NCCL: total work is fixed -> "strong".
+  e2e     = the same count through the reference-facing API, treegp_b200.two_pcf(...).comp_2pcf(X, y,
+            y_err) with HOST numpy inputs (H2D of the points and D2H of xi inside the timed region).
+  gp      = the other half of the BASELINE metric, reported in the same line under "gp_fit_predict":
+            wall seconds of GPInterpolation.initialize + solve(optimizer='anisotropic') + predict(1e6
+            points) for a 2-D AnisotropicVonKarman field with N = 40,000 (configs[2]), with a breakdown
+            and the Cholesky's FP64 tensor-pipe roofline.  Test points are sharded over the ranks.
+
+`--impl reference` times the CPU restatement of the same pair binning (oracle/, OpenMP over all host
+cores; TreeCorr itself is not installable here) on a bounded slab of rows of the same N = 1e6 problem.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--npoints", type=int, default=1_000_000, help="2PCF points (configs[3]: 1e6)")
+    ap.add_argument("--gp-train", type=int, default=40_000, help="GP training points (configs[2]: 40k)")
+    ap.add_argument("--gp-predict", type=int, default=1_000_000)
+    ap.add_argument("--skip-gp", action="store_true", help="only the 2PCF part (used for ncu captures)")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--cpu-rows", type=int, default=1500, help="rows of the pair matrix in the CPU sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs
+# ------------------------------------------------------------------------------------------------
+FIELD_2PCF = 1000.0
+NBINS = 21
+
+
+def make_2pcf_inputs(n, seed=42):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-FIELD_2PCF / 2, FIELD_2PCF / 2, size=(n, 2))
+    y = rng.normal(size=n)  # pair counts and timing do not depend on the field values
+    y_err = np.zeros(n)
+    max_sep = np.sqrt(2.0) * FIELD_2PCF / 2.0  # reference default: half the field diagonal
+    return X, y, y_err, 0.0, max_sep
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                parts = [p.strip() for p in out.stdout.strip().split(",")]
+                if len(parts) >= 7:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm
+# ------------------------------------------------------------------------------------------------
+def cpu_pairbin_sample(X, y, min_sep, max_sep, rows):
+    """Time the oracle (C, OpenMP, all host cores) on rows [0, rows) of the pair matrix."""
+    from oracle import pairbin_oracle as po
+
+    n = len(y)
+    rows = min(rows, n)
+    k = y - np.mean(y)
+    t0 = time.perf_counter()
+    po.pairbin(X[:, 0], X[:, 1], k, None, min_sep, max_sep, NBINS, "TwoD", rows=(0, rows))
+    dt = time.perf_counter() - t0
+    pairs = rows * n - rows * (rows + 1) // 2
+    return pairs / dt, dt, pairs, po.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    X, y, y_err, mn, mx = make_2pcf_inputs(args.npoints)
+    rates = []
+    for i in range(args.warmup + args.steps):
+        rate, dt, pairs, cores = cpu_pairbin_sample(X, y, mn, mx, args.cpu_rows)
+        if i >= args.warmup:
+            rates.append((rate, dt))
+    value = float(np.mean([r for r, _ in rates]))
+    ms = float(np.mean([d for _, d in rates]) * 1e3)
+    sample = "rows [0,%d) of the N=%d pair matrix = %.3g unordered pairs per step" % (args.cpu_rows, args.npoints, pairs)
+    line = {
+        "impl": "reference", "metric": "2pcf_pairs_per_s", "value": value, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "anisotropic TwoD 2PCF pair binning, N=%d, nbins=21, min_sep=0, max_sep=half field "
+                               "diagonal (configs[3])" % args.npoints},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample,
+                         "note": "oracle/pairbin_oracle.c (brute force, OpenMP); TreeCorr is not installable"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as tdist
+
+    import treegp_b200 as treegp
+    from treegp_b200 import _cabi, backend, binning, dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        tdist.init_process_group("nccl", device_id=dev)
+    _cabi.load()
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+        return float(t.item())
+
+    hbm_peak, peak_src = load_peaks()
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    # ---------------- 2PCF: device-resident timing ----------------
+    n = args.npoints
+    X, y, y_err, mn, mx = make_2pcf_inputs(n)
+    npairs_total = n * (n - 1) // 2
+    px, py = backend.to_device(X[:, 0]), backend.to_device(X[:, 1])
+    pk = backend.to_device(y - np.mean(y))
+    off = backend.to_device(np.array([0, n]), torch.int64)
+    edges = backend.to_device(binning.twod_thresholds(mx, NBINS))
+    launches = 0
+
+    def step_device():
+        res = backend.pairbin(px, py, pk, None, off, n, _cabi.BIN_TWOD, edges, NBINS, mn, mx, rank=rank, nranks=world)
+        if world > 1:
+            dist.allreduce_bins(None, res[0], res[1], res[2])
+        return res
+
+    for _ in range(args.warmup):
+        res = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    step_ms, kern_ms = [], []
+    for _ in range(args.steps):
+        flush_buf.fill_(1)
+        barrier()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        res = backend.pairbin(px, py, pk, None, off, n, _cabi.BIN_TWOD, edges, NBINS, mn, mx, rank=rank, nranks=world)
+        e1.record()
+        if world > 1:
+            dist.allreduce_bins(None, res[0], res[1], res[2])
+        e2.record()
+        barrier()
+        step_ms.append(max_over_ranks(e0.elapsed_time(e2)))
+        kern_ms.append(max_over_ranks(e0.elapsed_time(e1)))
+        launches += 1
+    clocks = sampler.stop() if rank == 0 else None
+    counted = int(res[0].sum().item())
+    total_ms = float(np.sum(step_ms))
+    value = npairs_total * args.steps / (total_ms * 1e-3)
+
+    # ---------------- 2PCF: end to end through the public API (host buffers) ----------------
+    Xp = np.ascontiguousarray(X)
+    e2e_ms = []
+    tp = treegp.two_pcf(Xp, y, y_err, mn, mx, nbins=NBINS, anisotropic=True)
+    tp.group = None if world > 1 else False
+    for i in range(1 + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        xi, _, _, _ = tp.comp_2pcf(Xp, y, y_err)
+        torch.cuda.synchronize()
+        dt = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        if i > 0:
+            e2e_ms.append(dt)
+    e2e_value = npairs_total / (float(np.mean(e2e_ms)) * 1e-3)
+    h2d = 3 * 8 * n + 8 * (NBINS + 1) + 16
+    d2h = NBINS * NBINS * (8 + 8 + 8)
+
+    # ---------------- FP64 peaks (roofline denominators), measured live ----------------
+    dfma_tf = backend.microbench_fp64(0, 20000)
+    dmma_tf = backend.microbench_fp64(1, 20000)
+    # algorithmic work per unordered pair: 10 FP64 operations; peak in operations/s is
+    # the measured DFMA rate / 2 (one FMA instruction = 2 flop = 1 operation slot)
+    ops_per_pair = 10.0
+    my_pairs = npairs_total / world
+    ach_gops = ops_per_pair * my_pairs / (float(np.mean(kern_ms)) * 1e-3) / 1e9
+    peak_gops = dfma_tf * 1e3 / 2.0
+    roofline = {"bound": "fp64_alu", "kernel": "pairbin_kernel<TwoD, unweighted>", "achieved": ach_gops,
+                "peak": peak_gops, "unit": "Gop/s (FP64 instructions x lanes)", "frac": ach_gops / peak_gops,
+                "traffic": None,
+                "note": "neither HBM- nor tensor-bound: 24 N bytes in, N^2/2 pair evaluations; peak = measured "
+                        "DFMA issue rate (tgp_microbench_fp64), algorithmic 10 FP64 ops per unordered pair",
+                "dram_GBs_for_reference": 24.0 * n / (float(np.mean(kern_ms)) * 1e-3) / 1e9,
+                "hbm_peak_GBs": hbm_peak, "hbm_peak_source": peak_src}
+
+    line = {
+        "metric": "2pcf_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "anisotropic TwoD 2PCF pair binning, N=%d, nbins=21, min_sep=0, max_sep=half field "
+                               "diagonal (configs[3])" % n,
+                   "pairs_per_step": npairs_total, "pairs_in_range_x2": counted, "sharding": "pair tiles over %d rank(s) + NCCL allreduce of bin sums" % world,
+                   "l2": "256 MB buffer written between timed iterations (L2 flush)"},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "treegp_b200.two_pcf(...).comp_2pcf(X, y, y_err) with host numpy inputs"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "fp64_peaks_measured": {"dfma_tflops": dfma_tf, "dmma_tflops": dmma_tf},
+    }
+
+    # ---------------- GP fit + predict at N = 40k ----------------
+    if not args.skip_gp:
+        line["gp_fit_predict"] = run_gp(args, treegp, backend, dist, rank, world, dev, barrier, max_over_ranks,
+                                        hbm_peak, dmma_tf)
+
+    # ---------------- CPU baseline (rank 0, bounded sample) ----------------
+    if rank == 0 and not args.skip_cpu:
+        rate, dt, pairs, cores = cpu_pairbin_sample(X, y, mn, mx, args.cpu_rows)
+        line["cpu_baseline"] = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
+                                "sample": "rows [0,%d) of the N=%d pair matrix = %.3g unordered pairs, %.1f s"
+                                          % (args.cpu_rows, n, pairs, dt),
+                                "note": "oracle/pairbin_oracle.c (brute force, OpenMP); TreeCorr is not installable"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        tdist.destroy_process_group()
+
+
+def run_gp(args, treegp, backend, dist, rank, world, dev, barrier, max_over_ranks, hbm_peak, dmma_tf):
+    """configs[2]: 2-D AnisotropicVonKarman, N train / M predict, optimizer='anisotropic'."""
+    import torch
+    from treegp_b200.kernels import lower_kernel
+    from treegp_b200.two_pcf import get_correlation_length_matrix
+
+    n, m = args.gp_train, args.gp_predict
+    L = 160.0 * np.sqrt(n / 40000.0)
+    size, g1, g2, sigma, noise = 1.5, 0.2, 0.2, 2.0, 0.01
+    inv = np.linalg.inv(get_correlation_length_matrix(size, g1, g2))
+    kstr = "%r**2 * AnisotropicVonKarman(invLam=array([[%.17g, %.17g], [%.17g, %.17g]]))" % (
+        sigma, inv[0, 0], inv[0, 1], inv[1, 0], inv[1, 1])
+    rng = np.random.default_rng(42)
+    X = rng.uniform(-L / 2, L / 2, size=(n, 2))
+    Xs = rng.uniform(-L / 2, L / 2, size=(m, 2))
+    # exact GRF draw y = L z + noise with our own factorisation (data generation, not timed)
+    kern = treegp.eval_kernel(kstr)
+    desc = lower_kernel(kern, 2)
+    ws = backend.kmat_sym(X, desc, diag_add=backend.to_device(np.full(n, 1e-8)), lower_only=True)
+    info = backend.potrf(ws, n)
+    assert int(info.item()) == 0
+    z = torch.as_tensor(rng.normal(size=n), device=dev)
+    y = torch.zeros(n, dtype=torch.float64, device=dev)
+    blk = 4096
+    for r0 in range(0, n, blk):  # y = tril(L) z, block rows (avoids a 12.8 GB tril copy)
+        r1 = min(n, r0 + blk)
+        rows = ws[r0:r1, :n]
+        y[r0:r1] = torch.tril(rows, diagonal=r0) @ z
+    y = y.cpu().numpy() + rng.normal(scale=noise, size=n)
+    y_err = np.full(n, noise)
+    del ws, z
+    torch.cuda.empty_cache()
+
+    lo, hi = dist.slab(m, rank, world)
+    Xs_local = Xs[lo:hi]
+    out = {}
+
+    def one_run():
+        t = {}
+        barrier()
+        t0 = time.perf_counter()
+        gp = treegp.GPInterpolation(kernel=kstr, optimizer="anisotropic", normalize=True, nbins=21, min_sep=0.0,
+                                    max_sep=4.0 * size, p0=[1.0, 0.0, 0.0])
+        gp.initialize(X, y, y_err=y_err)
+        gp.solve()
+        torch.cuda.synchronize()
+        t["solve_anisotropic_s"] = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        ypred = gp.predict(Xs_local)
+        torch.cuda.synchronize()
+        t["predict_s"] = time.perf_counter() - t1
+        t["total_s"] = time.perf_counter() - t0
+        return gp, ypred, t
+
+    one_run()  # warm-up (allocator, kernel load)
+    runs = []
+    for _ in range(2):
+        gp, ypred, t = one_run()
+        runs.append({k: max_over_ranks(v) for k, v in t.items()})
+    best = min(runs, key=lambda r: r["total_s"])
+
+    # kernel-level breakdown with CUDA events (device-resident, rank-local)
+    def ev(fn, reps=2):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e-3)
+        return float(np.mean(ts))
+
+    desc = lower_kernel(gp.kernel, 2)
+    Xd = backend.as_points(X)
+    e2 = backend.to_device(y_err ** 2)
+    ws = backend.alloc_matrix(n, n)
+    t_k = ev(lambda: backend.kmat_sym(Xd, desc, e2, out=ws, lower_only=True))
+
+    def build_and_factor():
+        backend.kmat_sym(Xd, desc, e2, out=ws, lower_only=True)
+        backend.potrf(ws, n)
+
+    t_kf = ev(build_and_factor)
+    t_chol = t_kf - t_k
+    b = backend.to_device(y)
+    t_solve = ev(lambda: backend.potrs_vec(ws, n, b.clone()))
+    Xsd = backend.as_points(Xs_local)
+    alpha = backend.potrs_vec(ws, n, b.clone())
+    t_mean = ev(lambda: backend.predict_mean(Xsd, Xd, desc, alpha))
+    mv = min(len(Xs_local), 8192)
+    t_var = ev(lambda: backend.predict_var(Xsd[:mv], Xd, desc, ws), reps=1)
+    flops = n ** 3 / 3.0
+    out.update({
+        "metric": "gp_fit_predict_wall_s", "value": best["total_s"], "unit": "s", "higher_is_better": False,
+        "config": {"workload": "2D AnisotropicVonKarman GP, N=%d train / M=%d predict (configs[2]); "
+                               "GPInterpolation.initialize + solve(optimizer='anisotropic', nbins=21, 444 bootstraps) "
+                               "+ predict(M), host numpy in/out; test points sharded over %d rank(s)" % (n, m, world)},
+        "wall_breakdown_s": best,
+        "kernel_breakdown_s": {"kmat_lower": t_k, "potrf": t_chol, "potrs_vec": t_solve,
+                               "predict_mean_local_M=%d" % len(Xs_local): t_mean,
+                               "predict_var_diag_M=%d" % mv: t_var},
+        "fitted_theta": [float(v) for v in gp.kernel.theta],
+        "true_theta": [float(v) for v in kern.theta],
+        "roofline_potrf": {"bound": "tensor", "kernel": "gemm_nt_sub_kernel (DMMA.8x8x4) inside tgp_potrf",
+                           "achieved": flops / t_chol / 1e12, "peak": dmma_tf, "unit": "TFLOP/s",
+                           "frac": flops / t_chol / 1e12 / dmma_tf,
+                           "note": "FP64 tensor pipe (mma.sync m8n8k4 f64); peak measured live by tgp_microbench_fp64"},
+        "roofline_kmat": {"bound": "hbm", "achieved": 4.0 * n * n / t_k / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": 4.0 * n * n / t_k / 1e9 / hbm_peak,
+                          "note": "lower-triangle build, algorithmic bytes 4 N^2; von Karman is FP64-ALU bound"},
+        "predict_mean_kernel_evals_per_s": len(Xs_local) * n / t_mean,
+    })
+    return out
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
