@@ -193,6 +193,9 @@ def run_ours(args):
     npairs_total = n * (n - 1) // 2
     px, py = backend.to_device(X[:, 0]), backend.to_device(X[:, 1])
     pk = backend.to_device(y - np.mean(y))
+    # device-resident inputs are stored in Hilbert order (what two_pcf.comp_2pcf does on the way in)
+    order = backend.hilbert_order(px, py)
+    px, py, pk = px[order].contiguous(), py[order].contiguous(), pk[order].contiguous()
     off = backend.to_device(np.array([0, n]), torch.int64)
     edges = backend.to_device(binning.twod_thresholds(mx, NBINS))
     launches = 0

@@ -159,6 +159,14 @@ int tgp_pairbin(const double* px, const double* py, const double* pk, const doub
                 int32_t tile_rank, int32_t tile_nranks, int64_t* npairs, double* sumw,
                 double* sumwkk, double* sumwr, void* stream);
 
+/* Hilbert-curve keys of 2-D points on a 2^order x 2^order grid over the square
+ * [xmin, xmin+extent) x [ymin, ymin+extent).  tgp_pairbin is correct for any point order, but when the
+ * catalogue is sorted by this key (torch.argsort on the caller's side) neighbouring points are stored
+ * together and the kernel's register-accumulation path applies (no shared-memory atomics in the inner
+ * loop).  keys: device int64[n]. */
+int tgp_hilbert_keys(const double* x, const double* y, int64_t n, double xmin, double ymin, double extent,
+                     int32_t order, int64_t* keys, void* stream);
+
 /* Points per pair tile (informational). */
 int tgp_pairbin_tile(void);
 

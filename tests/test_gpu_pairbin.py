@@ -10,9 +10,15 @@ from oracle import pairbin_oracle as po
 pytestmark = pytest.mark.gpu
 
 
-def _gpu_pairbin(x, y, k, w, min_sep, max_sep, nbins, bin_type, offsets=None, nranks=1):
+def _gpu_pairbin(x, y, k, w, min_sep, max_sep, nbins, bin_type, offsets=None, nranks=1, hilbert=False):
     import torch
     from treegp_b200 import _cabi, backend, binning
+
+    if hilbert:  # spatially sorted input exercises the register-accumulation path of the kernel
+        assert offsets is None
+        order = backend.hilbert_order(backend.to_device(x), backend.to_device(y)).cpu().numpy()
+        x, y, k = x[order], y[order], k[order]
+        w = None if w is None else w[order]
 
     bt = _cabi.BIN_TWOD if bin_type == "TwoD" else _cabi.BIN_LOG
     edges = binning.twod_thresholds(max_sep, nbins) if bin_type == "TwoD" else binning.log_thresholds(min_sep, max_sep, nbins)
@@ -54,6 +60,23 @@ def test_pairbin_matches_oracle(gpu_ready, n, weighted, cfg):
         x[7], y[7] = x[3], y[3]
     ref = po.pairbin(x, y, k, w, mn, mx, nb, bin_type)
     _check(_gpu_pairbin(x, y, k, w, mn, mx, nb, bin_type), ref)
+    _check(_gpu_pairbin(x, y, k, w, mn, mx, nb, bin_type, hilbert=True), ref)
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("n,mx,nb,mn", [(30000, 70.0, 21, 0.0), (30000, 12.0, 6, 0.0), (50000, 40.0, 9, 3.0),
+                                        (20011, 200.0, 1, 0.0), (40000, 25.0, 2, 0.0)])
+def test_pairbin_register_path_matches_oracle(gpu_ready, weighted, n, mx, nb, mn):
+    """Hilbert-sorted input at sizes where 32 x 32 pair blocks fit a 2 x 2 bin window: the
+    register-accumulation path (full-in, partial and out-of-range blocks) must stay bit-exact."""
+    rng = np.random.default_rng(n + nb)
+    x, y = rng.uniform(-50, 50, n), rng.uniform(-50, 50, n)
+    k = rng.normal(size=n)
+    w = rng.uniform(0.5, 2.0, n) if weighted else None
+    x[100], y[100] = x[5000], y[5000]  # coincident points far apart in memory
+    x[7], y[7] = x[8], y[8]            # and adjacent
+    ref = po.pairbin(x, y, k, w, mn, mx, nb, "TwoD")
+    _check(_gpu_pairbin(x, y, k, w, mn, mx, nb, "TwoD", hilbert=True), ref)
 
 
 def test_pairbin_values_on_bin_edges(gpu_ready):
@@ -66,6 +89,15 @@ def test_pairbin_values_on_bin_edges(gpu_ready):
     for mx, nb in ((5.0, 20), (5.25, 21), (4.0, 16)):
         ref = po.pairbin(x, y, k, None, 0.0, mx, nb, "TwoD")
         _check(_gpu_pairbin(x, y, k, None, 0.0, mx, nb, "TwoD"), ref)
+        _check(_gpu_pairbin(x, y, k, None, 0.0, mx, nb, "TwoD", hilbert=True), ref)
+    # a dense lattice: many points, displacements exactly on edges, register path
+    g = np.arange(-60, 61, dtype=np.float64)
+    X, Y = np.meshgrid(g, g)
+    xl, yl = X.ravel() * 0.25, Y.ravel() * 0.25
+    kl = np.cos(xl) * np.sin(yl)
+    for mx, nb in ((5.0, 20), (5.25, 21), (16.0, 4)):
+        ref = po.pairbin(xl, yl, kl, None, 0.0, mx, nb, "TwoD")
+        _check(_gpu_pairbin(xl, yl, kl, None, 0.0, mx, nb, "TwoD", hilbert=True), ref)
     ref = po.pairbin(x, y, k, None, 0.5, 8.0, 16, "Log")
     _check(_gpu_pairbin(x, y, k, None, 0.5, 8.0, 16, "Log"), ref)
 
@@ -107,3 +139,4 @@ def test_pairbin_n20000_vs_oracle(gpu_ready):
     res = _gpu_pairbin(x, y, k, None, 0.0, mx, nb, "TwoD")
     _check(res, ref)
     assert res[0].sum() == ref["npairs"].sum()
+    _check(_gpu_pairbin(x, y, k, None, 0.0, mx, nb, "TwoD", hilbert=True), ref)

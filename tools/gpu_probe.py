@@ -83,6 +83,8 @@ def main():
         x = backend.to_device(rng.uniform(0, Lf, n))
         y = backend.to_device(rng.uniform(0, Lf, n))
         k = backend.to_device(rng.normal(size=n))
+        order = backend.hilbert_order(x, y)
+        x, y, k = x[order].contiguous(), y[order].contiguous(), k[order].contiguous()
         off = backend.to_device(np.array([0, n]), torch.int64)
         for label, mx in (("default", Lf * np.sqrt(2) / 2), ("small", Lf / 100)):
             edges = backend.to_device(binning.twod_thresholds(mx, 21))

@@ -169,6 +169,23 @@ def pairbin(px, py, pk, pw, cat_off, max_cat_len, bin_type, edges, nbins, min_se
     return npairs, sumw, sumwkk, sumwr
 
 
+def hilbert_order(px, py):
+    """Permutation (device int64) that sorts the points along a Hilbert curve; makes tgp_pairbin's
+    register path applicable.  The argsort is torch plumbing; the keys come from the C ABI."""
+    n = int(px.numel())
+    if n == 0:
+        return torch.zeros(0, dtype=torch.int64, device=px.device)
+    xmin, xmax = float(px.min().item()), float(px.max().item())
+    ymin, ymax = float(py.min().item()), float(py.max().item())
+    extent = max(xmax - xmin, ymax - ymin)
+    extent = extent * (1.0 + 1e-9) if extent > 0 else 1.0
+    order = int(min(16, max(1, np.ceil(np.log2(max(np.sqrt(n), 2.0))) + 1)))
+    keys = torch.empty(n, dtype=torch.int64, device=px.device)
+    check(_cabi.load().tgp_hilbert_keys(_p(px), _p(py), n, xmin, ymin, extent, order, _p(keys), _stream()),
+          "tgp_hilbert_keys")
+    return torch.argsort(keys)
+
+
 def microbench_fp64(kind, iters=20000):
     require_cuda()
     v = ctypes.c_double(0.0)

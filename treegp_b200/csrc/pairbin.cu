@@ -16,17 +16,29 @@
 // division or logarithms on the device; r2 is formed with un-fused mul/add for the same reason.
 //
 // Kernel shape: persistent CTAs walk equal-sized runs of (row-tile, column-tile) pairs of the upper
-// triangle.  Each thread owns one row point in registers; column tiles are staged in shared memory
-// and read as broadcasts.  Histograms are privatised per warp in shared memory (32-bit native
-// atomics for counts, FP64 CAS adds for sums) and flushed to global memory with red.global once per
-// catalogue.  Multi-GPU: runs are dealt round-robin to ranks; the caller all-reduces the bin sums.
+// triangle of the pair matrix.  Each thread owns one row point in registers; column tiles are staged
+// in shared memory and read as broadcasts.  Every pair is evaluated individually.
+//
+// Accumulation has two paths, chosen per (warp = 32 row points, chunk = 32 column points):
+//   * REGISTER path.  When the points are spatially sorted (the host sorts along a Hilbert curve,
+//     tgp_hilbert_keys) the displacements of a 32 x 32 block span at most 2 x 2 bins.  The block's
+//     bounding boxes give that window exactly (FP subtraction is monotone), one threshold per axis
+//     decides the bin, and each lane keeps the four bin sums of the forward (dx,dy) and of the
+//     mirrored (-dx,-dy) entry in registers: no atomics in the inner loop.  Counts use
+//     inclusion-exclusion on three integer counters (exact).  Blocks entirely inside the range test
+//     skip it; blocks entirely outside are skipped.  Registers are flushed (warp shuffle reduction,
+//     then one shared-memory add per bin) only when the window moves.
+//   * GENERIC path (unsorted input, wide windows, Log bins, the diagonal block): per-pair bin search
+//     and shared-memory atomics on warp-privatised histograms.
+// Shared histograms are flushed to global memory with red.global once per catalogue.
+// Multi-GPU: runs are dealt round-robin to ranks; the caller all-reduces the bin sums.
 #include <float.h>
 #include <math.h>
 #include "tgp_common.cuh"
 
 constexpr int PB_T = 256;       // points per tile (rows per CTA = threads per CTA)
 constexpr int PB_WARPS = PB_T / 32;
-constexpr int PB_FLUSH_TILEPAIRS = 200000;  // keeps the 32-bit private counters from overflowing
+constexpr int PB_FLUSH_TILEPAIRS = 100000;  // keeps the 32-bit private counters from overflowing
 
 struct PBParams {
   const double *px, *py, *pk, *pw;
@@ -52,9 +64,19 @@ __device__ __forceinline__ int pb_bin_twod(double d, double hi, double inv_bin, 
   return i;
 }
 
+// Robust version for window end points (the estimate may be off by more than one there).
+__device__ __forceinline__ int pb_bin_twod_search(double d, int nbins, const double* __restrict__ ed) {
+  int lo = 0, hi = nbins - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (d >= ed[mid]) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
 __device__ __forceinline__ int pb_bin_log(double r2, int nbins, const double* __restrict__ ed) {
   // number of interior thresholds ed[1..nbins-1] that are <= r2 (binary search)
-  int lo = 0, hi = nbins - 1;  // answer in [lo, hi]
+  int lo = 0, hi = nbins - 1;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (r2 >= ed[mid]) lo = mid; else hi = mid - 1;
@@ -62,38 +84,179 @@ __device__ __forceinline__ int pb_bin_log(double r2, int nbins, const double* __
   return lo;
 }
 
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Per-lane register accumulators of the 2 x 2 window, forward and mirrored entry.
+template <bool WEIGHTED>
+struct RegAcc {
+  double fs[4], rs[4];       // sum wk wk per window bin: index = bx + 2*by
+  double fw[WEIGHTED ? 4 : 1], rw[WEIGHTED ? 4 : 1];
+  unsigned fcx, fcy, fcxy, rcx, rcy, rcxy, nin;
+  int fx0, fy0, rx0, ry0;    // window origins (bins); -1 = no open window
+  double tx, ty, ntx, nty;   // forward: bx = dx >= tx; mirrored: bx = -dx >= t' <=> dx <= ntx = -t'
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      fs[b] = rs[b] = 0.0;
+      if constexpr (WEIGHTED) fw[b] = rw[b] = 0.0;
+    }
+    fcx = fcy = fcxy = rcx = rcy = rcxy = nin = 0u;
+  }
+};
+
+
+// Branch-free accumulation of one pair into the 2 x 2 window registers (one direction).
+// px = (dx CMP tx), py = (dy CMP ty); exactly one of the four predicated FMAs executes.
+// Index convention s[bx + 2*by].  Written in PTX so that ptxas keeps predication instead of the
+// divergent branches nvcc generates for the equivalent if/else ladder.
+#define PB_ACCUM(CMP, S, CX, CY, CXY, DX, TX, DY, TY, KI, KJ)                                  \
+  asm volatile(                                                                                \
+      "{\n\t"                                                                                  \
+      ".reg .pred px, py, q0, q1, q2, q3;\n\t"                                                 \
+      "setp." CMP ".f64 px, %7, %8;\n\t"                                                       \
+      "setp." CMP ".f64 py, %9, %10;\n\t"                                                      \
+      "and.pred q3, px, py;\n\t"                                                               \
+      "xor.pred q1, px, q3;\n\t"                                                               \
+      "xor.pred q2, py, q3;\n\t"                                                               \
+      "or.pred q0, px, py;\n\t"                                                                \
+      "not.pred q0, q0;\n\t"                                                                   \
+      "@q0 fma.rn.f64 %0, %11, %12, %0;\n\t"                                                   \
+      "@q1 fma.rn.f64 %1, %11, %12, %1;\n\t"                                                   \
+      "@q2 fma.rn.f64 %2, %11, %12, %2;\n\t"                                                   \
+      "@q3 fma.rn.f64 %3, %11, %12, %3;\n\t"                                                   \
+      "@px add.u32 %4, %4, 1;\n\t"                                                             \
+      "@py add.u32 %5, %5, 1;\n\t"                                                             \
+      "@q3 add.u32 %6, %6, 1;\n\t"                                                             \
+      "}\n"                                                                                    \
+      : "+d"(S[0]), "+d"(S[1]), "+d"(S[2]), "+d"(S[3]), "+r"(CX), "+r"(CY), "+r"(CXY)          \
+      : "d"(DX), "d"(TX), "d"(DY), "d"(TY), "d"(KI), "d"(KJ))
+
+// Same with a second set of sums (weights) sharing the predicates.
+#define PB_ACCUM_W(CMP, S, WS, CX, CY, CXY, DX, TX, DY, TY, KI, KJ, WI, WJ)                    \
+  asm volatile(                                                                                \
+      "{\n\t"                                                                                  \
+      ".reg .pred px, py, q0, q1, q2, q3;\n\t"                                                 \
+      "setp." CMP ".f64 px, %11, %12;\n\t"                                                     \
+      "setp." CMP ".f64 py, %13, %14;\n\t"                                                     \
+      "and.pred q3, px, py;\n\t"                                                               \
+      "xor.pred q1, px, q3;\n\t"                                                               \
+      "xor.pred q2, py, q3;\n\t"                                                               \
+      "or.pred q0, px, py;\n\t"                                                                \
+      "not.pred q0, q0;\n\t"                                                                   \
+      "@q0 fma.rn.f64 %0, %15, %16, %0;\n\t"                                                   \
+      "@q1 fma.rn.f64 %1, %15, %16, %1;\n\t"                                                   \
+      "@q2 fma.rn.f64 %2, %15, %16, %2;\n\t"                                                   \
+      "@q3 fma.rn.f64 %3, %15, %16, %3;\n\t"                                                   \
+      "@q0 fma.rn.f64 %4, %17, %18, %4;\n\t"                                                   \
+      "@q1 fma.rn.f64 %5, %17, %18, %5;\n\t"                                                   \
+      "@q2 fma.rn.f64 %6, %17, %18, %6;\n\t"                                                   \
+      "@q3 fma.rn.f64 %7, %17, %18, %7;\n\t"                                                   \
+      "@px add.u32 %8, %8, 1;\n\t"                                                             \
+      "@py add.u32 %9, %9, 1;\n\t"                                                             \
+      "@q3 add.u32 %10, %10, 1;\n\t"                                                           \
+      "}\n"                                                                                    \
+      : "+d"(S[0]), "+d"(S[1]), "+d"(S[2]), "+d"(S[3]), "+d"(WS[0]), "+d"(WS[1]), "+d"(WS[2]),  \
+        "+d"(WS[3]), "+r"(CX), "+r"(CY), "+r"(CXY)                                             \
+      : "d"(DX), "d"(TX), "d"(DY), "d"(TY), "d"(KI), "d"(KJ), "d"(WI), "d"(WJ))
+
+enum { PB_OUT = 0, PB_REG_FULL = 1, PB_REG_CHECK = 2, PB_GENERIC = 3 };
+
 template <int BT, bool WEIGHTED>
 __global__ void __launch_bounds__(PB_T)
 pairbin_kernel(PBParams P) {
   extern __shared__ __align__(16) unsigned char pb_smem[];
-  const int nb = P.nb, ncopy = P.ncopy;
-  double* ed = reinterpret_cast<double*>(pb_smem);                 // nbins + 1
-  double* hs = ed + ((P.nbins + 2) & ~1);                          // ncopy * nb   sum wk wk
+  const int nb = P.nb, ncopy = P.ncopy, nbins = P.nbins;
+  double* ed = reinterpret_cast<double*>(pb_smem);                 // nbins + 1 (padded to even)
+  double2* txy = reinterpret_cast<double2*>(ed + ((nbins + 2) & ~1));  // PB_T column points (16-byte aligned)
+  double* tk = reinterpret_cast<double*>(txy + PB_T);              // PB_T
+  double* tw = tk + PB_T;                                          // PB_T
+  double* cbox = tw + PB_T;                                        // PB_WARPS * 4: minx, maxx, miny, maxy per chunk
+  double* hs = cbox + PB_WARPS * 4;                                // ncopy * nb   sum wk wk
   double* hw = hs + (size_t)ncopy * nb;                            // ncopy * nb   sum w w      (WEIGHTED)
   double* hr = hw + (WEIGHTED ? (size_t)ncopy * nb : 0);           // ncopy * nb   sum w w r    (LOG)
-  double* tx = hr + (BT == TGP_BIN_LOG ? (size_t)ncopy * nb : 0);  // PB_T each
-  double* ty = tx + PB_T;
-  double* tk = ty + PB_T;
-  double* tw = tk + PB_T;
-  unsigned int* hc = reinterpret_cast<unsigned int*>(tw + PB_T);   // ncopy * nb   counts
+  unsigned int* hc = reinterpret_cast<unsigned int*>(hr + (BT == TGP_BIN_LOG ? (size_t)ncopy * nb : 0));  // counts
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int copy = warp % ncopy;
   double* my_s = hs + (size_t)copy * nb;
   double* my_w = hw + (size_t)copy * nb;
   double* my_r = hr + (size_t)copy * nb;
   unsigned int* my_c = hc + (size_t)copy * nb;
 
-  for (int i = tid; i <= P.nbins; i += PB_T) ed[i] = P.edges[i];
+  for (int i = tid; i <= nbins; i += PB_T) ed[i] = P.edges[i];
   auto clear_hist = [&]() {
     for (int i = tid; i < ncopy * nb; i += PB_T) {
       hs[i] = 0.0;
       hc[i] = 0u;
-      if (WEIGHTED) hw[i] = 0.0;
+      if constexpr (WEIGHTED) hw[i] = 0.0;
       if (BT == TGP_BIN_LOG) hr[i] = 0.0;
     }
   };
+
+  RegAcc<WEIGHTED> A;
+  A.zero();
+  A.fx0 = -1;
+  // Move the lane registers of the open window into the warp's shared histogram.
+  auto flush_regs = [&]() {
+    if (BT != TGP_BIN_TWOD) return;
+    if (A.fx0 >= 0) {
+      const unsigned n_in = warp_sum_u(A.nin);
+      const unsigned fcx = warp_sum_u(A.fcx), fcy = warp_sum_u(A.fcy), fcxy = warp_sum_u(A.fcxy);
+      const unsigned rcx = warp_sum_u(A.rcx), rcy = warp_sum_u(A.rcy), rcxy = warp_sum_u(A.rcxy);
+      double fs[4], rs[4], fw[4], rw[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        fs[b] = warp_sum(A.fs[b]);
+        rs[b] = warp_sum(A.rs[b]);
+        if constexpr (WEIGHTED) { fw[b] = warp_sum(A.fw[b]); rw[b] = warp_sum(A.rw[b]); }
+      }
+      if (lane == 0 && n_in) {
+        // inclusion-exclusion: exact integer counts per window bin (index = bx + 2*by)
+        const unsigned fc[4] = {n_in - fcx - fcy + fcxy, fcx - fcxy, fcy - fcxy, fcxy};
+        const unsigned rc[4] = {n_in - rcx - rcy + rcxy, rcx - rcxy, rcy - rcxy, rcxy};
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int fxb = A.fx0 + (b & 1), fyb = A.fy0 + (b >> 1);
+          if (fc[b]) {  // a non-empty bin is always inside the grid
+            const int o = fyb * nbins + fxb;
+            atomicAdd(my_c + o, fc[b]);
+            atomicAdd(my_s + o, fs[b]);
+            if constexpr (WEIGHTED) atomicAdd(my_w + o, fw[b]);
+          }
+          const int rxb = A.rx0 + (b & 1), ryb = A.ry0 + (b >> 1);
+          if (rc[b]) {
+            const int o = ryb * nbins + rxb;
+            atomicAdd(my_c + o, rc[b]);
+            atomicAdd(my_s + o, rs[b]);
+            if constexpr (WEIGHTED) atomicAdd(my_w + o, rw[b]);
+          }
+        }
+      }
+      A.zero();
+      A.fx0 = -1;
+    }
+  };
   auto flush_hist = [&](int cat) {
+    flush_regs();
     __syncthreads();
     if (cat >= 0) {
       for (int b = tid; b < nb; b += PB_T) {
@@ -102,7 +265,7 @@ pairbin_kernel(PBParams P) {
         for (int k = 0; k < ncopy; ++k) {
           c += hc[k * nb + b];
           s += hs[k * nb + b];
-          if (WEIGHTED) w += hw[k * nb + b];
+          if constexpr (WEIGHTED) w += hw[k * nb + b];
           if (BT == TGP_BIN_LOG) r += hr[k * nb + b];
         }
         if (c) {
@@ -121,6 +284,7 @@ pairbin_kernel(PBParams P) {
   clear_hist();
   __syncthreads();
 
+  const double M = P.hi, lo2 = P.lo2;
   int cur_cat = -1;
   int since_flush = 0;
   for (int64_t q = blockIdx.x; q < P.my_items; q += gridDim.x) {
@@ -151,16 +315,22 @@ pairbin_kernel(PBParams P) {
 
     int64_t loadedI = -1;
     double xi = 0.0, yi = 0.0, ki = 0.0, wi = 0.0;
+    double ib_minx = 0.0, ib_maxx = 0.0, ib_miny = 0.0, ib_maxy = 0.0;  // bounding box of this warp's rows
     bool live = false;
     for (; p < p_end; ++p) {
       if (I != loadedI) {
         const int64_t ig = I * PB_T + tid;
         live = ig < n;
-        if (live) {
-          xi = P.px[off + ig];
-          yi = P.py[off + ig];
-          wi = WEIGHTED ? P.pw[off + ig] : 1.0;
-          ki = P.pk[off + ig] * wi;
+        // dead lanes: NaN coordinates make every comparison false, zero field/weight adds nothing
+        xi = live ? P.px[off + ig] : __longlong_as_double(0x7ff8000000000000ll);
+        yi = live ? P.py[off + ig] : __longlong_as_double(0x7ff8000000000000ll);
+        wi = live ? (WEIGHTED ? P.pw[off + ig] : 1.0) : 0.0;
+        ki = live ? P.pk[off + ig] * wi : 0.0;
+        if (BT == TGP_BIN_TWOD) {
+          ib_minx = warp_min(live ? xi : INFINITY);
+          ib_maxx = warp_max(live ? xi : -INFINITY);
+          ib_miny = warp_min(live ? yi : INFINITY);
+          ib_maxy = warp_max(live ? yi : -INFINITY);
         }
         loadedI = I;
       }
@@ -168,43 +338,157 @@ pairbin_kernel(PBParams P) {
       {
         const int64_t jg = J * PB_T + tid;
         const bool ok = jg < n;
-        tx[tid] = ok ? P.px[off + jg] : 0.0;
-        ty[tid] = ok ? P.py[off + jg] : 0.0;
+        const double x = ok ? P.px[off + jg] : 0.0, y = ok ? P.py[off + jg] : 0.0;
+        txy[tid] = make_double2(x, y);
         const double w = (ok && WEIGHTED) ? P.pw[off + jg] : 1.0;
         tk[tid] = ok ? P.pk[off + jg] * w : 0.0;
-        if (WEIGHTED) tw[tid] = w;
+        if constexpr (WEIGHTED) tw[tid] = ok ? w : 0.0;
+        if (BT == TGP_BIN_TWOD) {  // chunk `warp` of the column tile: bounding box
+          const double a = warp_min(ok ? x : INFINITY), b = warp_max(ok ? x : -INFINITY);
+          const double c = warp_min(ok ? y : INFINITY), d = warp_max(ok ? y : -INFINITY);
+          if (lane == 0) { cbox[warp * 4 + 0] = a; cbox[warp * 4 + 1] = b; cbox[warp * 4 + 2] = c; cbox[warp * 4 + 3] = d; }
+        }
       }
       __syncthreads();
       const int jcount = (int)((n - J * PB_T < PB_T) ? (n - J * PB_T) : PB_T);
-      const int jstart = (I == J) ? tid + 1 : 0;  // diagonal tile: j > i only
-      if (live) {
-        for (int jj = jstart; jj < jcount; ++jj) {
-          const double dx = tx[jj] - xi, dy = ty[jj] - yi;
-          const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));  // no FMA: matches the oracle bit for bit
-          if (BT == TGP_BIN_TWOD) {
-            if (r2 >= P.lo2 && fabs(dx) < P.hi && fabs(dy) < P.hi) {
-              const int b1 = pb_bin_twod(dy, P.hi, P.inv_bin, P.nbins, ed) * P.nbins +
-                             pb_bin_twod(dx, P.hi, P.inv_bin, P.nbins, ed);
-              const int b2 = pb_bin_twod(-dy, P.hi, P.inv_bin, P.nbins, ed) * P.nbins +
-                             pb_bin_twod(-dx, P.hi, P.inv_bin, P.nbins, ed);
-              const double kk = ki * tk[jj];
-              atomicAdd(my_c + b1, 1u);
-              atomicAdd(my_c + b2, 1u);
-              atomicAdd(my_s + b1, kk);
-              atomicAdd(my_s + b2, kk);
-              if (WEIGHTED) {
-                const double ww = wi * tw[jj];
-                atomicAdd(my_w + b1, ww);
-                atomicAdd(my_w + b2, ww);
+      const bool diag = (I == J);
+
+      if (BT == TGP_BIN_TWOD) {
+        // ---- lanes 0..7 classify chunks 0..7 of this column tile against this warp's rows ----
+        int cls = PB_OUT, wx = 0, wy = 0, wrx = 0, wry = 0;
+        if (lane < PB_WARPS && lane * 32 < jcount && ib_minx <= ib_maxx) {
+          const double cminx = cbox[lane * 4 + 0], cmaxx = cbox[lane * 4 + 1];
+          const double cminy = cbox[lane * 4 + 2], cmaxy = cbox[lane * 4 + 3];
+          // every dx = x_j - x_i of the block lies in [dx0, dx1] (rounding is monotone)
+          const double dx0 = cminx - ib_maxx, dx1 = cmaxx - ib_minx;
+          const double dy0 = cminy - ib_maxy, dy1 = cmaxy - ib_miny;
+          const double ax = fmax(fabs(dx0), fabs(dx1)), ay = fmax(fabs(dy0), fabs(dy1));   // max |dx|, |dy|
+          const double nx = dx0 > 0.0 ? dx0 : (dx1 < 0.0 ? -dx1 : 0.0);                    // min |dx|
+          const double ny = dy0 > 0.0 ? dy0 : (dy1 < 0.0 ? -dy1 : 0.0);
+          const double r2max = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
+          const double r2min = __dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny));
+          if (nx >= M || ny >= M || r2max < lo2) {
+            cls = PB_OUT;
+          } else if (diag && lane <= warp) {
+            // diagonal tile: chunks before this warp's rows hold only j < i; the warp's own chunk needs j > i
+            cls = (lane == warp) ? PB_GENERIC : PB_OUT;
+          } else {
+            const int x0 = pb_bin_twod_search(dx0, nbins, ed), x1 = pb_bin_twod_search(dx1, nbins, ed);
+            const int y0 = pb_bin_twod_search(dy0, nbins, ed), y1 = pb_bin_twod_search(dy1, nbins, ed);
+            const int rx0 = pb_bin_twod_search(-dx1, nbins, ed), rx1 = pb_bin_twod_search(-dx0, nbins, ed);
+            const int ry0 = pb_bin_twod_search(-dy1, nbins, ed), ry1 = pb_bin_twod_search(-dy0, nbins, ed);
+            if (x1 - x0 > 1 || y1 - y0 > 1 || rx1 - rx0 > 1 || ry1 - ry0 > 1) {
+              cls = PB_GENERIC;
+            } else {
+              cls = (ax < M && ay < M && r2min >= lo2) ? PB_REG_FULL : PB_REG_CHECK;
+              wx = x0 | ((x1 - x0) << 16); wy = y0 | ((y1 - y0) << 16);
+              wrx = rx0 | ((rx1 - rx0) << 16); wry = ry0 | ((ry1 - ry0) << 16);
+            }
+          }
+        }
+        const int nchunk = (jcount + 31) >> 5;
+        for (int c = 0; c < nchunk; ++c) {
+          const int ccls = __shfl_sync(0xffffffffu, cls, c);
+          if (ccls == PB_OUT) continue;
+          const int j0 = c * 32;
+          const int jn = (jcount - j0 < 32) ? (jcount - j0) : 32;
+          if (ccls == PB_GENERIC) {
+            const int jstart = (diag && c == warp) ? lane + 1 : 0;
+            if (live) {
+              for (int jj = j0 + jstart; jj < j0 + jn; ++jj) {
+                const double2 pj = txy[jj];
+                const double dx = pj.x - xi, dy = pj.y - yi;
+                const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                if (r2 >= lo2 && fabs(dx) < M && fabs(dy) < M) {
+                  const int b1 = pb_bin_twod(dy, M, P.inv_bin, nbins, ed) * nbins + pb_bin_twod(dx, M, P.inv_bin, nbins, ed);
+                  const int b2 = pb_bin_twod(-dy, M, P.inv_bin, nbins, ed) * nbins + pb_bin_twod(-dx, M, P.inv_bin, nbins, ed);
+                  const double kk = ki * tk[jj];
+                  atomicAdd(my_c + b1, 1u);
+                  atomicAdd(my_c + b2, 1u);
+                  atomicAdd(my_s + b1, kk);
+                  atomicAdd(my_s + b2, kk);
+                  if constexpr (WEIGHTED) {
+                    const double ww = wi * tw[jj];
+                    atomicAdd(my_w + b1, ww);
+                    atomicAdd(my_w + b2, ww);
+                  }
+                }
               }
             }
+            __syncwarp();
+            continue;
+          }
+          // ---- register path: make sure the open window covers this block ----
+          const int cwx = __shfl_sync(0xffffffffu, wx, c), cwy = __shfl_sync(0xffffffffu, wy, c);
+          const int cwrx = __shfl_sync(0xffffffffu, wrx, c), cwry = __shfl_sync(0xffffffffu, wry, c);
+          const int x0 = cwx & 0xffff, x1 = x0 + (cwx >> 16), y0 = cwy & 0xffff, y1 = y0 + (cwy >> 16);
+          const int rx0 = cwrx & 0xffff, rx1 = rx0 + (cwrx >> 16), ry0 = cwry & 0xffff, ry1 = ry0 + (cwry >> 16);
+          const bool fits = A.fx0 >= 0 && x0 >= A.fx0 && x1 <= A.fx0 + 1 && y0 >= A.fy0 && y1 <= A.fy0 + 1 &&
+                            rx0 >= A.rx0 && rx1 <= A.rx0 + 1 && ry0 >= A.ry0 && ry1 <= A.ry0 + 1;
+          if (!fits) {
+            flush_regs();
+            // a window [b0, b0+1] must stay inside the grid unless nbins == 1
+            A.fx0 = min(x0, max(nbins - 2, 0)); A.fy0 = min(y0, max(nbins - 2, 0));
+            A.rx0 = min(rx0, max(nbins - 2, 0)); A.ry0 = min(ry0, max(nbins - 2, 0));
+            // bx = (bin >= b0 + 1): forward dx >= ed[b0+1]; mirrored -dx >= ed[b0+1] <=> dx <= -ed[b0+1]
+            A.tx = (nbins > 1) ? ed[A.fx0 + 1] : INFINITY;
+            A.ty = (nbins > 1) ? ed[A.fy0 + 1] : INFINITY;
+            A.ntx = (nbins > 1) ? -ed[A.rx0 + 1] : -INFINITY;
+            A.nty = (nbins > 1) ? -ed[A.ry0 + 1] : -INFINITY;
+          }
+          const double tx = A.tx, ty = A.ty, ntx = A.ntx, nty = A.nty;
+          if (ccls == PB_REG_FULL) {
+#pragma unroll 4
+            for (int jj = j0; jj < j0 + jn; ++jj) {
+              const double2 pj = txy[jj];
+              const double dx = pj.x - xi, dy = pj.y - yi;
+              const double kj = tk[jj];
+              if constexpr (WEIGHTED) {
+                const double wj = tw[jj];
+                PB_ACCUM_W("ge", A.fs, A.fw, A.fcx, A.fcy, A.fcxy, dx, tx, dy, ty, ki, kj, wi, wj);
+                PB_ACCUM_W("le", A.rs, A.rw, A.rcx, A.rcy, A.rcxy, dx, ntx, dy, nty, ki, kj, wi, wj);
+              } else {
+                PB_ACCUM("ge", A.fs, A.fcx, A.fcy, A.fcxy, dx, tx, dy, ty, ki, kj);
+                PB_ACCUM("le", A.rs, A.rcx, A.rcy, A.rcxy, dx, ntx, dy, nty, ki, kj);
+              }
+            }
+            A.nin += live ? (unsigned)jn : 0u;
           } else {
-            if (r2 >= P.lo2 && r2 < P.hi) {
-              const int b = pb_bin_log(r2, P.nbins, ed);
+#pragma unroll 2
+            for (int jj = j0; jj < j0 + jn; ++jj) {
+              const double2 pj = txy[jj];
+              const double dx = pj.x - xi, dy = pj.y - yi;
+              const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+              const bool ok = r2 >= lo2 && fabs(dx) < M && fabs(dy) < M;  // false for dead lanes (NaN)
+              if (ok) {
+                const double kj = tk[jj];
+                if constexpr (WEIGHTED) {
+                  const double wj = tw[jj];
+                  PB_ACCUM_W("ge", A.fs, A.fw, A.fcx, A.fcy, A.fcxy, dx, tx, dy, ty, ki, kj, wi, wj);
+                  PB_ACCUM_W("le", A.rs, A.rw, A.rcx, A.rcy, A.rcxy, dx, ntx, dy, nty, ki, kj, wi, wj);
+                } else {
+                  PB_ACCUM("ge", A.fs, A.fcx, A.fcy, A.fcxy, dx, tx, dy, ty, ki, kj);
+                  PB_ACCUM("le", A.rs, A.rcx, A.rcy, A.rcxy, dx, ntx, dy, nty, ki, kj);
+                }
+                A.nin += 1u;
+              }
+            }
+          }
+        }
+      } else {
+        // ---- Log bins: generic path ----
+        const int jstart = diag ? tid + 1 : 0;  // diagonal tile: j > i only
+        if (live) {
+          for (int jj = jstart; jj < jcount; ++jj) {
+            const double2 pj = txy[jj];
+            const double dx = pj.x - xi, dy = pj.y - yi;
+            const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));  // no FMA: matches the oracle bit for bit
+            if (r2 >= lo2 && r2 < M) {
+              const int b = pb_bin_log(r2, nbins, ed);
               const double ww = WEIGHTED ? wi * tw[jj] : 1.0;
               atomicAdd(my_c + b, 1u);
               atomicAdd(my_s + b, ki * tk[jj]);
-              if (WEIGHTED) atomicAdd(my_w + b, ww);
+              if constexpr (WEIGHTED) atomicAdd(my_w + b, ww);
               atomicAdd(my_r + b, ww * sqrt(r2));
             }
           }
@@ -213,6 +497,9 @@ pairbin_kernel(PBParams P) {
       ++since_flush;
       if (++J == nt) { ++I; J = I; }
     }
+    // the per-lane 32-bit counters are bounded by the flush policy below: flush the registers at
+    // the end of every work item (cheap: once per `run` tile pairs)
+    flush_regs();
   }
   flush_hist(cur_cat);
 }
@@ -252,7 +539,7 @@ extern "C" int tgp_pairbin(const double* px, const double* py, const double* pk,
 
   // shared-memory budget -> number of private histogram copies
   const size_t per_copy = (size_t)P.nb * (8 + 4 + (weighted ? 8 : 0) + (twod ? 0 : 8));
-  const size_t fixed = (size_t)((nbins + 2) & ~1) * 8 + 4 * PB_T * 8;
+  const size_t fixed = (size_t)((nbins + 2) & ~1) * 8 + 4 * PB_T * 8 + PB_WARPS * 4 * 8;
   const size_t budget = 200 * 1024;
   TGP_CHECK_ARG(fixed + per_copy <= budget, "too many bins for the shared-memory histogram");
   int ncopy = (int)((budget - fixed) / per_copy);
@@ -291,6 +578,43 @@ extern "C" int tgp_pairbin(const double* px, const double* py, const double* pk,
     if (weighted) TGP_PB_LAUNCH(TGP_BIN_LOG, true); else TGP_PB_LAUNCH(TGP_BIN_LOG, false);
   }
 #undef TGP_PB_LAUNCH
+  TGP_LAUNCH_CHECK();
+  return TGP_OK;
+}
+
+// ============================================================================================
+// Hilbert-curve keys: sorting the points by this key makes consecutive points spatial neighbours,
+// which is what lets the pair-binning kernel keep whole 32 x 32 blocks inside a 2 x 2 bin window.
+// ============================================================================================
+__global__ void hilbert_keys_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
+                                    double x0, double y0, double inv_cell, int order, int64_t* __restrict__ keys) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned side = 1u << order;
+  long long cx = (long long)floor((x[i] - x0) * inv_cell), cy = (long long)floor((y[i] - y0) * inv_cell);
+  unsigned ux = (unsigned)(cx < 0 ? 0 : (cx >= (long long)side ? side - 1 : cx));
+  unsigned uy = (unsigned)(cy < 0 ? 0 : (cy >= (long long)side ? side - 1 : cy));
+  // classic xy -> d conversion
+  unsigned long long d = 0;
+  for (unsigned s = side >> 1; s > 0; s >>= 1) {
+    const unsigned rx = (ux & s) ? 1u : 0u, ry = (uy & s) ? 1u : 0u;
+    d += (unsigned long long)s * s * ((3u * rx) ^ ry);
+    if (ry == 0) {
+      if (rx == 1) { ux = side - 1 - ux; uy = side - 1 - uy; }
+      const unsigned t = ux; ux = uy; uy = t;
+    }
+  }
+  keys[i] = (int64_t)d;
+}
+
+extern "C" int tgp_hilbert_keys(const double* x, const double* y, int64_t n, double xmin, double ymin,
+                                double extent, int32_t order, int64_t* keys, void* stream) {
+  TGP_CHECK_ARG(n >= 0 && order >= 1 && order <= 30 && extent > 0.0, "n/order/extent");
+  if (n == 0) return TGP_OK;
+  TGP_CHECK_ARG(x && y && keys, "null pointer");
+  const double inv_cell = (double)(1u << order) / extent;
+  hilbert_keys_kernel<<<(unsigned)tgp_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n, xmin, ymin, inv_cell,
+                                                                                  order, keys);
   TGP_LAUNCH_CHECK();
   return TGP_OK;
 }

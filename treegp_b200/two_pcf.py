@@ -293,9 +293,14 @@ class two_pcf(object):
         y_err = np.asarray(y_err, dtype=np.float64)
         pw = None if np.sum(y_err) == 0 else backend.to_device(1.0 / y_err ** 2)
         n = len(y)
-        xi, meanr = self._pairbin(
-            backend.to_device(X[:, 0]), backend.to_device(X[:, 1]), backend.to_device(y - np.mean(y)), pw,
-            backend.to_device(np.array([0, n]), torch.int64), n)
+        px, py = backend.to_device(X[:, 0]), backend.to_device(X[:, 1])
+        pk = backend.to_device(y - np.mean(y))
+        if self.anisotropic:
+            # spatially sorted input lets the kernel keep 32 x 32 pair blocks inside a 2 x 2 bin window
+            order = backend.hilbert_order(px, py)
+            px, py, pk = px[order].contiguous(), py[order].contiguous(), pk[order].contiguous()
+            pw = None if pw is None else pw[order].contiguous()
+        xi, meanr = self._pairbin(px, py, pk, pw, backend.to_device(np.array([0, n]), torch.int64), n)
         return self._assemble(xi[0], None if meanr is None else meanr[0])
 
     def comp_xi_covariance(self, n_bootstrap=1000, mask=None, seed=610639139):
@@ -323,9 +328,13 @@ class two_pcf(object):
         val = backend.to_device(np.asarray(self.y, dtype=np.float64))
         err = np.asarray(self.y_err, dtype=np.float64)
         err_d = backend.to_device(err)
+        # Hilbert-sort the base catalogue once: every resample is a sub-multiset in the same order
+        order = backend.hilbert_order(x, yy) if self.anisotropic else None
         out = []
         per_batch = max(1, int(batch_points // max(n, 1)))
         done = 0
+        if order is not None:
+            x, yy, val, err_d = x[order], yy[order], val[order], err_d[order]
         while done < n_bootstrap:
             b = min(per_batch, n_bootstrap - done)
             # same stream of draws as `b` successive resample_bootstrap() calls
@@ -333,6 +342,8 @@ class two_pcf(object):
             idx_d = torch.as_tensor(idx, device=dev)
             mult = torch.zeros((b, n), dtype=torch.float64, device=dev)
             mult.scatter_add_(1, idx_d, torch.ones_like(idx_d, dtype=torch.float64))
+            if order is not None:
+                mult = mult[:, order]
             ybar = (mult * val).sum(dim=1) / n                      # mean of the resampled values
             # weights: None in the reference iff the resampled errors sum to 0 (two_pcf.py:291-294)
             esum = (mult * err_d).sum(dim=1)
