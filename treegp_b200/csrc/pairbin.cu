@@ -105,78 +105,148 @@ __device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
   return v;
 }
 
-// Per-lane register accumulators of the 2 x 2 window, forward and mirrored entry.
+// Per-lane register accumulators of the 2 x 2 window, forward (dx,dy) and mirrored (-dx,-dy) entry.
+// With px = "column bit" and py = "row bit" of a pair inside the window, the lane keeps
+//   tot = sum kk,  sx = sum kk [px],  sy = sum kk [py],  sxy = sum kk [px & py]
+// (masks applied as a multiplication by 0.0 / 1.0 inside one FMA, so there is no branch and no select
+// on the 64-bit data path) and the same three counters as integers.  The four window bins follow by
+// inclusion-exclusion at flush time: exact for the counts, and of the size of ordinary summation
+// rounding for the FP64 sums.
 template <bool WEIGHTED>
 struct RegAcc {
-  double fs[4], rs[4];       // sum wk wk per window bin: index = bx + 2*by
-  double fw[WEIGHTED ? 4 : 1], rw[WEIGHTED ? 4 : 1];
+  double tot, fsx, fsy, fsxy, rsx, rsy, rsxy;
+  double wtot, fwx, fwy, fwxy, rwx, rwy, rwxy;   // weights (WEIGHTED only)
   unsigned fcx, fcy, fcxy, rcx, rcy, rcxy, nin;
-  int fx0, fy0, rx0, ry0;    // window origins (bins); -1 = no open window
-  double tx, ty, ntx, nty;   // forward: bx = dx >= tx; mirrored: bx = -dx >= t' <=> dx <= ntx = -t'
+  int fx0, fy0, rx0, ry0;    // window origins (bins); fx0 == -1: no open window
+  long long ownerI;          // row tile the per-lane thresholds were derived for
+  // Per-lane thresholds on the COLUMN point's coordinates, equivalent to the bin thresholds on the
+  // displacement because rounding is monotone:  fl(xj - xi) >= t  <=>  xj >= Tx(xi, t).
+  double Tx, Ty, RTx, RTy;   // forward: px = xj >= Tx ; mirrored: px = xj <= RTx
   __device__ __forceinline__ void zero() {
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      fs[b] = rs[b] = 0.0;
-      if constexpr (WEIGHTED) fw[b] = rw[b] = 0.0;
-    }
+    tot = fsx = fsy = fsxy = rsx = rsy = rsxy = 0.0;
+    wtot = fwx = fwy = fwxy = rwx = rwy = rwxy = 0.0;
     fcx = fcy = fcxy = rcx = rcy = rcxy = nin = 0u;
   }
 };
 
+// next representable double above / below (finite inputs; NaN and the matching infinity are returned unchanged)
+__device__ __forceinline__ double pb_next_up(double v) {
+  if (!(v < INFINITY)) return v;
+  if (v == 0.0) return __longlong_as_double(1ll);
+  const long long b = __double_as_longlong(v);
+  return __longlong_as_double(v > 0.0 ? b + 1 : b - 1);
+}
+__device__ __forceinline__ double pb_next_down(double v) {
+  if (!(v > -INFINITY)) return v;
+  if (v == 0.0) return __longlong_as_double((long long)0x8000000000000001ull);
+  const long long b = __double_as_longlong(v);
+  return __longlong_as_double(v > 0.0 ? b - 1 : b + 1);
+}
 
-// Branch-free accumulation of one pair into the 2 x 2 window registers (one direction).
-// px = (dx CMP tx), py = (dy CMP ty); exactly one of the four predicated FMAs executes.
-// Index convention s[bx + 2*by].  Written in PTX so that ptxas keeps predication instead of the
-// divergent branches nvcc generates for the equivalent if/else ladder.
-#define PB_ACCUM(CMP, S, CX, CY, CXY, DX, TX, DY, TY, KI, KJ)                                  \
-  asm volatile(                                                                                \
-      "{\n\t"                                                                                  \
-      ".reg .pred px, py, q0, q1, q2, q3;\n\t"                                                 \
-      "setp." CMP ".f64 px, %7, %8;\n\t"                                                       \
-      "setp." CMP ".f64 py, %9, %10;\n\t"                                                      \
-      "and.pred q3, px, py;\n\t"                                                               \
-      "xor.pred q1, px, q3;\n\t"                                                               \
-      "xor.pred q2, py, q3;\n\t"                                                               \
-      "or.pred q0, px, py;\n\t"                                                                \
-      "not.pred q0, q0;\n\t"                                                                   \
-      "@q0 fma.rn.f64 %0, %11, %12, %0;\n\t"                                                   \
-      "@q1 fma.rn.f64 %1, %11, %12, %1;\n\t"                                                   \
-      "@q2 fma.rn.f64 %2, %11, %12, %2;\n\t"                                                   \
-      "@q3 fma.rn.f64 %3, %11, %12, %3;\n\t"                                                   \
-      "@px add.u32 %4, %4, 1;\n\t"                                                             \
-      "@py add.u32 %5, %5, 1;\n\t"                                                             \
-      "@q3 add.u32 %6, %6, 1;\n\t"                                                             \
-      "}\n"                                                                                    \
-      : "+d"(S[0]), "+d"(S[1]), "+d"(S[2]), "+d"(S[3]), "+r"(CX), "+r"(CY), "+r"(CXY)          \
-      : "d"(DX), "d"(TX), "d"(DY), "d"(TY), "d"(KI), "d"(KJ))
+// Smallest X with fl(X - xi) >= t.  `ok` is cleared if the short search did not settle (the caller
+// then uses the generic path).  NaN in -> NaN out (dead lanes: every comparison false).
+__device__ __forceinline__ double pb_coord_ge(double xi, double t, bool& ok) {
+  if (isinf(t) || isnan(xi)) return isnan(xi) ? xi : t;
+  double c = t + xi;
+  int it = 0;
+  while ((c - xi) < t && it < 16) { c = pb_next_up(c); ++it; }
+  while ((pb_next_down(c) - xi) >= t && it < 32) { c = pb_next_down(c); ++it; }
+  if (!((c - xi) >= t) || ((pb_next_down(c) - xi) >= t)) ok = false;
+  return c;
+}
+// Largest X with fl(X - xi) <= t.
+__device__ __forceinline__ double pb_coord_le(double xi, double t, bool& ok) {
+  if (isinf(t) || isnan(xi)) return isnan(xi) ? xi : t;
+  double c = t + xi;
+  int it = 0;
+  while ((c - xi) > t && it < 16) { c = pb_next_down(c); ++it; }
+  while ((pb_next_up(c) - xi) <= t && it < 32) { c = pb_next_up(c); ++it; }
+  if (!((c - xi) <= t) || ((pb_next_up(c) - xi) <= t)) ok = false;
+  return c;
+}
 
-// Same with a second set of sums (weights) sharing the predicates.
-#define PB_ACCUM_W(CMP, S, WS, CX, CY, CXY, DX, TX, DY, TY, KI, KJ, WI, WJ)                    \
-  asm volatile(                                                                                \
-      "{\n\t"                                                                                  \
-      ".reg .pred px, py, q0, q1, q2, q3;\n\t"                                                 \
-      "setp." CMP ".f64 px, %11, %12;\n\t"                                                     \
-      "setp." CMP ".f64 py, %13, %14;\n\t"                                                     \
-      "and.pred q3, px, py;\n\t"                                                               \
-      "xor.pred q1, px, q3;\n\t"                                                               \
-      "xor.pred q2, py, q3;\n\t"                                                               \
-      "or.pred q0, px, py;\n\t"                                                                \
-      "not.pred q0, q0;\n\t"                                                                   \
-      "@q0 fma.rn.f64 %0, %15, %16, %0;\n\t"                                                   \
-      "@q1 fma.rn.f64 %1, %15, %16, %1;\n\t"                                                   \
-      "@q2 fma.rn.f64 %2, %15, %16, %2;\n\t"                                                   \
-      "@q3 fma.rn.f64 %3, %15, %16, %3;\n\t"                                                   \
-      "@q0 fma.rn.f64 %4, %17, %18, %4;\n\t"                                                   \
-      "@q1 fma.rn.f64 %5, %17, %18, %5;\n\t"                                                   \
-      "@q2 fma.rn.f64 %6, %17, %18, %6;\n\t"                                                   \
-      "@q3 fma.rn.f64 %7, %17, %18, %7;\n\t"                                                   \
-      "@px add.u32 %8, %8, 1;\n\t"                                                             \
-      "@py add.u32 %9, %9, 1;\n\t"                                                             \
-      "@q3 add.u32 %10, %10, 1;\n\t"                                                           \
-      "}\n"                                                                                    \
-      : "+d"(S[0]), "+d"(S[1]), "+d"(S[2]), "+d"(S[3]), "+d"(WS[0]), "+d"(WS[1]), "+d"(WS[2]),  \
-        "+d"(WS[3]), "+r"(CX), "+r"(CY), "+r"(CXY)                                             \
-      : "d"(DX), "d"(TX), "d"(DY), "d"(TY), "d"(KI), "d"(KJ), "d"(WI), "d"(WJ))
+// One pair into the window registers.  Written in PTX: four compares give the window bits of the
+// forward and of the mirrored entry, each masked sum is one FMA with a 0.0 / 1.0 mask, and each counter
+// one predicated integer add (nvcc's code for the equivalent C++ needs ~2x the instructions).
+#define PB_ONE "0d3FF0000000000000"
+#define PB_ZERO "0d0000000000000000"
+#define PB_PAIR(A, XJ, YJ, KK)                                                                      \
+  asm volatile(                                                                                     \
+      "{\n\t"                                                                                       \
+      ".reg .pred px, py, qx, qy, pxy, qxy;\n\t"                                                    \
+      ".reg .f64 m0, m1, m2, m3, m4, m5;\n\t"                                                       \
+      "setp.ge.f64 px, %14, %16;\n\t"                                                               \
+      "setp.ge.f64 py, %15, %17;\n\t"                                                               \
+      "setp.le.f64 qx, %14, %18;\n\t"                                                               \
+      "setp.le.f64 qy, %15, %19;\n\t"                                                               \
+      "and.pred pxy, px, py;\n\t"                                                                   \
+      "and.pred qxy, qx, qy;\n\t"                                                                   \
+      "selp.f64 m0, " PB_ONE ", " PB_ZERO ", px;\n\t"                                               \
+      "selp.f64 m1, " PB_ONE ", " PB_ZERO ", py;\n\t"                                               \
+      "selp.f64 m2, " PB_ONE ", " PB_ZERO ", pxy;\n\t"                                              \
+      "selp.f64 m3, " PB_ONE ", " PB_ZERO ", qx;\n\t"                                               \
+      "selp.f64 m4, " PB_ONE ", " PB_ZERO ", qy;\n\t"                                               \
+      "selp.f64 m5, " PB_ONE ", " PB_ZERO ", qxy;\n\t"                                              \
+      "add.f64 %0, %0, %13;\n\t"                                                                    \
+      "fma.rn.f64 %1, %13, m0, %1;\n\t"                                                             \
+      "fma.rn.f64 %2, %13, m1, %2;\n\t"                                                             \
+      "fma.rn.f64 %3, %13, m2, %3;\n\t"                                                             \
+      "fma.rn.f64 %4, %13, m3, %4;\n\t"                                                             \
+      "fma.rn.f64 %5, %13, m4, %5;\n\t"                                                             \
+      "fma.rn.f64 %6, %13, m5, %6;\n\t"                                                             \
+      "@px add.u32 %7, %7, 1;\n\t"                                                                  \
+      "@py add.u32 %8, %8, 1;\n\t"                                                                  \
+      "@pxy add.u32 %9, %9, 1;\n\t"                                                                 \
+      "@qx add.u32 %10, %10, 1;\n\t"                                                                \
+      "@qy add.u32 %11, %11, 1;\n\t"                                                                \
+      "@qxy add.u32 %12, %12, 1;\n\t"                                                               \
+      "}\n"                                                                                         \
+      : "+d"(A.tot), "+d"(A.fsx), "+d"(A.fsy), "+d"(A.fsxy), "+d"(A.rsx), "+d"(A.rsy), "+d"(A.rsxy), \
+        "+r"(A.fcx), "+r"(A.fcy), "+r"(A.fcxy), "+r"(A.rcx), "+r"(A.rcy), "+r"(A.rcxy)              \
+      : "d"(KK), "d"(XJ), "d"(YJ), "d"(A.Tx), "d"(A.Ty), "d"(A.RTx), "d"(A.RTy))
+
+#define PB_PAIR_W(A, XJ, YJ, KK, WW)                                                                \
+  asm volatile(                                                                                     \
+      "{\n\t"                                                                                       \
+      ".reg .pred px, py, qx, qy, pxy, qxy;\n\t"                                                    \
+      ".reg .f64 m0, m1, m2, m3, m4, m5;\n\t"                                                       \
+      "setp.ge.f64 px, %22, %24;\n\t"                                                               \
+      "setp.ge.f64 py, %23, %25;\n\t"                                                               \
+      "setp.le.f64 qx, %22, %26;\n\t"                                                               \
+      "setp.le.f64 qy, %23, %27;\n\t"                                                               \
+      "and.pred pxy, px, py;\n\t"                                                                   \
+      "and.pred qxy, qx, qy;\n\t"                                                                   \
+      "selp.f64 m0, " PB_ONE ", " PB_ZERO ", px;\n\t"                                               \
+      "selp.f64 m1, " PB_ONE ", " PB_ZERO ", py;\n\t"                                               \
+      "selp.f64 m2, " PB_ONE ", " PB_ZERO ", pxy;\n\t"                                              \
+      "selp.f64 m3, " PB_ONE ", " PB_ZERO ", qx;\n\t"                                               \
+      "selp.f64 m4, " PB_ONE ", " PB_ZERO ", qy;\n\t"                                               \
+      "selp.f64 m5, " PB_ONE ", " PB_ZERO ", qxy;\n\t"                                              \
+      "add.f64 %0, %0, %20;\n\t"                                                                    \
+      "fma.rn.f64 %1, %20, m0, %1;\n\t"                                                             \
+      "fma.rn.f64 %2, %20, m1, %2;\n\t"                                                             \
+      "fma.rn.f64 %3, %20, m2, %3;\n\t"                                                             \
+      "fma.rn.f64 %4, %20, m3, %4;\n\t"                                                             \
+      "fma.rn.f64 %5, %20, m4, %5;\n\t"                                                             \
+      "fma.rn.f64 %6, %20, m5, %6;\n\t"                                                             \
+      "add.f64 %7, %7, %21;\n\t"                                                                    \
+      "fma.rn.f64 %8, %21, m0, %8;\n\t"                                                             \
+      "fma.rn.f64 %9, %21, m1, %9;\n\t"                                                             \
+      "fma.rn.f64 %10, %21, m2, %10;\n\t"                                                           \
+      "fma.rn.f64 %11, %21, m3, %11;\n\t"                                                           \
+      "fma.rn.f64 %12, %21, m4, %12;\n\t"                                                           \
+      "fma.rn.f64 %13, %21, m5, %13;\n\t"                                                           \
+      "@px add.u32 %14, %14, 1;\n\t"                                                                \
+      "@py add.u32 %15, %15, 1;\n\t"                                                                \
+      "@pxy add.u32 %16, %16, 1;\n\t"                                                               \
+      "@qx add.u32 %17, %17, 1;\n\t"                                                                \
+      "@qy add.u32 %18, %18, 1;\n\t"                                                                \
+      "@qxy add.u32 %19, %19, 1;\n\t"                                                               \
+      "}\n"                                                                                         \
+      : "+d"(A.tot), "+d"(A.fsx), "+d"(A.fsy), "+d"(A.fsxy), "+d"(A.rsx), "+d"(A.rsy), "+d"(A.rsxy), \
+        "+d"(A.wtot), "+d"(A.fwx), "+d"(A.fwy), "+d"(A.fwxy), "+d"(A.rwx), "+d"(A.rwy), "+d"(A.rwxy), \
+        "+r"(A.fcx), "+r"(A.fcy), "+r"(A.fcxy), "+r"(A.rcx), "+r"(A.rcy), "+r"(A.rcxy)              \
+      : "d"(KK), "d"(WW), "d"(XJ), "d"(YJ), "d"(A.Tx), "d"(A.Ty), "d"(A.RTx), "d"(A.RTy))
 
 enum { PB_OUT = 0, PB_REG_FULL = 1, PB_REG_CHECK = 2, PB_GENERIC = 3 };
 
@@ -222,29 +292,33 @@ pairbin_kernel(PBParams P) {
       const unsigned n_in = warp_sum_u(A.nin);
       const unsigned fcx = warp_sum_u(A.fcx), fcy = warp_sum_u(A.fcy), fcxy = warp_sum_u(A.fcxy);
       const unsigned rcx = warp_sum_u(A.rcx), rcy = warp_sum_u(A.rcy), rcxy = warp_sum_u(A.rcxy);
-      double fs[4], rs[4], fw[4], rw[4];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        fs[b] = warp_sum(A.fs[b]);
-        rs[b] = warp_sum(A.rs[b]);
-        if constexpr (WEIGHTED) { fw[b] = warp_sum(A.fw[b]); rw[b] = warp_sum(A.rw[b]); }
+      const double tot = warp_sum(A.tot);
+      const double fsx = warp_sum(A.fsx), fsy = warp_sum(A.fsy), fsxy = warp_sum(A.fsxy);
+      const double rsx = warp_sum(A.rsx), rsy = warp_sum(A.rsy), rsxy = warp_sum(A.rsxy);
+      double wtot = 0, fwx = 0, fwy = 0, fwxy = 0, rwx = 0, rwy = 0, rwxy = 0;
+      if constexpr (WEIGHTED) {
+        wtot = warp_sum(A.wtot);
+        fwx = warp_sum(A.fwx); fwy = warp_sum(A.fwy); fwxy = warp_sum(A.fwxy);
+        rwx = warp_sum(A.rwx); rwy = warp_sum(A.rwy); rwxy = warp_sum(A.rwxy);
       }
       if (lane == 0 && n_in) {
-        // inclusion-exclusion: exact integer counts per window bin (index = bx + 2*by)
+        // inclusion-exclusion per window bin (index = bx + 2*by)
         const unsigned fc[4] = {n_in - fcx - fcy + fcxy, fcx - fcxy, fcy - fcxy, fcxy};
         const unsigned rc[4] = {n_in - rcx - rcy + rcxy, rcx - rcxy, rcy - rcxy, rcxy};
+        const double fs[4] = {(tot - fsx) - (fsy - fsxy), fsx - fsxy, fsy - fsxy, fsxy};
+        const double rs[4] = {(tot - rsx) - (rsy - rsxy), rsx - rsxy, rsy - rsxy, rsxy};
+        const double fw[4] = {(wtot - fwx) - (fwy - fwxy), fwx - fwxy, fwy - fwxy, fwxy};
+        const double rw[4] = {(wtot - rwx) - (rwy - rwxy), rwx - rwxy, rwy - rwxy, rwxy};
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          const int fxb = A.fx0 + (b & 1), fyb = A.fy0 + (b >> 1);
           if (fc[b]) {  // a non-empty bin is always inside the grid
-            const int o = fyb * nbins + fxb;
+            const int o = (A.fy0 + (b >> 1)) * nbins + A.fx0 + (b & 1);
             atomicAdd(my_c + o, fc[b]);
             atomicAdd(my_s + o, fs[b]);
             if constexpr (WEIGHTED) atomicAdd(my_w + o, fw[b]);
           }
-          const int rxb = A.rx0 + (b & 1), ryb = A.ry0 + (b >> 1);
           if (rc[b]) {
-            const int o = ryb * nbins + rxb;
+            const int o = (A.ry0 + (b >> 1)) * nbins + A.rx0 + (b & 1);
             atomicAdd(my_c + o, rc[b]);
             atomicAdd(my_s + o, rs[b]);
             if constexpr (WEIGHTED) atomicAdd(my_w + o, rw[b]);
@@ -425,31 +499,55 @@ pairbin_kernel(PBParams P) {
           const int rx0 = cwrx & 0xffff, rx1 = rx0 + (cwrx >> 16), ry0 = cwry & 0xffff, ry1 = ry0 + (cwry >> 16);
           const bool fits = A.fx0 >= 0 && x0 >= A.fx0 && x1 <= A.fx0 + 1 && y0 >= A.fy0 && y1 <= A.fy0 + 1 &&
                             rx0 >= A.rx0 && rx1 <= A.rx0 + 1 && ry0 >= A.ry0 && ry1 <= A.ry0 + 1;
-          if (!fits) {
+          bool reg_ok = true;
+          if (!fits || A.ownerI != loadedI) {
             flush_regs();
             // a window [b0, b0+1] must stay inside the grid unless nbins == 1
             A.fx0 = min(x0, max(nbins - 2, 0)); A.fy0 = min(y0, max(nbins - 2, 0));
             A.rx0 = min(rx0, max(nbins - 2, 0)); A.ry0 = min(ry0, max(nbins - 2, 0));
-            // bx = (bin >= b0 + 1): forward dx >= ed[b0+1]; mirrored -dx >= ed[b0+1] <=> dx <= -ed[b0+1]
-            A.tx = (nbins > 1) ? ed[A.fx0 + 1] : INFINITY;
-            A.ty = (nbins > 1) ? ed[A.fy0 + 1] : INFINITY;
-            A.ntx = (nbins > 1) ? -ed[A.rx0 + 1] : -INFINITY;
-            A.nty = (nbins > 1) ? -ed[A.ry0 + 1] : -INFINITY;
+            A.ownerI = loadedI;
+            // bit = (bin >= b0 + 1): forward dx >= ed[b0+1]; mirrored -dx >= ed[b0+1] <=> dx <= -ed[b0+1];
+            // turned into thresholds on the column coordinate for this lane's row point
+            const double tx = (nbins > 1) ? ed[A.fx0 + 1] : INFINITY, ty = (nbins > 1) ? ed[A.fy0 + 1] : INFINITY;
+            const double ntx = (nbins > 1) ? -ed[A.rx0 + 1] : -INFINITY, nty = (nbins > 1) ? -ed[A.ry0 + 1] : -INFINITY;
+            bool okl = true;
+            A.Tx = pb_coord_ge(xi, tx, okl);
+            A.Ty = pb_coord_ge(yi, ty, okl);
+            A.RTx = pb_coord_le(xi, ntx, okl);
+            A.RTy = pb_coord_le(yi, nty, okl);
+            reg_ok = __all_sync(0xffffffffu, okl);
+            if (!reg_ok) A.fx0 = -1;  // nothing accumulated yet: simply close the window again
           }
-          const double tx = A.tx, ty = A.ty, ntx = A.ntx, nty = A.nty;
+          if (!reg_ok) {
+            // (never seen in practice) per-lane thresholds did not settle: generic path for this block
+            if (live) {
+              for (int jj = j0; jj < j0 + jn; ++jj) {
+                const double2 pj = txy[jj];
+                const double dx = pj.x - xi, dy = pj.y - yi;
+                const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                if (r2 >= lo2 && fabs(dx) < M && fabs(dy) < M) {
+                  const int b1 = pb_bin_twod(dy, M, P.inv_bin, nbins, ed) * nbins + pb_bin_twod(dx, M, P.inv_bin, nbins, ed);
+                  const int b2 = pb_bin_twod(-dy, M, P.inv_bin, nbins, ed) * nbins + pb_bin_twod(-dx, M, P.inv_bin, nbins, ed);
+                  const double kk = ki * tk[jj];
+                  atomicAdd(my_c + b1, 1u); atomicAdd(my_c + b2, 1u);
+                  atomicAdd(my_s + b1, kk); atomicAdd(my_s + b2, kk);
+                  if constexpr (WEIGHTED) { const double ww = wi * tw[jj]; atomicAdd(my_w + b1, ww); atomicAdd(my_w + b2, ww); }
+                }
+              }
+            }
+            __syncwarp();
+            continue;
+          }
           if (ccls == PB_REG_FULL) {
 #pragma unroll 4
             for (int jj = j0; jj < j0 + jn; ++jj) {
               const double2 pj = txy[jj];
-              const double dx = pj.x - xi, dy = pj.y - yi;
-              const double kj = tk[jj];
+              const double kk = ki * tk[jj];
               if constexpr (WEIGHTED) {
-                const double wj = tw[jj];
-                PB_ACCUM_W("ge", A.fs, A.fw, A.fcx, A.fcy, A.fcxy, dx, tx, dy, ty, ki, kj, wi, wj);
-                PB_ACCUM_W("le", A.rs, A.rw, A.rcx, A.rcy, A.rcxy, dx, ntx, dy, nty, ki, kj, wi, wj);
+                const double ww = wi * tw[jj];
+                PB_PAIR_W(A, pj.x, pj.y, kk, ww);
               } else {
-                PB_ACCUM("ge", A.fs, A.fcx, A.fcy, A.fcxy, dx, tx, dy, ty, ki, kj);
-                PB_ACCUM("le", A.rs, A.rcx, A.rcy, A.rcxy, dx, ntx, dy, nty, ki, kj);
+                PB_PAIR(A, pj.x, pj.y, kk);
               }
             }
             A.nin += live ? (unsigned)jn : 0u;
@@ -461,14 +559,12 @@ pairbin_kernel(PBParams P) {
               const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
               const bool ok = r2 >= lo2 && fabs(dx) < M && fabs(dy) < M;  // false for dead lanes (NaN)
               if (ok) {
-                const double kj = tk[jj];
+                const double kk = ki * tk[jj];
                 if constexpr (WEIGHTED) {
-                  const double wj = tw[jj];
-                  PB_ACCUM_W("ge", A.fs, A.fw, A.fcx, A.fcy, A.fcxy, dx, tx, dy, ty, ki, kj, wi, wj);
-                  PB_ACCUM_W("le", A.rs, A.rw, A.rcx, A.rcy, A.rcxy, dx, ntx, dy, nty, ki, kj, wi, wj);
+                  const double ww = wi * tw[jj];
+                  PB_PAIR_W(A, pj.x, pj.y, kk, ww);
                 } else {
-                  PB_ACCUM("ge", A.fs, A.fcx, A.fcy, A.fcxy, dx, tx, dy, ty, ki, kj);
-                  PB_ACCUM("le", A.rs, A.rcx, A.rcy, A.rcxy, dx, ntx, dy, nty, ki, kj);
+                  PB_PAIR(A, pj.x, pj.y, kk);
                 }
                 A.nin += 1u;
               }
