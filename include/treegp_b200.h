@@ -152,12 +152,18 @@ typedef enum {
  *  sumwr          : device double[ncat*nb]  sum w_i w_j r   (LOG only; may be NULL)
  * Outputs are ACCUMULATED into (the caller zeroes them).  xi = sumwkk / sumw is left to the caller
  * so that multi-GPU partial sums can be all-reduced first.
+ *  work           : optional 32-byte aligned device scratch of tgp_pairbin_work_doubles(total, ncat)
+ *                   doubles (bounding boxes of the 32-point chunks, filled by a pre-pass).  NULL: the
+ *                   boxes are recomputed on the fly (slower when most blocks are out of range).
  */
 int tgp_pairbin(const double* px, const double* py, const double* pk, const double* pw,
                 const int64_t* cat_off, int32_t ncat, int64_t max_cat_len, int32_t bin_type,
                 const double* edges, int32_t nbins, double min_sep2, double max_sep,
                 int32_t tile_rank, int32_t tile_nranks, int64_t* npairs, double* sumw,
-                double* sumwkk, double* sumwr, void* stream);
+                double* sumwkk, double* sumwr, double* work, void* stream);
+
+/* Size (in doubles) of the optional scratch buffer of tgp_pairbin. */
+int64_t tgp_pairbin_work_doubles(int64_t total_points, int32_t ncat);
 
 /* Hilbert-curve keys of 2-D points on a 2^order x 2^order grid over the square
  * [xmin, xmin+extent) x [ymin, ymin+extent).  tgp_pairbin is correct for any point order, but when the
@@ -167,7 +173,7 @@ int tgp_pairbin(const double* px, const double* py, const double* pk, const doub
 int tgp_hilbert_keys(const double* x, const double* y, int64_t n, double xmin, double ymin, double extent,
                      int32_t order, int64_t* keys, void* stream);
 
-/* Points per pair tile (informational). */
+/* Points per pair block: 32 (informational). */
 int tgp_pairbin_tile(void);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */

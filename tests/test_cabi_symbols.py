@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
         assert name in _cabi.SIGNATURES, "binding missing for %s" % name
     assert sorted(_cabi.SIGNATURES) == names
     assert lib.tgp_abi_version() == _cabi.ABI_VERSION
-    assert lib.tgp_pairbin_tile() == 256
+    assert lib.tgp_pairbin_tile() == 32
 
 
 def test_invalid_arguments_are_rejected_without_a_gpu():

@@ -162,10 +162,12 @@ def pairbin(px, py, pk, pw, cat_off, max_cat_len, bin_type, edges, nbins, min_se
     sumw = torch.zeros((ncat, nb), dtype=F64, device=dev)
     sumwkk = torch.zeros((ncat, nb), dtype=F64, device=dev)
     sumwr = torch.zeros((ncat, nb), dtype=F64, device=dev) if bin_type == _cabi.BIN_LOG else None
-    check(_cabi.load().tgp_pairbin(_p(px), _p(py), _p(pk), _p(pw), _p(cat_off), ncat, int(max_cat_len),
+    lib = _cabi.load()
+    work = torch.empty(int(lib.tgp_pairbin_work_doubles(int(px.numel()), ncat)), dtype=F64, device=dev)
+    check(lib.tgp_pairbin(_p(px), _p(py), _p(pk), _p(pw), _p(cat_off), ncat, int(max_cat_len),
                                    int(bin_type), _p(edges), int(nbins), float(min_sep) ** 2, float(max_sep),
-                                   int(rank), int(nranks), _p(npairs), _p(sumw), _p(sumwkk), _p(sumwr),
-                                   _stream()), "tgp_pairbin")
+                      int(rank), int(nranks), _p(npairs), _p(sumw), _p(sumwkk), _p(sumwr), _p(work),
+                      _stream()), "tgp_pairbin")
     return npairs, sumw, sumwkk, sumwr
 
 

@@ -15,43 +15,49 @@
 // the formula above sends to bin >= k), so counts are bit-exact with the oracle without FP64
 // division or logarithms on the device; r2 is formed with un-fused mul/add for the same reason.
 //
-// Kernel shape: persistent CTAs walk equal-sized runs of (row-tile, column-tile) pairs of the upper
-// triangle of the pair matrix.  Each thread owns one row point in registers; column tiles are staged
-// in shared memory and read as broadcasts.  Every pair is evaluated individually.
+// Kernel shape (warp-centric, no CTA barriers in the main loop).  The pair matrix is cut into
+// blocks of 32 row points x 32 column points.  A work item is one row block times a run of column
+// chunks; warps of persistent CTAs pull items from a global counter (dynamic load balance: blocks
+// that are provably out of range are skipped, so items differ in cost).  A lane owns one row point in
+// registers; the warp stages one column chunk at a time in its private slice of shared memory and
+// reads it back as broadcasts.  Every pair of a processed block is evaluated individually.
 //
-// Accumulation has two paths, chosen per (warp = 32 row points, chunk = 32 column points):
-//   * REGISTER path.  When the points are spatially sorted (the host sorts along a Hilbert curve,
-//     tgp_hilbert_keys) the displacements of a 32 x 32 block span at most 2 x 2 bins.  The block's
-//     bounding boxes give that window exactly (FP subtraction is monotone), one threshold per axis
-//     decides the bin, and each lane keeps the four bin sums of the forward (dx,dy) and of the
-//     mirrored (-dx,-dy) entry in registers: no atomics in the inner loop.  Counts use
-//     inclusion-exclusion on three integer counters (exact).  Blocks entirely inside the range test
-//     skip it; blocks entirely outside are skipped.  Registers are flushed (warp shuffle reduction,
-//     then one shared-memory add per bin) only when the window moves.
-//   * GENERIC path (unsorted input, wide windows, Log bins, the diagonal block): per-pair bin search
-//     and shared-memory atomics on warp-privatised histograms.
-// Shared histograms are flushed to global memory with red.global once per catalogue.
-// Multi-GPU: runs are dealt round-robin to ranks; the caller all-reduces the bin sums.
+// For 32 chunks at a time each lane derives the bounding box of "its" chunk and classifies the
+// block against the warp's row bounding box (FP subtraction is monotone, so the box gives exact bounds
+// on dx, dy):
+//   OUT        every pair fails the range test                          -> skipped, not even loaded
+//   REG_FULL   every pair passes it and the displacements span <= 2 x 2 bins (both entries)
+//   REG_CHECK  same window, range test needed per pair
+//   GENERIC    wider window (unsorted input), Log bins, the diagonal block
+// REG blocks accumulate in registers (see RegAcc): no atomics in the inner loop; the registers are
+// flushed to the warp's private shared-memory histogram only when the window moves.  When the points
+// are sorted along a Hilbert curve (tgp_hilbert_keys) nearly all blocks are REG; a GENERIC block is
+// first retried as four 8-column sub-blocks.  The GENERIC path does a per-pair bin search and
+// shared-memory atomics.  Histograms go to global memory with red.global when the warp changes
+// catalogue.  Multi-GPU: items are dealt round-robin to ranks; the caller all-reduces the bin sums.
 #include <float.h>
 #include <math.h>
 #include "tgp_common.cuh"
 
-constexpr int PB_T = 256;       // points per tile (rows per CTA = threads per CTA)
-constexpr int PB_WARPS = PB_T / 32;
-constexpr int PB_FLUSH_TILEPAIRS = 100000;  // keeps the 32-bit private counters from overflowing
+constexpr int PB_CHUNK = 32;          // column points per block (= row points per warp)
+constexpr int PB_MAX_WARPS = 8;       // warps per CTA (each owns a private histogram)
+constexpr int PB_FLUSH_ITEMS = 2048;  // keeps the 32-bit private counters from overflowing
 
 struct PBParams {
   const double *px, *py, *pk, *pw;
   const int64_t* cat_off;
   const double* edges;
-  int64_t *npairs;
+  int64_t* npairs;
   double *sumw, *sumwkk, *sumwr;
+  unsigned long long* counter;  // dynamic work counter (zeroed before the launch)
+  const double* boxes;          // optional precomputed chunk bounding boxes (4 doubles per slot) or NULL
   double lo2;       // pairs need r2 >= lo2 (= max(min_sep^2, DBL_TRUE_MIN) for TwoD; min_sep^2 for Log)
   double hi;        // TwoD: max_sep (|dx|,|dy| < hi);  Log: max_sep^2 (r2 < hi)
   double inv_bin;   // TwoD: nbins / (2 max_sep)
-  int64_t items_per_cat, run;  // run = tile pairs per work item
-  int64_t my_items;            // number of work items of this rank
-  int32_t ncat, nbins, nb, ncopy, rank, nranks;
+  int64_t items_per_cat;  // upper bound from max_cat_len
+  int64_t my_items;       // number of work items of this rank
+  int32_t run;            // column chunks per work item (multiple of 32)
+  int32_t ncat, nbins, nb, warps, rank, nranks;
 };
 
 __device__ __forceinline__ int pb_bin_twod(double d, double hi, double inv_bin, int nbins,
@@ -250,41 +256,70 @@ __device__ __forceinline__ double pb_coord_le(double xi, double t, bool& ok) {
 
 enum { PB_OUT = 0, PB_REG_FULL = 1, PB_REG_CHECK = 2, PB_GENERIC = 3 };
 
+// Classification of one (row block, column block) pair from the two bounding boxes.
+// Returns the class; for REG classes w[0..3] receive the packed windows (origin | extent << 16) of the
+// forward x, forward y, mirrored x and mirrored y bins.
+__device__ __forceinline__ int pb_classify_twod(double iminx, double imaxx, double iminy, double imaxy,
+                                                double cminx, double cmaxx, double cminy, double cmaxy,
+                                                double M, double lo2, int nbins, const double* __restrict__ ed,
+                                                int (&w)[4]) {
+  // every dx = x_j - x_i of the block lies in [dx0, dx1] (rounding is monotone)
+  const double dx0 = cminx - imaxx, dx1 = cmaxx - iminx;
+  const double dy0 = cminy - imaxy, dy1 = cmaxy - iminy;
+  const double ax = fmax(fabs(dx0), fabs(dx1)), ay = fmax(fabs(dy0), fabs(dy1));   // max |dx|, |dy|
+  const double nx = dx0 > 0.0 ? dx0 : (dx1 < 0.0 ? -dx1 : 0.0);                    // min |dx|
+  const double ny = dy0 > 0.0 ? dy0 : (dy1 < 0.0 ? -dy1 : 0.0);
+  const double r2max = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
+  const double r2min = __dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny));
+  if (nx >= M || ny >= M || r2max < lo2) return PB_OUT;
+  const int x0 = pb_bin_twod_search(dx0, nbins, ed), x1 = pb_bin_twod_search(dx1, nbins, ed);
+  const int y0 = pb_bin_twod_search(dy0, nbins, ed), y1 = pb_bin_twod_search(dy1, nbins, ed);
+  const int rx0 = pb_bin_twod_search(-dx1, nbins, ed), rx1 = pb_bin_twod_search(-dx0, nbins, ed);
+  const int ry0 = pb_bin_twod_search(-dy1, nbins, ed), ry1 = pb_bin_twod_search(-dy0, nbins, ed);
+  if (x1 - x0 > 1 || y1 - y0 > 1 || rx1 - rx0 > 1 || ry1 - ry0 > 1) return PB_GENERIC;
+  w[0] = x0 | ((x1 - x0) << 16);
+  w[1] = y0 | ((y1 - y0) << 16);
+  w[2] = rx0 | ((rx1 - rx0) << 16);
+  w[3] = ry0 | ((ry1 - ry0) << 16);
+  return (ax < M && ay < M && r2min >= lo2) ? PB_REG_FULL : PB_REG_CHECK;
+}
+
 template <int BT, bool WEIGHTED>
-__global__ void __launch_bounds__(PB_T)
+__global__ void __launch_bounds__(PB_MAX_WARPS * 32)
 pairbin_kernel(PBParams P) {
   extern __shared__ __align__(16) unsigned char pb_smem[];
-  const int nb = P.nb, ncopy = P.ncopy, nbins = P.nbins;
-  double* ed = reinterpret_cast<double*>(pb_smem);                 // nbins + 1 (padded to even)
-  double2* txy = reinterpret_cast<double2*>(ed + ((nbins + 2) & ~1));  // PB_T column points (16-byte aligned)
-  double* tk = reinterpret_cast<double*>(txy + PB_T);              // PB_T
-  double* tw = tk + PB_T;                                          // PB_T
-  double* cbox = tw + PB_T;                                        // PB_WARPS * 4: minx, maxx, miny, maxy per chunk
-  double* hs = cbox + PB_WARPS * 4;                                // ncopy * nb   sum wk wk
-  double* hw = hs + (size_t)ncopy * nb;                            // ncopy * nb   sum w w      (WEIGHTED)
-  double* hr = hw + (WEIGHTED ? (size_t)ncopy * nb : 0);           // ncopy * nb   sum w w r    (LOG)
-  unsigned int* hc = reinterpret_cast<unsigned int*>(hr + (BT == TGP_BIN_LOG ? (size_t)ncopy * nb : 0));  // counts
-
+  const int nb = P.nb, nbins = P.nbins, nwarps = P.warps;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int copy = warp % ncopy;
-  double* my_s = hs + (size_t)copy * nb;
-  double* my_w = hw + (size_t)copy * nb;
-  double* my_r = hr + (size_t)copy * nb;
-  unsigned int* my_c = hc + (size_t)copy * nb;
+  // ---- shared memory: thresholds (CTA), then per warp: column chunk buffer + private histogram ----
+  double* ed = reinterpret_cast<double*>(pb_smem);                          // nbins + 1 (padded to even)
+  double2* cxy_all = reinterpret_cast<double2*>(ed + ((nbins + 2) & ~1));   // [warps][32]
+  double* ck_all = reinterpret_cast<double*>(cxy_all + nwarps * PB_CHUNK);  // [warps][32]
+  double* cw_all = ck_all + nwarps * PB_CHUNK;                              // [warps][32]
+  double* hs_all = cw_all + nwarps * PB_CHUNK;                              // [warps][nb]  sum wk wk
+  double* hw_all = hs_all + (size_t)nwarps * nb;                            // [warps][nb]  sum w w     (WEIGHTED)
+  double* hr_all = hw_all + (WEIGHTED ? (size_t)nwarps * nb : 0);           // [warps][nb]  sum w w r   (LOG)
+  unsigned* hc_all = reinterpret_cast<unsigned*>(hr_all + (BT == TGP_BIN_LOG ? (size_t)nwarps * nb : 0));
+  double2* cxy = cxy_all + warp * PB_CHUNK;
+  double* ck = ck_all + warp * PB_CHUNK;
+  double* cw = cw_all + warp * PB_CHUNK;
+  double* my_s = hs_all + (size_t)warp * nb;
+  double* my_w = hw_all + (size_t)warp * nb;
+  double* my_r = hr_all + (size_t)warp * nb;
+  unsigned* my_c = hc_all + (size_t)warp * nb;
 
-  for (int i = tid; i <= nbins; i += PB_T) ed[i] = P.edges[i];
-  auto clear_hist = [&]() {
-    for (int i = tid; i < ncopy * nb; i += PB_T) {
-      hs[i] = 0.0;
-      hc[i] = 0u;
-      if constexpr (WEIGHTED) hw[i] = 0.0;
-      if (BT == TGP_BIN_LOG) hr[i] = 0.0;
-    }
-  };
+  for (int i = tid; i <= nbins; i += blockDim.x) ed[i] = P.edges[i];
+  for (int i = lane; i < nb; i += 32) {
+    my_s[i] = 0.0;
+    my_c[i] = 0u;
+    if constexpr (WEIGHTED) my_w[i] = 0.0;
+    if (BT == TGP_BIN_LOG) my_r[i] = 0.0;
+  }
+  __syncthreads();  // the only CTA-wide barrier
 
   RegAcc<WEIGHTED> A;
   A.zero();
   A.fx0 = -1;
+  A.ownerI = -1;
   // Move the lane registers of the open window into the warp's shared histogram.
   auto flush_regs = [&]() {
     if (BT != TGP_BIN_TWOD) return;
@@ -311,201 +346,252 @@ pairbin_kernel(PBParams P) {
         const double rw[4] = {(wtot - rwx) - (rwy - rwxy), rwx - rwxy, rwy - rwxy, rwxy};
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          if (fc[b]) {  // a non-empty bin is always inside the grid
+          if (fc[b]) {  // a non-empty bin is always inside the grid; the histogram is private to this warp
             const int o = (A.fy0 + (b >> 1)) * nbins + A.fx0 + (b & 1);
-            atomicAdd(my_c + o, fc[b]);
-            atomicAdd(my_s + o, fs[b]);
-            if constexpr (WEIGHTED) atomicAdd(my_w + o, fw[b]);
+            my_c[o] += fc[b];
+            my_s[o] += fs[b];
+            if constexpr (WEIGHTED) my_w[o] += fw[b];
           }
           if (rc[b]) {
             const int o = (A.ry0 + (b >> 1)) * nbins + A.rx0 + (b & 1);
-            atomicAdd(my_c + o, rc[b]);
-            atomicAdd(my_s + o, rs[b]);
-            if constexpr (WEIGHTED) atomicAdd(my_w + o, rw[b]);
+            my_c[o] += rc[b];
+            my_s[o] += rs[b];
+            if constexpr (WEIGHTED) my_w[o] += rw[b];
           }
         }
       }
+      __syncwarp();
       A.zero();
       A.fx0 = -1;
     }
   };
+  // Warp-private shared histogram -> global (red.global), then clear.
   auto flush_hist = [&](int cat) {
     flush_regs();
-    __syncthreads();
+    __syncwarp();
     if (cat >= 0) {
-      for (int b = tid; b < nb; b += PB_T) {
-        unsigned long long c = 0;
-        double s = 0.0, w = 0.0, r = 0.0;
-        for (int k = 0; k < ncopy; ++k) {
-          c += hc[k * nb + b];
-          s += hs[k * nb + b];
-          if constexpr (WEIGHTED) w += hw[k * nb + b];
-          if (BT == TGP_BIN_LOG) r += hr[k * nb + b];
-        }
+      for (int b = lane; b < nb; b += 32) {
+        const unsigned c = my_c[b];
         if (c) {
           const size_t o = (size_t)cat * nb + b;
-          atomicAdd(reinterpret_cast<unsigned long long*>(P.npairs) + o, c);
-          atomicAdd(P.sumwkk + o, s);
-          atomicAdd(P.sumw + o, WEIGHTED ? w : (double)c);
-          if (BT == TGP_BIN_LOG && P.sumwr) atomicAdd(P.sumwr + o, r);
+          atomicAdd(reinterpret_cast<unsigned long long*>(P.npairs) + o, (unsigned long long)c);
+          atomicAdd(P.sumwkk + o, my_s[b]);
+          atomicAdd(P.sumw + o, WEIGHTED ? my_w[b] : (double)c);
+          if (BT == TGP_BIN_LOG && P.sumwr) atomicAdd(P.sumwr + o, my_r[b]);
+          my_c[b] = 0u;
+          my_s[b] = 0.0;
+          if constexpr (WEIGHTED) my_w[b] = 0.0;
+          if (BT == TGP_BIN_LOG) my_r[b] = 0.0;
         }
       }
     }
-    __syncthreads();
-    clear_hist();
-    __syncthreads();
+    __syncwarp();
   };
-  clear_hist();
-  __syncthreads();
+
+  // per-pair generic accumulation of columns [j0, j0+jn) of the staged chunk; `jfirst` = first column this
+  // lane may pair with (diagonal block: j > i)
+  auto generic_block = [&](int j0, int jn, int jfirst, double xi, double yi, double ki, double wi, bool live) {
+    if (live) {
+      for (int jj = max(j0, jfirst); jj < j0 + jn; ++jj) {
+        const double2 pj = cxy[jj];
+        const double dx = pj.x - xi, dy = pj.y - yi;
+        const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));  // no FMA: matches the oracle bit for bit
+        if (BT == TGP_BIN_TWOD) {
+          if (r2 >= P.lo2 && fabs(dx) < P.hi && fabs(dy) < P.hi) {
+            const int b1 = pb_bin_twod(dy, P.hi, P.inv_bin, nbins, ed) * nbins + pb_bin_twod(dx, P.hi, P.inv_bin, nbins, ed);
+            const int b2 = pb_bin_twod(-dy, P.hi, P.inv_bin, nbins, ed) * nbins + pb_bin_twod(-dx, P.hi, P.inv_bin, nbins, ed);
+            const double kk = ki * ck[jj];
+            atomicAdd(my_c + b1, 1u); atomicAdd(my_c + b2, 1u);
+            atomicAdd(my_s + b1, kk); atomicAdd(my_s + b2, kk);
+            if constexpr (WEIGHTED) { const double ww = wi * cw[jj]; atomicAdd(my_w + b1, ww); atomicAdd(my_w + b2, ww); }
+          }
+        } else {
+          if (r2 >= P.lo2 && r2 < P.hi) {
+            const int b = pb_bin_log(r2, nbins, ed);
+            double ww = 1.0;
+            if constexpr (WEIGHTED) ww = wi * cw[jj];
+            atomicAdd(my_c + b, 1u);
+            atomicAdd(my_s + b, ki * ck[jj]);
+            if constexpr (WEIGHTED) atomicAdd(my_w + b, ww);
+            atomicAdd(my_r + b, ww * sqrt(r2));
+          }
+        }
+      }
+    }
+    __syncwarp();
+  };
 
   const double M = P.hi, lo2 = P.lo2;
+  const int R = P.run;
   int cur_cat = -1;
   int since_flush = 0;
-  for (int64_t q = blockIdx.x; q < P.my_items; q += gridDim.x) {
-    const int64_t item = q * P.nranks + P.rank;
+  while (true) {
+    // ---- next work item for this warp ----
+    unsigned long long q = 0;
+    if (lane == 0) q = atomicAdd(P.counter, 1ull);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if ((int64_t)q >= P.my_items) break;
+    const int64_t item = (int64_t)q * P.nranks + P.rank;
     const int cat = (int)(item / P.items_per_cat);
     if (cat >= P.ncat) break;
-    const int64_t local = item % P.items_per_cat;
+    const int64_t lq = item % P.items_per_cat;
     const int64_t off = P.cat_off[cat];
     const int64_t n = P.cat_off[cat + 1] - off;
-    const int64_t nt = (n + PB_T - 1) / PB_T;
-    const int64_t npair_tiles = nt * (nt + 1) / 2;
-    int64_t p = local * P.run;
-    if (p >= npair_tiles) continue;
-    const int64_t p_end = (p + P.run < npair_tiles) ? (p + P.run) : npair_tiles;
-    if (cat != cur_cat || since_flush >= PB_FLUSH_TILEPAIRS) {
+    const int64_t nblk = (n + PB_CHUNK - 1) / PB_CHUNK;
+    if (nblk == 0) continue;
+    const int64_t nruns = (nblk + R - 1) / R;
+    // decode lq -> (row block ib, run r): rows of group g = ib / R pair with runs g .. nruns-1;
+    // items before group g: R * (g*nruns - g*(g-1)/2)
+    const double tn = 2.0 * (double)nruns + 1.0;
+    const double disc = tn * tn - 8.0 * (double)lq / (double)R;
+    int64_t g = (int64_t)((tn - sqrt(disc > 0.0 ? disc : 0.0)) * 0.5);
+    if (g < 0) g = 0;
+    if (g >= nruns) g = nruns - 1;
+    while (g > 0 && (int64_t)R * (g * nruns - g * (g - 1) / 2) > lq) --g;
+    while (g + 1 < nruns && (int64_t)R * ((g + 1) * nruns - (g + 1) * g / 2) <= lq) ++g;
+    const int64_t rem = lq - (int64_t)R * (g * nruns - g * (g - 1) / 2);
+    const int64_t per_row = nruns - g;
+    const int64_t row_in_g = rem / per_row;
+    const int64_t ib = g * R + row_in_g;
+    const int64_t r = g + rem % per_row;
+    if (row_in_g >= R || ib >= nblk) continue;  // past the end of this (shorter) catalogue
+    const int64_t c_lo = (r * R > ib) ? r * R : ib;
+    const int64_t c_hi = ((r + 1) * R < nblk) ? (r + 1) * R : nblk;
+    if (c_lo >= c_hi) continue;
+
+    if (cat != cur_cat || since_flush >= PB_FLUSH_ITEMS) {
       flush_hist(cur_cat);
       cur_cat = cat;
       since_flush = 0;
     }
-    // p -> (I, J): row-major upper triangle, offset(I) = I*nt - I*(I-1)/2
-    const double tn = 2.0 * (double)nt + 1.0;
-    int64_t I = (int64_t)((tn - sqrt(tn * tn - 8.0 * (double)p)) * 0.5);
-    if (I < 0) I = 0;
-    if (I >= nt) I = nt - 1;
-    while (I > 0 && I * nt - I * (I - 1) / 2 > p) --I;
-    while ((I + 1) * nt - (I + 1) * I / 2 <= p) ++I;
-    int64_t J = I + (p - (I * nt - I * (I - 1) / 2));
+    ++since_flush;
 
-    int64_t loadedI = -1;
-    double xi = 0.0, yi = 0.0, ki = 0.0, wi = 0.0;
-    double ib_minx = 0.0, ib_maxx = 0.0, ib_miny = 0.0, ib_maxy = 0.0;  // bounding box of this warp's rows
-    bool live = false;
-    for (; p < p_end; ++p) {
-      if (I != loadedI) {
-        const int64_t ig = I * PB_T + tid;
-        live = ig < n;
-        // dead lanes: NaN coordinates make every comparison false, zero field/weight adds nothing
-        xi = live ? P.px[off + ig] : __longlong_as_double(0x7ff8000000000000ll);
-        yi = live ? P.py[off + ig] : __longlong_as_double(0x7ff8000000000000ll);
-        wi = live ? (WEIGHTED ? P.pw[off + ig] : 1.0) : 0.0;
-        ki = live ? P.pk[off + ig] * wi : 0.0;
+    // ---- this warp's row points ----
+    const int64_t ig = ib * PB_CHUNK + lane;
+    const bool live = ig < n;
+    // dead lanes: NaN coordinates make every comparison false, zero field/weight adds nothing
+    const double xi = live ? P.px[off + ig] : __longlong_as_double(0x7ff8000000000000ll);
+    const double yi = live ? P.py[off + ig] : __longlong_as_double(0x7ff8000000000000ll);
+    double wi = live ? 1.0 : 0.0;
+    if constexpr (WEIGHTED) wi = live ? P.pw[off + ig] : 0.0;
+    const double ki = live ? P.pk[off + ig] * wi : 0.0;
+    const double iminx = warp_min(live ? xi : INFINITY), imaxx = warp_max(live ? xi : -INFINITY);
+    const double iminy = warp_min(live ? yi : INFINITY), imaxy = warp_max(live ? yi : -INFINITY);
+    const long long owner = (long long)(off + ib * PB_CHUNK);
+
+    for (int64_t sc = c_lo; sc < c_hi; sc += 32) {
+      // ---- lane l classifies column chunk sc + l ----
+      const int64_t mychunk = sc + lane;
+      int cls = PB_OUT;
+      int win[4] = {0, 0, 0, 0};
+      if (mychunk < c_hi) {
+        const int64_t j0g = mychunk * PB_CHUNK;
+        const int cnt = (int)((n - j0g < PB_CHUNK) ? (n - j0g) : PB_CHUNK);
+        double cminx = INFINITY, cmaxx = -INFINITY, cminy = INFINITY, cmaxy = -INFINITY;
+        if (P.boxes) {
+          const double4 bb = *reinterpret_cast<const double4*>(P.boxes + 4 * ((off + j0g) / PB_CHUNK + cat));
+          cminx = bb.x; cmaxx = bb.y; cminy = bb.z; cmaxy = bb.w;
+        } else {
+          const double* xs = P.px + off + j0g;
+          const double* ys = P.py + off + j0g;
+#pragma unroll 8
+          for (int t = 0; t < PB_CHUNK; ++t) {
+            if (t < cnt) {
+              const double x = xs[t], y = ys[t];
+              cminx = fmin(cminx, x); cmaxx = fmax(cmaxx, x);
+              cminy = fmin(cminy, y); cmaxy = fmax(cmaxy, y);
+            }
+          }
+        }
         if (BT == TGP_BIN_TWOD) {
-          ib_minx = warp_min(live ? xi : INFINITY);
-          ib_maxx = warp_max(live ? xi : -INFINITY);
-          ib_miny = warp_min(live ? yi : INFINITY);
-          ib_maxy = warp_max(live ? yi : -INFINITY);
-        }
-        loadedI = I;
-      }
-      __syncthreads();  // previous column tile fully consumed
-      {
-        const int64_t jg = J * PB_T + tid;
-        const bool ok = jg < n;
-        const double x = ok ? P.px[off + jg] : 0.0, y = ok ? P.py[off + jg] : 0.0;
-        txy[tid] = make_double2(x, y);
-        const double w = (ok && WEIGHTED) ? P.pw[off + jg] : 1.0;
-        tk[tid] = ok ? P.pk[off + jg] * w : 0.0;
-        if constexpr (WEIGHTED) tw[tid] = ok ? w : 0.0;
-        if (BT == TGP_BIN_TWOD) {  // chunk `warp` of the column tile: bounding box
-          const double a = warp_min(ok ? x : INFINITY), b = warp_max(ok ? x : -INFINITY);
-          const double c = warp_min(ok ? y : INFINITY), d = warp_max(ok ? y : -INFINITY);
-          if (lane == 0) { cbox[warp * 4 + 0] = a; cbox[warp * 4 + 1] = b; cbox[warp * 4 + 2] = c; cbox[warp * 4 + 3] = d; }
-        }
-      }
-      __syncthreads();
-      const int jcount = (int)((n - J * PB_T < PB_T) ? (n - J * PB_T) : PB_T);
-      const bool diag = (I == J);
-
-      if (BT == TGP_BIN_TWOD) {
-        // ---- lanes 0..7 classify chunks 0..7 of this column tile against this warp's rows ----
-        int cls = PB_OUT, wx = 0, wy = 0, wrx = 0, wry = 0;
-        if (lane < PB_WARPS && lane * 32 < jcount && ib_minx <= ib_maxx) {
-          const double cminx = cbox[lane * 4 + 0], cmaxx = cbox[lane * 4 + 1];
-          const double cminy = cbox[lane * 4 + 2], cmaxy = cbox[lane * 4 + 3];
-          // every dx = x_j - x_i of the block lies in [dx0, dx1] (rounding is monotone)
-          const double dx0 = cminx - ib_maxx, dx1 = cmaxx - ib_minx;
-          const double dy0 = cminy - ib_maxy, dy1 = cmaxy - ib_miny;
-          const double ax = fmax(fabs(dx0), fabs(dx1)), ay = fmax(fabs(dy0), fabs(dy1));   // max |dx|, |dy|
-          const double nx = dx0 > 0.0 ? dx0 : (dx1 < 0.0 ? -dx1 : 0.0);                    // min |dx|
-          const double ny = dy0 > 0.0 ? dy0 : (dy1 < 0.0 ? -dy1 : 0.0);
+          if (mychunk == ib) {
+            cls = PB_GENERIC;  // diagonal block: needs j > i
+          } else {
+            cls = pb_classify_twod(iminx, imaxx, iminy, imaxy, cminx, cmaxx, cminy, cmaxy, M, lo2, nbins, ed, win);
+          }
+        } else {
+          const double dx0 = cminx - imaxx, dx1 = cmaxx - iminx, dy0 = cminy - imaxy, dy1 = cmaxy - iminy;
+          const double ax = fmax(fabs(dx0), fabs(dx1)), ay = fmax(fabs(dy0), fabs(dy1));
+          const double nx = dx0 > 0.0 ? dx0 : (dx1 < 0.0 ? -dx1 : 0.0), ny = dy0 > 0.0 ? dy0 : (dy1 < 0.0 ? -dy1 : 0.0);
           const double r2max = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
           const double r2min = __dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny));
-          if (nx >= M || ny >= M || r2max < lo2) {
-            cls = PB_OUT;
-          } else if (diag && lane <= warp) {
-            // diagonal tile: chunks before this warp's rows hold only j < i; the warp's own chunk needs j > i
-            cls = (lane == warp) ? PB_GENERIC : PB_OUT;
-          } else {
-            const int x0 = pb_bin_twod_search(dx0, nbins, ed), x1 = pb_bin_twod_search(dx1, nbins, ed);
-            const int y0 = pb_bin_twod_search(dy0, nbins, ed), y1 = pb_bin_twod_search(dy1, nbins, ed);
-            const int rx0 = pb_bin_twod_search(-dx1, nbins, ed), rx1 = pb_bin_twod_search(-dx0, nbins, ed);
-            const int ry0 = pb_bin_twod_search(-dy1, nbins, ed), ry1 = pb_bin_twod_search(-dy0, nbins, ed);
-            if (x1 - x0 > 1 || y1 - y0 > 1 || rx1 - rx0 > 1 || ry1 - ry0 > 1) {
-              cls = PB_GENERIC;
-            } else {
-              cls = (ax < M && ay < M && r2min >= lo2) ? PB_REG_FULL : PB_REG_CHECK;
-              wx = x0 | ((x1 - x0) << 16); wy = y0 | ((y1 - y0) << 16);
-              wrx = rx0 | ((rx1 - rx0) << 16); wry = ry0 | ((ry1 - ry0) << 16);
+          cls = (r2max < lo2 || r2min >= M) ? PB_OUT : PB_GENERIC;  // M = max_sep^2 for Log
+          if (mychunk == ib) cls = PB_GENERIC;
+        }
+        if (!(iminx <= imaxx)) cls = PB_OUT;  // no live row in this warp
+      }
+      const unsigned todo = __ballot_sync(0xffffffffu, cls != PB_OUT);
+      // ---- process the non-OUT chunks; the next chunk's points are prefetched into registers ----
+      unsigned rest = todo;
+      double nx_ = 0.0, ny_ = 0.0, nk_ = 0.0, nw_ = 1.0;
+      auto fetch = [&](int c) {
+        const int64_t jg = (sc + c) * PB_CHUNK + lane;
+        const bool ok = jg < n;
+        nx_ = ok ? P.px[off + jg] : 0.0;
+        ny_ = ok ? P.py[off + jg] : 0.0;
+        if constexpr (WEIGHTED) nw_ = ok ? P.pw[off + jg] : 0.0;
+        nk_ = ok ? P.pk[off + jg] * nw_ : 0.0;
+      };
+      if (rest) fetch(__ffs(rest) - 1);
+      while (rest) {
+        const int c = __ffs(rest) - 1;
+        rest &= rest - 1;
+        __syncwarp();  // previous chunk fully consumed
+        cxy[lane] = make_double2(nx_, ny_);
+        ck[lane] = nk_;
+        if constexpr (WEIGHTED) cw[lane] = nw_;
+        __syncwarp();
+        if (rest) fetch(__ffs(rest) - 1);
+        const int64_t j0g = (sc + c) * PB_CHUNK;
+        const int jcount = (int)((n - j0g < PB_CHUNK) ? (n - j0g) : PB_CHUNK);
+        int ccls = __shfl_sync(0xffffffffu, cls, c);
+        if (BT != TGP_BIN_TWOD || (sc + c) == ib) {
+          generic_block(0, jcount, ((sc + c) == ib) ? lane + 1 : 0, xi, yi, ki, wi, live);
+          continue;
+        }
+        int cw4[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cw4[k] = __shfl_sync(0xffffffffu, win[k], c);
+        // a block whose window is too wide is retried as four 8-column sub-blocks
+        const int nsub = (ccls == PB_GENERIC) ? 4 : 1;
+        int scls = ccls;
+        int sw[4] = {cw4[0], cw4[1], cw4[2], cw4[3]};
+        if (nsub == 4) {
+          scls = PB_OUT;
+          if (lane < 4 && lane * 8 < jcount) {
+            double cminx = INFINITY, cmaxx = -INFINITY, cminy = INFINITY, cmaxy = -INFINITY;
+            for (int t = lane * 8; t < min(lane * 8 + 8, jcount); ++t) {
+              const double2 pj = cxy[t];
+              cminx = fmin(cminx, pj.x); cmaxx = fmax(cmaxx, pj.x);
+              cminy = fmin(cminy, pj.y); cmaxy = fmax(cmaxy, pj.y);
             }
+            scls = pb_classify_twod(iminx, imaxx, iminy, imaxy, cminx, cmaxx, cminy, cmaxy, M, lo2, nbins, ed, sw);
           }
         }
-        const int nchunk = (jcount + 31) >> 5;
-        for (int c = 0; c < nchunk; ++c) {
-          const int ccls = __shfl_sync(0xffffffffu, cls, c);
-          if (ccls == PB_OUT) continue;
-          const int j0 = c * 32;
-          const int jn = (jcount - j0 < 32) ? (jcount - j0) : 32;
-          if (ccls == PB_GENERIC) {
-            const int jstart = (diag && c == warp) ? lane + 1 : 0;
-            if (live) {
-              for (int jj = j0 + jstart; jj < j0 + jn; ++jj) {
-                const double2 pj = txy[jj];
-                const double dx = pj.x - xi, dy = pj.y - yi;
-                const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                if (r2 >= lo2 && fabs(dx) < M && fabs(dy) < M) {
-                  const int b1 = pb_bin_twod(dy, M, P.inv_bin, nbins, ed) * nbins + pb_bin_twod(dx, M, P.inv_bin, nbins, ed);
-                  const int b2 = pb_bin_twod(-dy, M, P.inv_bin, nbins, ed) * nbins + pb_bin_twod(-dx, M, P.inv_bin, nbins, ed);
-                  const double kk = ki * tk[jj];
-                  atomicAdd(my_c + b1, 1u);
-                  atomicAdd(my_c + b2, 1u);
-                  atomicAdd(my_s + b1, kk);
-                  atomicAdd(my_s + b2, kk);
-                  if constexpr (WEIGHTED) {
-                    const double ww = wi * tw[jj];
-                    atomicAdd(my_w + b1, ww);
-                    atomicAdd(my_w + b2, ww);
-                  }
-                }
-              }
-            }
-            __syncwarp();
-            continue;
+        for (int sb = 0; sb < nsub; ++sb) {
+          int bcls = scls, bw[4] = {sw[0], sw[1], sw[2], sw[3]};
+          int j0 = 0, jn = jcount;
+          if (nsub == 4) {
+            bcls = __shfl_sync(0xffffffffu, scls, sb);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bw[k] = __shfl_sync(0xffffffffu, sw[k], sb);
+            j0 = sb * 8;
+            jn = min(8, jcount - j0);
+            if (jn <= 0) bcls = PB_OUT;
           }
+          if (bcls == PB_OUT) continue;
+          if (bcls == PB_GENERIC) { generic_block(j0, jn, 0, xi, yi, ki, wi, live); continue; }
           // ---- register path: make sure the open window covers this block ----
-          const int cwx = __shfl_sync(0xffffffffu, wx, c), cwy = __shfl_sync(0xffffffffu, wy, c);
-          const int cwrx = __shfl_sync(0xffffffffu, wrx, c), cwry = __shfl_sync(0xffffffffu, wry, c);
-          const int x0 = cwx & 0xffff, x1 = x0 + (cwx >> 16), y0 = cwy & 0xffff, y1 = y0 + (cwy >> 16);
-          const int rx0 = cwrx & 0xffff, rx1 = rx0 + (cwrx >> 16), ry0 = cwry & 0xffff, ry1 = ry0 + (cwry >> 16);
-          const bool fits = A.fx0 >= 0 && x0 >= A.fx0 && x1 <= A.fx0 + 1 && y0 >= A.fy0 && y1 <= A.fy0 + 1 &&
-                            rx0 >= A.rx0 && rx1 <= A.rx0 + 1 && ry0 >= A.ry0 && ry1 <= A.ry0 + 1;
-          bool reg_ok = true;
-          if (!fits || A.ownerI != loadedI) {
+          const int x0 = bw[0] & 0xffff, x1 = x0 + (bw[0] >> 16), y0 = bw[1] & 0xffff, y1 = y0 + (bw[1] >> 16);
+          const int rx0 = bw[2] & 0xffff, rx1 = rx0 + (bw[2] >> 16), ry0 = bw[3] & 0xffff, ry1 = ry0 + (bw[3] >> 16);
+          const bool fits = A.fx0 >= 0 && A.ownerI == owner && x0 >= A.fx0 && x1 <= A.fx0 + 1 && y0 >= A.fy0 &&
+                            y1 <= A.fy0 + 1 && rx0 >= A.rx0 && rx1 <= A.rx0 + 1 && ry0 >= A.ry0 && ry1 <= A.ry0 + 1;
+          if (!fits) {
             flush_regs();
             // a window [b0, b0+1] must stay inside the grid unless nbins == 1
             A.fx0 = min(x0, max(nbins - 2, 0)); A.fy0 = min(y0, max(nbins - 2, 0));
             A.rx0 = min(rx0, max(nbins - 2, 0)); A.ry0 = min(ry0, max(nbins - 2, 0));
-            A.ownerI = loadedI;
+            A.ownerI = owner;
             // bit = (bin >= b0 + 1): forward dx >= ed[b0+1]; mirrored -dx >= ed[b0+1] <=> dx <= -ed[b0+1];
             // turned into thresholds on the column coordinate for this lane's row point
             const double tx = (nbins > 1) ? ed[A.fx0 + 1] : INFINITY, ty = (nbins > 1) ? ed[A.fy0 + 1] : INFINITY;
@@ -515,36 +601,20 @@ pairbin_kernel(PBParams P) {
             A.Ty = pb_coord_ge(yi, ty, okl);
             A.RTx = pb_coord_le(xi, ntx, okl);
             A.RTy = pb_coord_le(yi, nty, okl);
-            reg_ok = __all_sync(0xffffffffu, okl);
-            if (!reg_ok) A.fx0 = -1;  // nothing accumulated yet: simply close the window again
-          }
-          if (!reg_ok) {
-            // (never seen in practice) per-lane thresholds did not settle: generic path for this block
-            if (live) {
-              for (int jj = j0; jj < j0 + jn; ++jj) {
-                const double2 pj = txy[jj];
-                const double dx = pj.x - xi, dy = pj.y - yi;
-                const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                if (r2 >= lo2 && fabs(dx) < M && fabs(dy) < M) {
-                  const int b1 = pb_bin_twod(dy, M, P.inv_bin, nbins, ed) * nbins + pb_bin_twod(dx, M, P.inv_bin, nbins, ed);
-                  const int b2 = pb_bin_twod(-dy, M, P.inv_bin, nbins, ed) * nbins + pb_bin_twod(-dx, M, P.inv_bin, nbins, ed);
-                  const double kk = ki * tk[jj];
-                  atomicAdd(my_c + b1, 1u); atomicAdd(my_c + b2, 1u);
-                  atomicAdd(my_s + b1, kk); atomicAdd(my_s + b2, kk);
-                  if constexpr (WEIGHTED) { const double ww = wi * tw[jj]; atomicAdd(my_w + b1, ww); atomicAdd(my_w + b2, ww); }
-                }
-              }
+            if (!__all_sync(0xffffffffu, okl)) {
+              // (never seen in practice) the per-lane thresholds did not settle: generic path for this block
+              A.fx0 = -1;
+              generic_block(j0, jn, 0, xi, yi, ki, wi, live);
+              continue;
             }
-            __syncwarp();
-            continue;
           }
-          if (ccls == PB_REG_FULL) {
+          if (bcls == PB_REG_FULL) {
 #pragma unroll 4
             for (int jj = j0; jj < j0 + jn; ++jj) {
-              const double2 pj = txy[jj];
-              const double kk = ki * tk[jj];
+              const double2 pj = cxy[jj];
+              const double kk = ki * ck[jj];
               if constexpr (WEIGHTED) {
-                const double ww = wi * tw[jj];
+                const double ww = wi * cw[jj];
                 PB_PAIR_W(A, pj.x, pj.y, kk, ww);
               } else {
                 PB_PAIR(A, pj.x, pj.y, kk);
@@ -554,14 +624,14 @@ pairbin_kernel(PBParams P) {
           } else {
 #pragma unroll 2
             for (int jj = j0; jj < j0 + jn; ++jj) {
-              const double2 pj = txy[jj];
+              const double2 pj = cxy[jj];
               const double dx = pj.x - xi, dy = pj.y - yi;
               const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
               const bool ok = r2 >= lo2 && fabs(dx) < M && fabs(dy) < M;  // false for dead lanes (NaN)
               if (ok) {
-                const double kk = ki * tk[jj];
+                const double kk = ki * ck[jj];
                 if constexpr (WEIGHTED) {
-                  const double ww = wi * tw[jj];
+                  const double ww = wi * cw[jj];
                   PB_PAIR_W(A, pj.x, pj.y, kk, ww);
                 } else {
                   PB_PAIR(A, pj.x, pj.y, kk);
@@ -571,42 +641,51 @@ pairbin_kernel(PBParams P) {
             }
           }
         }
-      } else {
-        // ---- Log bins: generic path ----
-        const int jstart = diag ? tid + 1 : 0;  // diagonal tile: j > i only
-        if (live) {
-          for (int jj = jstart; jj < jcount; ++jj) {
-            const double2 pj = txy[jj];
-            const double dx = pj.x - xi, dy = pj.y - yi;
-            const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));  // no FMA: matches the oracle bit for bit
-            if (r2 >= lo2 && r2 < M) {
-              const int b = pb_bin_log(r2, nbins, ed);
-              const double ww = WEIGHTED ? wi * tw[jj] : 1.0;
-              atomicAdd(my_c + b, 1u);
-              atomicAdd(my_s + b, ki * tk[jj]);
-              if constexpr (WEIGHTED) atomicAdd(my_w + b, ww);
-              atomicAdd(my_r + b, ww * sqrt(r2));
-            }
-          }
-        }
       }
-      ++since_flush;
-      if (++J == nt) { ++I; J = I; }
     }
-    // the per-lane 32-bit counters are bounded by the flush policy below: flush the registers at
-    // the end of every work item (cheap: once per `run` tile pairs)
+    // bound the per-lane 32-bit counters: registers go to shared memory at the end of every item
     flush_regs();
   }
   flush_hist(cur_cat);
 }
 
-extern "C" int tgp_pairbin_tile(void) { return PB_T; }
+// Pre-pass: bounding box of every 32-point chunk of every catalogue (one warp per chunk).
+// Slot of chunk c of catalogue `cat`: (cat_off[cat] + 32 c) / 32 + cat  (distinct and monotone).
+__global__ void __launch_bounds__(256)
+pairbin_boxes_kernel(const double* __restrict__ px, const double* __restrict__ py, const int64_t* __restrict__ cat_off,
+                     int32_t ncat, int64_t chunks_per_cat, double* __restrict__ boxes) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t cat = w / chunks_per_cat, c = w % chunks_per_cat;
+  if (cat >= ncat) return;
+  const int64_t off = cat_off[cat], n = cat_off[cat + 1] - off;
+  const int64_t j = c * PB_CHUNK + lane;
+  if (c * PB_CHUNK >= n) return;
+  const bool ok = j < n;
+  const double x = ok ? px[off + j] : 0.0, y = ok ? py[off + j] : 0.0;
+  const double a = warp_min(ok ? x : INFINITY), b = warp_max(ok ? x : -INFINITY);
+  const double cc = warp_min(ok ? y : INFINITY), d = warp_max(ok ? y : -INFINITY);
+  if (lane == 0) {
+    double* o = boxes + 4 * ((off + c * PB_CHUNK) / PB_CHUNK + cat);
+    o[0] = a; o[1] = b; o[2] = cc; o[3] = d;
+  }
+}
+
+extern "C" int tgp_pairbin_tile(void) { return PB_CHUNK; }
+
+extern "C" int64_t tgp_pairbin_work_doubles(int64_t total_points, int32_t ncat) {
+  return 4 * (total_points / PB_CHUNK + (int64_t)ncat + 2);
+}
+
+// ring of work counters so that launches on different streams do not share one
+constexpr int PB_COUNTER_SLOTS = 64;
+__device__ unsigned long long g_pb_counters[PB_COUNTER_SLOTS];
 
 extern "C" int tgp_pairbin(const double* px, const double* py, const double* pk, const double* pw,
                            const int64_t* cat_off, int32_t ncat, int64_t max_cat_len, int32_t bin_type,
                            const double* edges, int32_t nbins, double min_sep2, double max_sep,
                            int32_t tile_rank, int32_t tile_nranks, int64_t* npairs, double* sumw,
-                           double* sumwkk, double* sumwr, void* stream) {
+                           double* sumwkk, double* sumwr, double* work, void* stream) {
   TGP_CHECK_ARG(bin_type == TGP_BIN_TWOD || bin_type == TGP_BIN_LOG, "bin_type");
   TGP_CHECK_ARG(ncat >= 0 && max_cat_len >= 0 && nbins >= 1, "ncat/max_cat_len/nbins");
   TGP_CHECK_ARG(tile_nranks >= 1 && tile_rank >= 0 && tile_rank < tile_nranks, "rank");
@@ -633,40 +712,66 @@ extern "C" int tgp_pairbin(const double* px, const double* py, const double* pk,
   }
   const bool weighted = pw != nullptr;
 
-  // shared-memory budget -> number of private histogram copies
-  const size_t per_copy = (size_t)P.nb * (8 + 4 + (weighted ? 8 : 0) + (twod ? 0 : 8));
-  const size_t fixed = (size_t)((nbins + 2) & ~1) * 8 + 4 * PB_T * 8 + PB_WARPS * 4 * 8;
+  // shared memory: every warp owns a private histogram; the budget decides the warps per CTA
+  const size_t per_warp = (size_t)P.nb * (8 + 4 + (weighted ? 8 : 0) + (twod ? 0 : 8)) + PB_CHUNK * (16 + 8 + 8) + 16;
+  const size_t fixed = (size_t)((nbins + 2) & ~1) * 8;
   const size_t budget = 200 * 1024;
-  TGP_CHECK_ARG(fixed + per_copy <= budget, "too many bins for the shared-memory histogram");
-  int ncopy = (int)((budget - fixed) / per_copy);
-  if (ncopy > PB_WARPS) ncopy = PB_WARPS;
-  // keep at least 2 CTAs per SM when that costs no privatisation below 4 copies
-  while (ncopy > 4 && fixed + ncopy * per_copy > 100 * 1024) --ncopy;
-  P.ncopy = ncopy;
-  const size_t smem = fixed + (size_t)ncopy * per_copy;
-
-  // work decomposition
-  const int64_t nt = tgp_cdiv(max_cat_len, PB_T);
-  const int64_t tile_pairs = nt * (nt + 1) / 2;
+  TGP_CHECK_ARG(fixed + per_warp <= budget, "too many bins for the shared-memory histogram");
+  int warps = (int)((100 * 1024 - fixed) / per_warp);  // aim at two CTAs per SM
+  if (warps < 1) warps = (int)((budget - fixed) / per_warp);
+  if (warps > PB_MAX_WARPS) warps = PB_MAX_WARPS;
+  if (warps < 1) warps = 1;
+  P.warps = warps;
+  const size_t smem = fixed + (size_t)warps * per_warp + 64;
   const int sms = tgp_num_sms();
-  const int ctas_per_sm = (smem <= 100 * 1024) ? 2 : 1;
+  const int ctas_per_sm = (2 * smem <= 220 * 1024) ? 2 : 1;
   const int64_t grid_target = (int64_t)sms * ctas_per_sm;
-  // aim for >= 16 work items per CTA over the whole batch, runs of at most 64 tile pairs
-  int64_t run = (tile_pairs * ncat) / (grid_target * 16 * tile_nranks);
-  if (run < 1) run = 1;
-  if (run > 64) run = 64;
-  P.run = run;
-  P.items_per_cat = tgp_cdiv(tile_pairs, run);
+
+  // work decomposition: item = 32 row points x a run of `run` column chunks
+  const int64_t nblk = tgp_cdiv(max_cat_len, PB_CHUNK);
+  const double chunk_pairs = 0.5 * (double)nblk * (double)nblk * (double)ncat;
+  const double slots = (double)grid_target * warps * tile_nranks;
+  int64_t run = (int64_t)(chunk_pairs / (slots * 32.0));  // >= ~32 items per warp slot
+  run = (run / 32) * 32;
+  if (run < 32) run = 32;
+  if (run > 256) run = 256;
+  P.run = (int32_t)run;
+  const int64_t nruns = tgp_cdiv(nblk, run);
+  // items of one catalogue: groups g of `run` rows pair with runs g..nruns-1
+  int64_t items = 0;
+  for (int64_t g = 0; g < nruns; ++g) {
+    const int64_t rows = (nblk - g * run < run) ? (nblk - g * run) : run;
+    items += rows * (nruns - g);
+  }
+  // the decode assumes full groups; the upper bound below covers the (shorter) last group too
+  P.items_per_cat = run * (nruns * nruns - nruns * (nruns - 1) / 2);
+  (void)items;
   const int64_t total_items = P.items_per_cat * ncat;
   P.my_items = (total_items - tile_rank + tile_nranks - 1) / tile_nranks;
   if (P.my_items <= 0) return TGP_OK;
-  const int64_t grid = P.my_items < grid_target ? P.my_items : grid_target;
+  int64_t grid = tgp_cdiv(P.my_items, warps);
+  if (grid > grid_target) grid = grid_target;
+
+  P.boxes = nullptr;
+  if (work) {
+    TGP_CHECK_ARG(((uintptr_t)work % 32) == 0, "work must be 32-byte aligned");
+    const int64_t warps_needed = nblk * ncat;
+    pairbin_boxes_kernel<<<(unsigned)tgp_cdiv(warps_needed * 32, 256), 256, 0, st>>>(px, py, cat_off, ncat, nblk, work);
+    TGP_LAUNCH_CHECK();
+    P.boxes = work;
+  }
+
+  static unsigned launch_seq = 0;
+  void* cbase = nullptr;
+  TGP_CUDA(cudaGetSymbolAddress(&cbase, g_pb_counters));
+  P.counter = reinterpret_cast<unsigned long long*>(cbase) + (launch_seq++ % PB_COUNTER_SLOTS);
+  TGP_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), st));
 
 #define TGP_PB_LAUNCH(BT, W)                                                                          \
   do {                                                                                                \
     TGP_CUDA(cudaFuncSetAttribute(pairbin_kernel<BT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   (int)budget));                                                      \
-    pairbin_kernel<BT, W><<<(unsigned)grid, PB_T, smem, st>>>(P);                                     \
+    pairbin_kernel<BT, W><<<(unsigned)grid, warps * 32, smem, st>>>(P);                               \
   } while (0)
   if (twod) {
     if (weighted) TGP_PB_LAUNCH(TGP_BIN_TWOD, true); else TGP_PB_LAUNCH(TGP_BIN_TWOD, false);
