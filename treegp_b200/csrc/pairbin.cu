@@ -135,40 +135,47 @@ struct RegAcc {
   }
 };
 
-// next representable double above / below (finite inputs; NaN and the matching infinity are returned unchanged)
-__device__ __forceinline__ double pb_next_up(double v) {
-  if (!(v < INFINITY)) return v;
-  if (v == 0.0) return __longlong_as_double(1ll);
-  const long long b = __double_as_longlong(v);
-  return __longlong_as_double(v > 0.0 ? b + 1 : b - 1);
+// Monotone map between doubles and signed integers (order-preserving; -0.0 and +0.0 share key 0).
+__device__ __forceinline__ long long pb_key(double d) {
+  const long long b = __double_as_longlong(d);
+  return b >= 0 ? b : -(b & 0x7fffffffffffffffll);
 }
-__device__ __forceinline__ double pb_next_down(double v) {
-  if (!(v > -INFINITY)) return v;
-  if (v == 0.0) return __longlong_as_double((long long)0x8000000000000001ull);
-  const long long b = __double_as_longlong(v);
-  return __longlong_as_double(v > 0.0 ? b - 1 : b + 1);
+__device__ __forceinline__ double pb_unkey(long long k) {
+  return __longlong_as_double(k >= 0 ? k : (long long)(0x8000000000000000ull | (unsigned long long)(-k)));
 }
 
-// Smallest X with fl(X - xi) >= t.  `ok` is cleared if the short search did not settle (the caller
-// then uses the generic path).  NaN in -> NaN out (dead lanes: every comparison false).
+// Smallest X with fl(X - xi) >= t.  X -> fl(X - xi) is monotone, so the answer is found by bisection over
+// the ordered doubles inside a bracket of a few ulp(t) + ulp(t + xi) around t + xi.  `ok` is cleared if no
+// bracket was found (the caller then uses the generic path).  NaN xi -> NaN (dead lanes: every comparison
+// false); infinite t is returned unchanged (nbins == 1: the bit is constant).
 __device__ __forceinline__ double pb_coord_ge(double xi, double t, bool& ok) {
   if (isinf(t) || isnan(xi)) return isnan(xi) ? xi : t;
-  double c = t + xi;
-  int it = 0;
-  while ((c - xi) < t && it < 16) { c = pb_next_up(c); ++it; }
-  while ((pb_next_down(c) - xi) >= t && it < 32) { c = pb_next_down(c); ++it; }
-  if (!((c - xi) >= t) || ((pb_next_down(c) - xi) >= t)) ok = false;
-  return c;
+  const double c = t + xi;
+  double e = (fabs(t) + fabs(c)) * 0x1p-50 + 0x1p-1060;
+  double lo = c - e, hi = c + e;
+  for (int it = 0; it < 8 && (!((hi - xi) >= t) || ((lo - xi) >= t)); ++it) { e *= 8.0; lo = c - e; hi = c + e; }
+  if (!((hi - xi) >= t) || ((lo - xi) >= t)) { ok = false; return c; }
+  long long klo = pb_key(lo), khi = pb_key(hi);  // pred(lo) false, pred(hi) true
+  while (khi - klo > 1) {
+    const long long mid = klo + ((khi - klo) >> 1);
+    if ((pb_unkey(mid) - xi) >= t) khi = mid; else klo = mid;
+  }
+  return pb_unkey(khi);
 }
 // Largest X with fl(X - xi) <= t.
 __device__ __forceinline__ double pb_coord_le(double xi, double t, bool& ok) {
   if (isinf(t) || isnan(xi)) return isnan(xi) ? xi : t;
-  double c = t + xi;
-  int it = 0;
-  while ((c - xi) > t && it < 16) { c = pb_next_down(c); ++it; }
-  while ((pb_next_up(c) - xi) <= t && it < 32) { c = pb_next_up(c); ++it; }
-  if (!((c - xi) <= t) || ((pb_next_up(c) - xi) <= t)) ok = false;
-  return c;
+  const double c = t + xi;
+  double e = (fabs(t) + fabs(c)) * 0x1p-50 + 0x1p-1060;
+  double lo = c - e, hi = c + e;
+  for (int it = 0; it < 8 && (!((lo - xi) <= t) || ((hi - xi) <= t)); ++it) { e *= 8.0; lo = c - e; hi = c + e; }
+  if (!((lo - xi) <= t) || ((hi - xi) <= t)) { ok = false; return c; }
+  long long klo = pb_key(lo), khi = pb_key(hi);  // pred(lo) true, pred(hi) false
+  while (khi - klo > 1) {
+    const long long mid = klo + ((khi - klo) >> 1);
+    if ((pb_unkey(mid) - xi) <= t) klo = mid; else khi = mid;
+  }
+  return pb_unkey(klo);
 }
 
 // One pair into the window registers.  Written in PTX: four compares give the window bits of the
