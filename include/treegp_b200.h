@@ -176,6 +176,10 @@ int tgp_hilbert_keys(const double* x, const double* y, int64_t n, double xmin, d
 /* Points per pair block: 32 (informational). */
 int tgp_pairbin_tile(void);
 
+/* Tuning knobs for experiments (not needed for normal use).  "gemm_config": -1 automatic,
+ * 0 = 128x128 CTA tile (1 CTA/SM), 1 = 128x64 CTA tile (2 CTAs/SM). */
+int tgp_set_option(const char* name, int value);
+
 /* ---- measurement helpers --------------------------------------------------------------------- */
 
 /* FP64 micro-peaks used as roofline denominators.  kind 0: DFMA (FP64 FMA pipe), 1: DMMA

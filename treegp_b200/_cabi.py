@@ -48,6 +48,7 @@ SIGNATURES = {
     "tgp_pairbin_work_doubles": [_i64, _i32],
     "tgp_hilbert_keys": [_vp, _vp, _i64, _f64, _f64, _f64, _i32, _vp, _vp],
     "tgp_pairbin_tile": [],
+    "tgp_set_option": [ctypes.c_char_p, ctypes.c_int],
     "tgp_microbench_fp64": [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)],
 }
 _RESTYPES = {"tgp_last_error": ctypes.c_char_p, "tgp_pairbin_work_doubles": ctypes.c_int64}

@@ -188,6 +188,10 @@ def hilbert_order(px, py):
     return torch.argsort(keys)
 
 
+def set_option(name, value):
+    check(_cabi.load().tgp_set_option(name.encode(), int(value)), "tgp_set_option")
+
+
 def microbench_fp64(kind, iters=20000):
     require_cuda()
     v = ctypes.c_double(0.0)

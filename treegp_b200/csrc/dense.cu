@@ -19,14 +19,13 @@
 // The O(N^2 nb) parts (64x64 potf2, 64-wide triangular panel solve) are FP64-ALU kernels.
 #include <float.h>
 #include <math.h>
+#include <string.h>
 #include "tgp_common.cuh"
 
 // ============================================================================================
 // gemm_nt_sub
 // ============================================================================================
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, GEMM_THREADS = 256;
-constexpr int STAGE_DOUBLES = (BM + BN) * BK;                 // 4096 doubles = 32 KB
-constexpr int GEMM_SMEM = STAGES * STAGE_DOUBLES * 8;          // 128 KB
+constexpr int BM = 128, BK = 16, STAGES = 4, GEMM_THREADS = 256;
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, int src_bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -43,8 +42,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// Load one BK-wide stage of a (rows x BK) operand tile: `rows` = 128, 8 chunks of 16 B per row.
+// Load one BK-wide stage of a (ROWS x BK) operand tile: 8 chunks of 16 B per row.
 // Chunk c of row r is stored at physical chunk c ^ ((r & 1) << 2).
+template <int ROWS>
 __device__ __forceinline__ void load_operand_stage(double* smem, const double* __restrict__ G,
                                                    int64_t ldg, int64_t row0, int64_t nrows,
                                                    int64_t k0, int64_t Kd, int tid) {
@@ -54,7 +54,7 @@ __device__ __forceinline__ void load_operand_stage(double* smem, const double* _
   int kbytes = (int)((Kd - k) * 8);
   kbytes = kbytes < 0 ? 0 : (kbytes > 16 ? 16 : kbytes);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  for (int i = 0; i < ROWS / 32; ++i) {
     const int r = rbase + 32 * i;
     const int64_t gr = row0 + r;
     const bool ok = gr < nrows;
@@ -65,30 +65,39 @@ __device__ __forceinline__ void load_operand_stage(double* smem, const double* _
 }
 
 // C (M x Nc) -= A (M x Kd) * B^T (Nc x Kd).  lower_only: skip tiles above the diagonal and mask n > m.
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// CTA tile BM x BN_, 8 warps arranged WARPS_M x WARPS_N.  Two configurations are instantiated:
+//   <128, 2, 4, 1>: 128 x 128 tile, warp tile 64 x 32, one CTA per SM (largest operand reuse);
+//   < 64, 4, 2, 2>: 128 x  64 tile, warp tile 32 x 32, two CTAs per SM so that the epilogue (C read-modify-
+//                   write) and the pipeline fill of one CTA hide under the DMMA work of the other.
+template <int BN_, int WARPS_M, int WARPS_N, int MIN_CTAS>
+__global__ void __launch_bounds__(GEMM_THREADS, MIN_CTAS)
 gemm_nt_sub_kernel(double* __restrict__ C, int64_t M, int64_t Nc, int64_t ldc,
                    const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
                    int64_t Kd, int lower_only) {
+  constexpr int WM = BM / WARPS_M, WN = BN_ / WARPS_N;   // warp tile
+  constexpr int MB = WM / 8, NBK = WN / 8;                // 8x8 blocks per warp tile
+  constexpr int STAGE_D = (BM + BN_) * BK;
+  static_assert(WARPS_M * WARPS_N == 8, "8 warps");
   extern __shared__ __align__(16) double gsm[];
-  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN_;
   if (lower_only && n0 > m0 + BM - 1) return;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm0 = (warp >> 2) * 64, wn0 = (warp & 3) * 32;
+  const int wm0 = (warp / WARPS_N) * WM, wn0 = (warp % WARPS_N) * WN;
   const int g = lane >> 2, t = lane & 3;
 
-  double acc[8][4][2];
+  double acc[MB][NBK][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MB; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NBK; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   const int KT_ = (int)((Kd + BK - 1) / BK);
   auto issue = [&](int kt) {
     if (kt < KT_) {
-      double* sa = gsm + (kt % STAGES) * STAGE_DOUBLES;
+      double* sa = gsm + (kt % STAGES) * STAGE_D;
       double* sb = sa + BM * BK;
-      load_operand_stage(sa, A, lda, m0, M, (int64_t)kt * BK, Kd, tid);
-      load_operand_stage(sb, B, ldb, n0, Nc, (int64_t)kt * BK, Kd, tid);
+      load_operand_stage<BM>(sa, A, lda, m0, M, (int64_t)kt * BK, Kd, tid);
+      load_operand_stage<BN_>(sb, B, ldb, n0, Nc, (int64_t)kt * BK, Kd, tid);
     }
     cp_async_commit();
   };
@@ -100,37 +109,37 @@ gemm_nt_sub_kernel(double* __restrict__ C, int64_t M, int64_t Nc, int64_t ldc,
     cp_async_wait<STAGES - 2>();
     __syncthreads();
     issue(kt + STAGES - 1);
-    const double* sa = gsm + (kt % STAGES) * STAGE_DOUBLES;
+    const double* sa = gsm + (kt % STAGES) * STAGE_D;
     const double* sb = sa + BM * BK;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int pc = (h * 4 + t) ^ swz;
-      double2 af[8], bf[4];
+      double2 af[MB], bf[NBK];
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MB; ++i)
         af[i] = *reinterpret_cast<const double2*>(sa + ((wm0 + i * 8 + g) * 8 + pc) * 2);
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < NBK; ++j)
         bf[j] = *reinterpret_cast<const double2*>(sb + ((wn0 + j * 8 + g) * 8 + pc) * 2);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MB; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
+        for (int j = 0; j < NBK; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i].x, bf[j].x);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < MB; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y);
+        for (int j = 0; j < NBK; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i].y, bf[j].y);
     }
   }
   cp_async_wait<0>();
 
   const bool vec = ((ldc & 1) == 0) && ((((uintptr_t)C) & 15) == 0);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < MB; ++i) {
     const int64_t r = m0 + wm0 + i * 8 + g;
     if (r >= M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NBK; ++j) {
       const int64_t c = n0 + wn0 + j * 8 + 2 * t;
       bool ok0 = c < Nc, ok1 = c + 1 < Nc;
       if (lower_only) {
@@ -151,21 +160,40 @@ gemm_nt_sub_kernel(double* __restrict__ C, int64_t M, int64_t Nc, int64_t ldc,
   }
 }
 
+static int g_gemm_config = -1;  // -1: pick by shape; 0: 128x128; 1: 128x64 (tgp_set_option for experiments)
+
+template <int BN_, int WARPS_M, int WARPS_N, int MIN_CTAS>
+static int gemm_launch_cfg(double* C, int64_t M, int64_t Nc, int64_t ldc, const double* A, int64_t lda,
+                           const double* B, int64_t ldb, int64_t Kd, int lower_only, cudaStream_t st) {
+  constexpr int SMEM = STAGES * (BM + BN_) * BK * 8;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TGP_CUDA(cudaFuncSetAttribute(gemm_nt_sub_kernel<BN_, WARPS_M, WARPS_N, MIN_CTAS>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)tgp_cdiv(Nc, BN_), (unsigned)tgp_cdiv(M, BM));
+  TGP_CHECK_ARG(grid.y <= 65535u, "M too large for one launch");
+  gemm_nt_sub_kernel<BN_, WARPS_M, WARPS_N, MIN_CTAS><<<grid, GEMM_THREADS, SMEM, st>>>(C, M, Nc, ldc, A, lda, B, ldb,
+                                                                                       Kd, lower_only);
+  TGP_LAUNCH_CHECK();
+  return TGP_OK;
+}
+
 static int gemm_nt_sub_launch(double* C, int64_t M, int64_t Nc, int64_t ldc, const double* A, int64_t lda,
                               const double* B, int64_t ldb, int64_t Kd, int lower_only, cudaStream_t st) {
   if (M <= 0 || Nc <= 0 || Kd <= 0) return TGP_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TGP_CUDA(cudaFuncSetAttribute(gemm_nt_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    attr_set = true;
-  }
   TGP_CHECK_ARG((lda % 2 == 0) && (ldb % 2 == 0), "leading dimensions must be even (16-byte rows)");
   TGP_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), "operands must be 16-byte aligned");
-  dim3 grid((unsigned)tgp_cdiv(Nc, BN), (unsigned)tgp_cdiv(M, BM));
-  TGP_CHECK_ARG(grid.y <= 65535u, "M too large for one launch");
-  gemm_nt_sub_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(C, M, Nc, ldc, A, lda, B, ldb, Kd, lower_only);
-  TGP_LAUNCH_CHECK();
-  return TGP_OK;
+  const int cfg = g_gemm_config >= 0 ? g_gemm_config : 1;
+  if (cfg == 0) return gemm_launch_cfg<128, 2, 4, 1>(C, M, Nc, ldc, A, lda, B, ldb, Kd, lower_only, st);
+  return gemm_launch_cfg<64, 4, 2, 2>(C, M, Nc, ldc, A, lda, B, ldb, Kd, lower_only, st);
+}
+
+extern "C" int tgp_set_option(const char* name, int value) {
+  if (name && !strcmp(name, "gemm_config")) { g_gemm_config = value; return TGP_OK; }
+  tgp_set_error("tgp_set_option: unknown option");
+  return TGP_ERR_INVALID;
 }
 
 // ============================================================================================
@@ -174,38 +202,48 @@ static int gemm_nt_sub_launch(double* C, int64_t M, int64_t Nc, int64_t ldc, con
 constexpr int NB = 64;           // inner block
 constexpr int NB_PITCH = NB + 1;
 
-__global__ void __launch_bounds__(256)
+// One thread per row (64 threads): row i of the lower triangle lives in registers, column j is
+// broadcast through shared memory, the trailing update of a row is a run of independent FMAs.
+__global__ void __launch_bounds__(NB)
 potf2_kernel(double* __restrict__ A, int n, int64_t ld, int32_t* __restrict__ info, int64_t global_off) {
   __shared__ double S[NB * NB_PITCH];
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < n * NB; idx += blockDim.x) {
-    const int i = idx / NB, j = idx % NB;
-    S[i * NB_PITCH + j] = (j <= i && j < n) ? A[(int64_t)i * ld + j] : 0.0;
+  __shared__ double col[NB];
+  __shared__ double piv_s;
+  const int i = threadIdx.x;
+  for (int idx = i; idx < NB * NB; idx += NB) {
+    const int r = idx / NB, c = idx % NB;  // coalesced along c
+    S[r * NB_PITCH + c] = (r < n && c <= r) ? A[(int64_t)r * ld + c] : (r == c ? 1.0 : 0.0);
   }
   __syncthreads();
-  for (int j = 0; j < n; ++j) {
-    const double d = S[j * NB_PITCH + j];
-    if (!(d > 0.0) || !isfinite(d)) {  // not positive definite (or NaN upstream)
-      if (tid == 0) atomicCAS(info, 0, (int32_t)(global_off + j + 1));  // keep the first failure
-    }
-    const double piv = sqrt(d);
-    const double rinv = 1.0 / piv;
-    __syncthreads();
-    // scale column j
-    for (int i = j + 1 + tid; i < n; i += blockDim.x) S[i * NB_PITCH + j] *= rinv;
-    if (tid == 0) S[j * NB_PITCH + j] = piv;
-    __syncthreads();
-    // rank-1 update of the trailing lower triangle: (i, c), j < c <= i < n
-    const int m = n - j - 1;
-    for (int idx = tid; idx < m * m; idx += blockDim.x) {
-      const int i = j + 1 + idx / m, c = j + 1 + idx % m;
-      if (c <= i) S[i * NB_PITCH + c] -= S[i * NB_PITCH + j] * S[c * NB_PITCH + j];
+  double a[NB];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) a[c] = S[i * NB_PITCH + c];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    if (i == j) {
+      const double d = a[j];
+      if (j < n && (!(d > 0.0) || !isfinite(d))) atomicCAS(info, 0, (int32_t)(global_off + j + 1));  // first failure wins
+      piv_s = sqrt(d);
     }
     __syncthreads();
+    const double piv = piv_s;
+    if (i == j) a[j] = piv;
+    if (i > j) a[j] = a[j] / piv;
+    col[i] = a[j];
+    __syncthreads();
+    if (i > j) {
+      const double lij = a[j];
+#pragma unroll
+      for (int k = j + 1; k < NB; ++k)
+        if (k <= i) a[k] = fma(-lij, col[k], a[k]);
+    }
   }
-  for (int idx = tid; idx < n * NB; idx += blockDim.x) {
-    const int i = idx / NB, j = idx % NB;
-    if (j <= i && j < n) A[(int64_t)i * ld + j] = S[i * NB_PITCH + j];
+#pragma unroll
+  for (int c = 0; c < NB; ++c) S[i * NB_PITCH + c] = a[c];
+  __syncthreads();
+  for (int idx = i; idx < NB * NB; idx += NB) {
+    const int r = idx / NB, c = idx % NB;
+    if (r < n && c <= r) A[(int64_t)r * ld + c] = S[r * NB_PITCH + c];
   }
 }
 
@@ -281,19 +319,32 @@ static int trsm_panel_launch(const double* L, int nb, int64_t ldl, double* B, in
 // ============================================================================================
 constexpr int OB = 512;
 
-// B (M x n) <- B * L^-T, L n x n lower.  bs = block size of this level.
+// B (M x n) <- B * L^-T for an n x n (n <= OB) lower-triangular L, by recursive halving of the columns:
+//   [B1 B2] <- [B1 L11^-T,  (B2 - B1 L21^T) L22^-T]
+// so the updates are GEMMs with K = n/2, n/4, ... (large K, each C column block touched once per level)
+// and only the 64-wide leaves run the FP64-ALU substitution kernel.
+static int trsm_rows_halving(const double* L, int64_t n, int64_t ldl, double* B, int64_t M, int64_t ldb,
+                             cudaStream_t st) {
+  if (n <= NB) return trsm_panel_launch(L, (int)n, ldl, B, M, ldb, st);
+  const int64_t h = ((n / 2 + NB - 1) / NB) * NB;  // split at a multiple of 64
+  int rc = trsm_rows_halving(L, h, ldl, B, M, ldb, st);
+  if (rc) return rc;
+  // B2 -= B1 * L21^T, L21 = L[h:n, 0:h]
+  rc = gemm_nt_sub_launch(B + h, M, n - h, ldb, B, ldb, L + h * ldl, ldl, h, 0, st);
+  if (rc) return rc;
+  return trsm_rows_halving(L + h * ldl + h, n - h, ldl, B + h, M, ldb, st);
+}
+
+// B (M x n) <- B * L^-T, L n x n lower.  bs = block size of this level (OB: right-looking over OB-wide
+// column blocks with DMMA updates of everything to the right; the OB-wide diagonal solves use halving).
 static int trsm_rows_rec(const double* L, int64_t n, int64_t ldl, double* B, int64_t M, int64_t ldb, int bs,
                          cudaStream_t st) {
+  if (bs == NB) return trsm_rows_halving(L, n, ldl, B, M, ldb, st);
   for (int64_t k = 0; k < n; k += bs) {
     const int64_t w = (n - k < bs) ? (n - k) : bs;
     const double* Lkk = L + k * ldl + k;
     double* Bk = B + k;
-    int rc;
-    if (bs == NB) {
-      rc = trsm_panel_launch(Lkk, (int)w, ldl, Bk, M, ldb, st);
-    } else {
-      rc = trsm_rows_rec(Lkk, w, ldl, Bk, M, ldb, NB, st);
-    }
+    int rc = trsm_rows_halving(Lkk, w, ldl, Bk, M, ldb, st);
     if (rc) return rc;
     const int64_t rest = n - k - w;
     if (rest > 0) {
@@ -311,7 +362,7 @@ static int potrf_rec(double* A, int64_t n, int64_t ld, int bs, int32_t* info, in
     double* Akk = A + k * ld + k;
     int rc;
     if (bs == NB) {
-      potf2_kernel<<<1, 256, 0, st>>>(Akk, (int)w, ld, info, goff + k);
+      potf2_kernel<<<1, NB, 0, st>>>(Akk, (int)w, ld, info, goff + k);
       TGP_LAUNCH_CHECK();
       rc = TGP_OK;
     } else {
