@@ -342,7 +342,7 @@ def run_gp(args, treegp, backend, dist, rank, world, dev, barrier, max_over_rank
         barrier()
         t0 = time.perf_counter()
         gp = treegp.GPInterpolation(kernel=kstr, optimizer="anisotropic", normalize=True, nbins=21, min_sep=0.0,
-                                    max_sep=4.0 * size, p0=[1.0, 0.0, 0.0])
+                                    max_sep=1.0, p0=[1.0, 0.0, 0.0])
         gp.initialize(X, y, y_err=y_err)
         gp.solve()
         torch.cuda.synchronize()
@@ -398,7 +398,7 @@ def run_gp(args, treegp, backend, dist, rank, world, dev, barrier, max_over_rank
     out.update({
         "metric": "gp_fit_predict_wall_s", "value": best["total_s"], "unit": "s", "higher_is_better": False,
         "config": {"workload": "2D AnisotropicVonKarman GP, N=%d train / M=%d predict (configs[2]); "
-                               "GPInterpolation.initialize + solve(optimizer='anisotropic', nbins=21, 444 bootstraps) "
+                               "GPInterpolation.initialize + solve(optimizer='anisotropic', nbins=21, max_sep=1 as tests/test_hyp_search.py, 444 bootstraps) "
                                "+ predict(M), host numpy in/out; test points sharded over %d rank(s)" % (n, m, world)},
         "wall_breakdown_s": best,
         "kernel_breakdown_s": {"kmat_lower": t_k, "potrf": t_chol, "potrs_vec": t_solve,

@@ -1,0 +1,227 @@
+"""CPU: host-side logic that needs no GPU -- bin thresholds, oracle self-consistency, the von Karman
+profile (host compilation of the device header), the MIGRAD stand-in, FITS table I/O, kernel lowering."""
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- bin thresholds ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("max_sep,nbins", [(14.142135623730951, 21), (1.0, 21), (5.0, 20), (707.1067811865476, 21), (3.3, 1), (2.5, 2)])
+def test_twod_thresholds_reproduce_the_formula(max_sep, nbins):
+    from treegp_b200 import binning
+
+    e = binning.twod_thresholds(max_sep, nbins)
+    assert e[0] == -np.inf and e[-1] == np.inf and np.all(np.diff(e[1:-1]) > 0)
+    rng = np.random.default_rng(0)
+    v = rng.uniform(-max_sep, max_sep, 50000)
+    inner = e[1:-1]
+    v = np.concatenate([v, inner, np.nextafter(inner, -np.inf), np.nextafter(inner, np.inf)])
+    v = v[np.abs(v) < max_sep]
+    bin_size = 2.0 * max_sep / nbins
+    f = ((v + max_sep) / bin_size).astype(np.int64)
+    f[f == nbins] -= 1
+    g = (v[:, None] >= inner[None, :]).sum(axis=1)
+    np.testing.assert_array_equal(f, g)
+
+
+def test_log_thresholds_reproduce_the_formula():
+    from treegp_b200 import binning
+
+    mn, mx, nb = 0.1, 1.75, 15
+    e = binning.log_thresholds(mn, mx, nb)
+    rng = np.random.default_rng(1)
+    r2 = np.concatenate([rng.uniform(mn * mn, mx * mx, 20000), e[1:-1], np.nextafter(e[1:-1], 0), np.nextafter(e[1:-1], 10)])
+    bs = math.log(mx / mn) / nb
+    f = np.array([min(max(int((0.5 * math.log(x) - math.log(mn)) / bs), 0), nb - 1) for x in r2])
+    g = (r2[:, None] >= e[None, 1:-1]).sum(axis=1)
+    np.testing.assert_array_equal(f, g)
+
+
+@pytest.mark.parametrize("nbins", [4, 5, 15, 20, 21])
+def test_mask_and_coords_match_the_oracle_restatement(nbins):
+    from oracle import pairbin_oracle as po
+    from treegp_b200 import binning
+
+    m, c = po.twod_mask_and_coords(nbins, 1.37)
+    np.testing.assert_array_equal(m, binning.twod_mask(nbins))
+    np.testing.assert_array_equal(c, binning.twod_coords(nbins, 1.37))
+    # number of kept pixels quoted in SURVEY.md section 3.3
+    assert binning.twod_mask(21).sum() == 221 and binning.twod_mask(20).sum() == 200 and binning.twod_mask(15).sum() == 113
+
+
+# ---- oracle: C vs independent numpy restatement -----------------------------------------------------
+@pytest.mark.parametrize("cfg", [("TwoD", 0.0, 14.1, 21), ("TwoD", 0.3, 5.0, 20), ("Log", 0.1, 1.75, 15)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_c_oracle_matches_numpy_oracle(cfg, weighted):
+    from oracle import pairbin_oracle as po
+
+    bt, mn, mx, nb = cfg
+    rng = np.random.default_rng(3)
+    n = 600
+    x, y, k = rng.uniform(-10, 10, n), rng.uniform(-10, 10, n), rng.normal(size=n)
+    x[5], y[5] = x[9], y[9]
+    w = rng.uniform(0.5, 2.0, n) if weighted else None
+    a, b = po.pairbin(x, y, k, w, mn, mx, nb, bt), po.pairbin_numpy(x, y, k, w, mn, mx, nb, bt)
+    np.testing.assert_array_equal(a["npairs"], b["npairs"])
+    np.testing.assert_allclose(a["sumwkk"], b["sumwkk"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(a["weight"], b["weight"], rtol=1e-12)
+    # row slabs add up (what the multi-GPU split relies on)
+    parts = [po.pairbin(x, y, k, w, mn, mx, nb, bt, rows=r) for r in ((0, 100), (100, 350), (350, n))]
+    np.testing.assert_array_equal(sum(p["npairs"] for p in parts), a["npairs"])
+    if bt == "TwoD":
+        c = a["npairs"].reshape(nb, nb)
+        np.testing.assert_array_equal(c, c[::-1, ::-1])  # point symmetry two_pcf.py:306-321 relies on
+
+
+# ---- von Karman profile: the device header compiled for the host ------------------------------------
+@pytest.fixture(scope="module")
+def vk_host(tmp_path_factory):
+    d = tmp_path_factory.mktemp("vk")
+    src = d / "h.cpp"
+    src.write_text('#include "vk_profile.cuh"\nextern "C" void vk_eval(const double* q, long n, double* out)'
+                   '{ for (long i = 0; i < n; i++) out[i] = tgp_vk_profile(q[i], tgp_vk_phi_host); }\n')
+    so = d / "libvk.so"
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC",
+                           "-I", os.path.join(ROOT, "treegp_b200", "csrc"), str(src), "-o", str(so)])
+    lib = ctypes.CDLL(str(so))
+
+    def f(q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        out = np.empty_like(q)
+        lib.vk_eval(q.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(q.size), out.ctypes.data_as(ctypes.c_void_p))
+        return out
+
+    return f
+
+
+def test_vk_profile_against_mpmath(vk_host):
+    import mpmath as mp
+
+    mp.mp.dps = 40
+    nu = mp.mpf(5) / 6
+    rng = np.random.default_rng(1)
+    d = np.concatenate([10 ** rng.uniform(-8, 1.2, 1500), rng.uniform(0, 3, 500), [1 / (2 * np.pi), 0.5 / np.pi]])
+    got = vk_host(d * d)
+    for di, gi in zip(d, got):
+        q = mp.mpf(float(di)) ** 2
+        z = 2 * mp.pi * mp.sqrt(q)
+        truth = mp.mpf(2) ** (mp.mpf(1) / 6) / mp.gamma(nu) * z ** nu * mp.besselk(nu, z)
+        assert abs(mp.mpf(float(gi)) - truth) < mp.mpf(4e-15) * max(truth, mp.mpf(1e-3)), (di, gi)
+    assert vk_host(np.array([0.0]))[0] == 1.0
+    assert vk_host(np.array([1e6]))[0] == 0.0
+
+
+def test_vk_profile_against_scipy_reference_formula(vk_host):
+    """The reference's own expression (kernels.py:255-262) evaluated with scipy: atol 1e-12 is the
+    reference tests' tolerance (tests/test_kernels.py:122-123)."""
+    from scipy import special
+
+    d = np.concatenate([np.linspace(1e-6, 20, 20001), 10 ** np.linspace(-12, 2, 2000)])
+    lim0 = special.gamma(5 / 6) / (2 * np.pi ** (5 / 6))
+    ref = d ** (5 / 6) * special.kv(5 / 6, 2 * np.pi * d) / lim0
+    np.testing.assert_allclose(vk_host(d * d), ref, rtol=0, atol=5e-14)
+
+
+# ---- MIGRAD stand-in ----------------------------------------------------------------------------------
+def test_migrad_finds_minima_and_flags_accuracy():
+    from treegp_b200.migrad import Migrad
+
+    def rosen(p):
+        return (1 - p[0]) ** 2 + 100 * (p[1] - p[0] ** 2) ** 2 + (p[2] - 0.3) ** 2
+
+    m = Migrad(rosen, [-1.2, 1.0, 0.0]).migrad()
+    assert m.accurate and m.fval < 1e-3
+    np.testing.assert_allclose(m.values, [1.0, 1.0, 0.3], atol=0.05)
+
+    def walled(p):  # inf outside |g| <= 1, like two_pcf.py:105-106
+        if abs(p[1]) > 1 or abs(p[2]) > 1:
+            return np.inf
+        return 50 * np.log(p[0] / 0.5) ** 2 + 30 * (p[1] - 0.2) ** 2 + 30 * (p[2] + 0.9) ** 2 + 3 * p[1] * p[2]
+
+    m = Migrad(walled, [0.3, 0.0, 0.0]).migrad()
+    assert m.accurate
+    np.testing.assert_allclose(m.values, [0.5, 0.246, -0.912], atol=2e-2)
+    m = Migrad(lambda p: np.inf, [1.0, 0.0, 0.0]).migrad()
+    assert not m.accurate
+
+
+# ---- FITS table I/O -------------------------------------------------------------------------------------
+def test_fits_table_round_trip(tmp_path):
+    from treegp_b200 import fitstable
+
+    rng = np.random.default_rng(0)
+    cols = {"COORDS0": rng.normal(size=(37, 2)), "PARAMS0": rng.normal(size=37), "WRMS0": np.zeros(37)}
+    path = str(tmp_path / "mean.fits")
+    fitstable.write_table(path, cols)
+    assert os.path.getsize(path) % 2880 == 0
+    back = fitstable.read_table(path)
+    for k, v in cols.items():
+        np.testing.assert_array_equal(back[k][0], v)
+
+
+# ---- kernel objects / lowering ------------------------------------------------------------------------
+def test_kernel_protocol_and_lowering(golden):
+    import treegp_b200 as treegp
+    from treegp_b200 import _cabi
+    from treegp_b200.kernels import lower_kernel
+
+    k = treegp.AnisotropicRBF(invLam=golden["rt_invLam"])
+    np.testing.assert_allclose(k.theta, golden["rt_theta"], atol=1e-14)
+    k.theta = golden["rt_theta2"]
+    np.testing.assert_allclose(k.invLam, golden["rt_invLam2"], atol=1e-14)
+    for name in [str(c) for c in golden["cases"]]:
+        ker = treegp.eval_kernel(str(golden["kstr_" + name]))
+        np.testing.assert_allclose(ker.theta, golden["theta_" + name], atol=1e-12)  # same theta layout as the reference
+        clone = ker.clone_with_theta(ker.theta + 0.1)
+        np.testing.assert_allclose(clone.theta, ker.theta + 0.1, atol=1e-12)
+        assert ker.bounds.shape == (len(ker.theta), 2)
+    d = lower_kernel(treegp.eval_kernel("2.0**2 * RBF(0.5)"), 2)
+    assert (d.family, d.ndim, d.amp, d.m00, d.m01, d.m11) == (_cabi.FAM_RBF, 2, 4.0, 4.0, 0.0, 4.0)
+    d = lower_kernel(treegp.eval_kernel("3.0 * VonKarman(length_scale=2.0)"), 1)
+    assert (d.family, d.ndim, d.amp, d.m00) == (_cabi.FAM_VONKARMAN, 1, 3.0, 0.25)
+    d = lower_kernel(treegp.eval_kernel("Matern(length_scale=2.0, nu=2.5)"), 2)
+    assert d.family == _cabi.FAM_MATERN52 and d.amp == 1.0
+    with pytest.raises(_cabi.TgpError):
+        lower_kernel(treegp.eval_kernel("Matern(length_scale=2.0, nu=0.7)"), 2)
+    with pytest.raises(TypeError):
+        treegp.AnisotropicRBF(invLam=np.eye(2), scale_length=[1.0, 1.0])
+    with pytest.raises(RuntimeError):
+        treegp.eval_kernel("NoSuchKernel(1)")
+    with pytest.raises(TypeError):
+        treegp.eval_kernel("RBF")
+
+
+def test_gpinterpolation_argument_errors():
+    import treegp_b200 as treegp
+
+    with pytest.raises(TypeError):
+        treegp.GPInterpolation(kernel=3)
+    with pytest.raises(ValueError):
+        treegp.GPInterpolation(optimizer="nope")
+    with pytest.raises(ValueError):
+        treegp.two_pcf(np.zeros((4, 3)), np.zeros(4), np.zeros(4), 0.0, 1.0)
+    gp = treegp.GPInterpolation(kernel="RBF(1)", optimizer="none")
+    assert gp.robust_fit is False and gp.nbins == 20 and gp.n_neighbors == 4
+
+
+def test_product_path_never_falls_back_to_cpu():
+    """Without a CUDA device every compute entry must raise (no silent CPU path)."""
+    import torch
+    import treegp_b200 as treegp
+    from treegp_b200 import _cabi
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    k = treegp.eval_kernel("1.0 * RBF(1.0)")
+    with pytest.raises(_cabi.TgpError):
+        k.k2(np.zeros((3, 2))) if False else treegp.AnisotropicRBF(scale_length=[1.0, 1.0])(np.zeros((3, 2)))
+    gp = treegp.GPInterpolation(kernel="1.0 * AnisotropicRBF(scale_length=[1.0, 1.0])", optimizer="none")
+    gp.initialize(np.zeros((3, 2)), np.zeros(3))
+    with pytest.raises(_cabi.TgpError):
+        gp.predict(np.zeros((2, 2)))
