@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--gp-predict", type=int, default=1_000_000)
     ap.add_argument("--skip-gp", action="store_true", help="only the 2PCF part (used for ncu captures)")
     ap.add_argument("--skip-cpu", action="store_true")
-    ap.add_argument("--cpu-rows", type=int, default=1500, help="rows of the pair matrix in the CPU sample")
+    ap.add_argument("--cpu-rows", type=int, default=20000, help="rows of the pair matrix in the CPU sample")
     return ap.parse_args()
 
 
