@@ -76,6 +76,11 @@ int tgp_kmat_cross(const double* Xs, int64_t M, const double* X, int64_t N,
  * info: device int32, see header comment. */
 int tgp_potrf(double* A, int64_t N, int64_t ld, int32_t* info, void* stream);
 
+/* Same factorisation, carrying `nrows` extra rows stored directly below the matrix (rows N .. N+nrows-1 of
+ * the same workspace, N columns each: right-hand sides as rows).  On exit row N+r holds L^-1 y_r -- the
+ * forward substitution is done by the factorisation's own panel solves and DMMA updates. */
+int tgp_potrf_rows(double* A, int64_t N, int64_t ld, int64_t nrows, int32_t* info, void* stream);
+
 /* Solve L L^T x = b in place for one right-hand side (b: N).  Replaces cho_solve
  * (gp_interp.py:182, log_likelihood.py:31). */
 int tgp_potrs_vec(const double* L, int64_t N, int64_t ld, double* b, void* stream);
@@ -97,7 +102,8 @@ int tgp_logdet_chi2(const double* L, int64_t N, int64_t ld, const double* y, con
                     double* out, void* stream);
 
 /* Whole marginal log-likelihood evaluation (log_likelihood.py:29-37) in one call:
- * work (N x N, ld) receives K (lower) then L; out: device double[3] = {logL, chi2, logdet}; info as
+ * work ((N+1) x ld: one extra row carries y through the factorisation) receives K (lower) then L;
+ * out: device double[3] = {logL, chi2, logdet}; info as
  * tgp_potrf.  When *info != 0 out[0] is -inf (log_likelihood.py:38-39).
  * want_alpha != 0: alpha (N) receives K^-1 y (both triangular sweeps) and chi2 = y . alpha;
  * want_alpha == 0: alpha receives L^-1 y (forward sweep only) and chi2 = ||L^-1 y||^2 -- the same

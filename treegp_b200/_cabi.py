@@ -36,6 +36,7 @@ SIGNATURES = {
     "tgp_kmat_sym": [_vp, _i64, _kp, _vp, _vp, _i64, ctypes.c_int, _vp],
     "tgp_kmat_cross": [_vp, _i64, _vp, _i64, _kp, _vp, _i64, _vp],
     "tgp_potrf": [_vp, _i64, _i64, _vp, _vp],
+    "tgp_potrf_rows": [_vp, _i64, _i64, _i64, _vp, _vp],
     "tgp_potrs_vec": [_vp, _i64, _i64, _vp, _vp],
     "tgp_trsm_rows": [_vp, _i64, _i64, _vp, _i64, _i64, _vp],
     "tgp_gemm_nt_sub": [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _i64, ctypes.c_int, _vp],

@@ -116,7 +116,9 @@ def loglike(X, y, yerr2, kdesc, work=None, want_alpha=False):
     X = as_points(X)
     N = X.shape[0]
     if work is None:
-        work = alloc_matrix(N, N, X.device)
+        work = alloc_matrix(N + 1, N, X.device)
+    if work.shape[0] < N + 1:
+        raise ValueError("loglike workspace needs N+1 rows")
     alpha = torch.empty(N, dtype=F64, device=X.device)
     out = torch.zeros(3, dtype=F64, device=X.device)
     info = torch.zeros(1, dtype=torch.int32, device=X.device)

@@ -160,6 +160,7 @@ gemm_nt_sub_kernel(double* __restrict__ C, int64_t M, int64_t Nc, int64_t ldc,
   }
 }
 
+static int g_lookahead = 1;  // 0 disables the two-stream look-ahead Cholesky driver
 static int g_gemm_config = -1;  // -1: pick by shape; 0: 128x128; 1: 128x64 (tgp_set_option for experiments)
 
 template <int BN_, int WARPS_M, int WARPS_N, int MIN_CTAS>
@@ -192,6 +193,7 @@ static int gemm_nt_sub_launch(double* C, int64_t M, int64_t Nc, int64_t ldc, con
 
 extern "C" int tgp_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_config")) { g_gemm_config = value; return TGP_OK; }
+  if (name && !strcmp(name, "potrf_lookahead")) { g_lookahead = value; return TGP_OK; }
   tgp_set_error("tgp_set_option: unknown option");
   return TGP_ERR_INVALID;
 }
@@ -356,7 +358,10 @@ static int trsm_rows_rec(const double* L, int64_t n, int64_t ldl, double* B, int
   return TGP_OK;
 }
 
-static int potrf_rec(double* A, int64_t n, int64_t ld, int bs, int32_t* info, int64_t goff, cudaStream_t st) {
+// `extra` rows stored below the n x n matrix (right-hand sides as ROWS) are carried through the panel solves and
+// trailing updates, so that on exit they hold Y L^-T (= L^-1 y per row): the forward substitution at DMMA speed.
+static int potrf_rec(double* A, int64_t n, int64_t ld, int bs, int32_t* info, int64_t goff, cudaStream_t st,
+                     int64_t extra = 0) {
   for (int64_t k = 0; k < n; k += bs) {
     const int64_t w = (n - k < bs) ? (n - k) : bs;
     double* Akk = A + k * ld + k;
@@ -370,13 +375,91 @@ static int potrf_rec(double* A, int64_t n, int64_t ld, int bs, int32_t* info, in
     }
     if (rc) return rc;
     const int64_t rest = n - k - w;
-    if (rest > 0) {
-      double* Ark = A + (k + w) * ld + k;  // rows below the diagonal block
-      rc = trsm_rows_rec(Akk, w, ld, Ark, rest, ld, NB, st);
+    if (rest + extra > 0) {
+      double* Ark = A + (k + w) * ld + k;  // rows below the diagonal block (+ the extra right-hand-side rows)
+      rc = trsm_rows_rec(Akk, w, ld, Ark, rest + extra, ld, NB, st);
       if (rc) return rc;
-      rc = gemm_nt_sub_launch(A + (k + w) * ld + (k + w), rest, rest, ld, Ark, ld, Ark, ld, w, 1, st);
+      if (rest > 0) {
+        rc = gemm_nt_sub_launch(A + (k + w) * ld + (k + w), rest + extra, rest, ld, Ark, ld, Ark, ld, w, 1, st);
+        if (rc) return rc;
+      }
+    }
+  }
+  return TGP_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// Look-ahead driver for large N.  The OB-wide panel (diagonal factorisation + solve of the rows
+// below) is a chain of ~40 small, latency-bound launches; run on its own high-priority stream it
+// hides under the previous step's big trailing update:
+//   panel stream P : panel(b) .. wait U2(b-1) .. U1(b) = update of the NEXT panel's column block only
+//   caller stream U: wait panel(b) .. U2(b) = update of everything right of the next panel
+// U1(b) and U2(b) write disjoint blocks; panel(b+1) needs U1(b) and U2(b-1) only, so U2(b) overlaps
+// with panel(b+1).  The caller's stream is joined with P before returning.
+// --------------------------------------------------------------------------------------------
+#include <vector>
+struct LookaheadCtx {
+  cudaStream_t panel = nullptr;
+  std::vector<cudaEvent_t> ev;
+  cudaEvent_t get(size_t i) {
+    while (ev.size() <= i) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      ev.push_back(e);
+    }
+    return ev[i];
+  }
+};
+static LookaheadCtx& lookahead_ctx() {
+  static thread_local LookaheadCtx c;
+  if (!c.panel) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    cudaStreamCreateWithPriority(&c.panel, cudaStreamNonBlocking, hi);
+  }
+  return c;
+}
+static int potrf_lookahead(double* A, int64_t n, int64_t ld, int32_t* info, cudaStream_t U, int64_t extra = 0) {
+  LookaheadCtx& L = lookahead_ctx();
+  cudaStream_t P = L.panel;
+  const int64_t nblk = tgp_cdiv(n, OB);
+  cudaEvent_t e_start = L.get(0);
+  TGP_CUDA(cudaEventRecord(e_start, U));
+  TGP_CUDA(cudaStreamWaitEvent(P, e_start, 0));
+  // event slots: 1 + 2*b = panel(b) done, 2 + 2*b = U2(b) done
+  for (int64_t b = 0; b < nblk; ++b) {
+    const int64_t k = b * OB;
+    const int64_t w = (n - k < OB) ? (n - k) : OB;
+    double* Akk = A + k * ld + k;
+    int rc = potrf_rec(Akk, w, ld, NB, info, k, P);
+    if (rc) return rc;
+    const int64_t rest = n - k - w;
+    if (rest + extra > 0) {
+      double* Ark = A + (k + w) * ld + k;
+      rc = trsm_rows_halving(Akk, w, ld, Ark, rest + extra, ld, P);
       if (rc) return rc;
     }
+    cudaEvent_t e_panel = L.get(1 + 2 * b);
+    TGP_CUDA(cudaEventRecord(e_panel, P));
+    if (rest <= 0) {
+      TGP_CUDA(cudaStreamWaitEvent(U, e_panel, 0));
+      break;
+    }
+    double* Ark = A + (k + w) * ld + k;
+    const int64_t w2 = (rest < OB) ? rest : OB;
+    TGP_CUDA(cudaStreamWaitEvent(U, e_panel, 0));
+    if (b >= 1) TGP_CUDA(cudaStreamWaitEvent(P, L.get(2 + 2 * (b - 1)), 0));
+    // U1(b): next panel's column block, all rows below the current panel (+ extra rows)
+    rc = gemm_nt_sub_launch(A + (k + w) * ld + (k + w), rest + extra, w2, ld, Ark, ld, Ark, ld, w, 1, P);
+    if (rc) return rc;
+    // U2(b): everything to the right of the next panel
+    const int64_t rest2 = rest - w2;
+    if (rest2 > 0) {
+      rc = gemm_nt_sub_launch(A + (k + w + w2) * ld + (k + w + w2), rest2 + extra, rest2, ld, Ark + w2 * ld, ld,
+                              Ark + w2 * ld, ld, w, 1, U);
+      if (rc) return rc;
+    }
+    TGP_CUDA(cudaEventRecord(L.get(2 + 2 * b), U));
   }
   return TGP_OK;
 }
@@ -387,13 +470,23 @@ static int check_mat(const double* A, int64_t N, int64_t ld) {
   return 0;
 }
 
+static int potrf_with_rows(double* A, int64_t N, int64_t ld, int64_t extra, int32_t* info, cudaStream_t st) {
+  TGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+  if (N == 0) return TGP_OK;
+  if (g_lookahead && N >= 3 * OB) return potrf_lookahead(A, N, ld, info, st, extra);
+  return potrf_rec(A, N, ld, N > OB ? OB : NB, info, 0, st, extra);
+}
+
 extern "C" int tgp_potrf(double* A, int64_t N, int64_t ld, int32_t* info, void* stream) {
   TGP_CHECK_ARG(!check_mat(A, N, ld), "A must be 16-byte aligned with even ld >= N");
   TGP_CHECK_ARG(info != nullptr, "info");
-  cudaStream_t st = (cudaStream_t)stream;
-  TGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
-  if (N == 0) return TGP_OK;
-  return potrf_rec(A, N, ld, N > OB ? OB : NB, info, 0, st);
+  return potrf_with_rows(A, N, ld, 0, info, (cudaStream_t)stream);
+}
+
+extern "C" int tgp_potrf_rows(double* A, int64_t N, int64_t ld, int64_t nrows, int32_t* info, void* stream) {
+  TGP_CHECK_ARG(!check_mat(A, N, ld), "A must be 16-byte aligned with even ld >= N");
+  TGP_CHECK_ARG(info != nullptr && nrows >= 0, "info/nrows");
+  return potrf_with_rows(A, N, ld, nrows, info, (cudaStream_t)stream);
 }
 
 extern "C" int tgp_trsm_rows(const double* L, int64_t N, int64_t ld, double* B, int64_t M, int64_t ldb,
@@ -670,20 +763,21 @@ extern "C" int tgp_loglike(const double* X, const double* y, const double* yerr2
   cudaStream_t st = (cudaStream_t)stream;
   int rc = tgp_kmat_sym(X, N, k, yerr2, work, ld, /*lower_only=*/1, stream);
   if (rc) return rc;
-  rc = tgp_potrf(work, N, ld, info, stream);
+  // y rides along as row N of the workspace: the factorisation's panel solves turn it into w = L^-1 y
+  double* wrow = work + N * ld;
+  TGP_CUDA(cudaMemcpyAsync(wrow, y, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  rc = tgp_potrf_rows(work, N, ld, 1, info, stream);
   if (rc) return rc;
-  TGP_CUDA(cudaMemcpyAsync(alpha, y, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  TGP_CUDA(cudaMemcpyAsync(alpha, wrow, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
   // out[1], out[2] double as scratch {logdet, chi2} until the finishing kernel reorders them
   double* tmp = out + 1;
   if (want_alpha) {
-    rc = tgp_potrs_vec(work, N, ld, alpha, stream);
+    rc = trsv_backward(work, N, ld, alpha, st);   // alpha = L^-T w
     if (rc) return rc;
     logdet_chi2_kernel<<<1, 1024, 0, st>>>(work, N, ld, y, alpha, tmp);  // chi2 = y . alpha
     TGP_LAUNCH_CHECK();
   } else {
     // y^T K^-1 y = ||L^-1 y||^2: the backward sweep is not needed for the likelihood alone
-    rc = trsv_forward(work, N, ld, alpha, st);
-    if (rc) return rc;
     logdet_chi2_kernel<<<1, 1024, 0, st>>>(work, N, ld, nullptr, nullptr, tmp);
     TGP_LAUNCH_CHECK();
     sumsq_kernel<<<1, 1024, 0, st>>>(alpha, N, tmp + 1);

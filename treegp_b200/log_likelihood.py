@@ -36,7 +36,7 @@ class log_likelihood(object):
             Xd = backend.as_points(self.X)
             yd = backend.to_device(np.asarray(self.y, dtype=np.float64).reshape(-1))
             e2 = backend.to_device(np.asarray(self.y_err, dtype=np.float64).reshape(-1) ** 2)
-            work = backend.alloc_matrix(self.ndata, self.ndata, Xd.device)
+            work = backend.alloc_matrix(self.ndata + 1, self.ndata, Xd.device)  # +1 row: y rides through potrf
             self._dev = (Xd, yd, e2, work)
         return self._dev
 
