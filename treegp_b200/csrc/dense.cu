@@ -171,6 +171,10 @@ static int gemm_launch_cfg(double* C, int64_t M, int64_t Nc, int64_t ldc, const 
   if (!attr_set) {
     TGP_CUDA(cudaFuncSetAttribute(gemm_nt_sub_kernel<BN_, WARPS_M, WARPS_N, MIN_CTAS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    // same shared-memory carve-out for every kernel of the factorisation: no L1/shared reconfiguration
+    // between the back-to-back small launches of a panel
+    TGP_CUDA(cudaFuncSetAttribute(gemm_nt_sub_kernel<BN_, WARPS_M, WARPS_N, MIN_CTAS>,
+                                  cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   dim3 grid((unsigned)tgp_cdiv(Nc, BN_), (unsigned)tgp_cdiv(M, BM));
@@ -204,46 +208,86 @@ extern "C" int tgp_set_option(const char* name, int value) {
 constexpr int NB = 64;           // inner block
 constexpr int NB_PITCH = NB + 1;
 
-// One thread per row (64 threads): row i of the lower triangle lives in registers, column j is
-// broadcast through shared memory, the trailing update of a row is a run of independent FMAs.
-__global__ void __launch_bounds__(NB)
+// 256 threads, the block in shared memory, factorised in four 16-column steps so that only 4 x 3
+// CTA barriers separate the phases instead of 64 x 2:
+//   (i)   warp 0 factorises the 16 x 16 diagonal sub-block in registers (lane = row, shuffles),
+//   (ii)  one thread per row below solves its 16 entries against that sub-block,
+//   (iii) all threads apply the rank-16 update to the trailing lower triangle.
+constexpr int PF_B = 16;
+__global__ void __launch_bounds__(256)
 potf2_kernel(double* __restrict__ A, int n, int64_t ld, int32_t* __restrict__ info, int64_t global_off) {
   __shared__ double S[NB * NB_PITCH];
-  __shared__ double col[NB];
-  __shared__ double piv_s;
-  const int i = threadIdx.x;
-  for (int idx = i; idx < NB * NB; idx += NB) {
+  __shared__ double rdiag[NB];   // 1 / L[j][j]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll 4
+  for (int idx = tid; idx < NB * NB; idx += 256) {
     const int r = idx / NB, c = idx % NB;  // coalesced along c
     S[r * NB_PITCH + c] = (r < n && c <= r) ? A[(int64_t)r * ld + c] : (r == c ? 1.0 : 0.0);
   }
   __syncthreads();
-  double a[NB];
+  for (int k0 = 0; k0 < NB; k0 += PF_B) {
+    // (i) 16 x 16 diagonal sub-block, lanes 0..15 hold one row each
+    if (warp == 0) {
+      double a[PF_B];
+      const int r = k0 + (lane & 15);
 #pragma unroll
-  for (int c = 0; c < NB; ++c) a[c] = S[i * NB_PITCH + c];
+      for (int c = 0; c < PF_B; ++c) a[c] = S[r * NB_PITCH + k0 + c];
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    if (i == j) {
-      const double d = a[j];
-      if (j < n && (!(d > 0.0) || !isfinite(d))) atomicCAS(info, 0, (int32_t)(global_off + j + 1));  // first failure wins
-      piv_s = sqrt(d);
+      for (int j = 0; j < PF_B; ++j) {
+        const double d = __shfl_sync(0xffffffffu, a[j], j);           // pivot a_jj from lane j
+        if (lane == j && k0 + j < n && (!(d > 0.0) || !isfinite(d)))
+          atomicCAS(info, 0, (int32_t)(global_off + k0 + j + 1));     // keep the first failure
+        // one reciprocal square root per pivot: l_jj = d * rsqrt(d), l_ij = a_ij * rsqrt(d) (no FP64 divide or
+        // square-root call on the critical path; results agree with sqrt/divide to ~1 ulp)
+        double rinv = rsqrt(d);
+        rinv = fma(fma(-d * rinv, rinv, 1.0), 0.5 * rinv, rinv);    // one Newton step: full double accuracy
+        if ((lane & 15) == j) { a[j] = d * rinv; if (lane < 16) rdiag[k0 + j] = rinv; }
+        if ((lane & 15) > j) a[j] = a[j] * rinv;
+#pragma unroll
+        for (int c = j + 1; c < PF_B; ++c) {
+          const double lcj = __shfl_sync(0xffffffffu, a[j], c);       // l_cj from lane c
+          if ((lane & 15) >= c) a[c] = fma(-a[j], lcj, a[c]);
+        }
+      }
+      if (lane < 16) {
+#pragma unroll
+        for (int c = 0; c < PF_B; ++c) S[r * NB_PITCH + k0 + c] = a[c];
+      }
     }
     __syncthreads();
-    const double piv = piv_s;
-    if (i == j) a[j] = piv;
-    if (i > j) a[j] = a[j] / piv;
-    col[i] = a[j];
-    __syncthreads();
-    if (i > j) {
-      const double lij = a[j];
+    // (ii) rows below: x <- x * L11^-T (thread per row)
+    const int below = NB - k0 - PF_B;
+    if (tid < below) {
+      const int r = k0 + PF_B + tid;
+      double x[PF_B];
 #pragma unroll
-      for (int k = j + 1; k < NB; ++k)
-        if (k <= i) a[k] = fma(-lij, col[k], a[k]);
+      for (int c = 0; c < PF_B; ++c) x[c] = S[r * NB_PITCH + k0 + c];
+#pragma unroll
+      for (int j = 0; j < PF_B; ++j) {
+        x[j] = x[j] * rdiag[k0 + j];
+#pragma unroll
+        for (int c = j + 1; c < PF_B; ++c) x[c] = fma(-x[j], S[(k0 + c) * NB_PITCH + k0 + j], x[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < PF_B; ++c) S[r * NB_PITCH + k0 + c] = x[c];
     }
+    __syncthreads();
+    // (iii) trailing update: S[i][c] -= sum_k S[i][k0+k] S[c][k0+k], k0+16 <= c <= i < 64; 16 x 16 thread grid
+    if (below > 0) {
+      const int ty = tid >> 4, tx = tid & 15;
+      for (int i = k0 + PF_B + ty; i < NB; i += 16) {
+        for (int c = k0 + PF_B + tx; c <= i; c += 16) {
+          double acc = S[i * NB_PITCH + c];
+#pragma unroll
+          for (int k = 0; k < PF_B; ++k) acc = fma(-S[i * NB_PITCH + k0 + k], S[c * NB_PITCH + k0 + k], acc);
+          S[i * NB_PITCH + c] = acc;
+        }
+      }
+    }
+    __syncthreads();
   }
-#pragma unroll
-  for (int c = 0; c < NB; ++c) S[i * NB_PITCH + c] = a[c];
-  __syncthreads();
-  for (int idx = i; idx < NB * NB; idx += NB) {
+#pragma unroll 4
+  for (int idx = tid; idx < NB * NB; idx += 256) {
     const int r = idx / NB, c = idx % NB;
     if (r < n && c <= r) A[(int64_t)r * ld + c] = S[r * NB_PITCH + c];
   }
@@ -253,18 +297,35 @@ potf2_kernel(double* __restrict__ A, int n, int64_t ld, int32_t* __restrict__ in
 // trsm panel: B (M x nb) <- B * L^-T for an nb x nb (nb <= 64) lower-triangular L.  Thread per row,
 // right-looking over columns so the FMAs of one step are independent.
 // ============================================================================================
-constexpr int TRSM_ROWS = 128;
+constexpr int TRSM_ROWS = 64;   // rows per CTA: small CTAs spread short panels over many SMs
 constexpr int TRSM_SMEM = (NB * NB + NB + TRSM_ROWS * NB_PITCH) * 8;
 
+// FULL: nb == 64 and 16-byte aligned rows: every thread streams its own row with 32 independent 16-byte
+// loads (no staging, nothing to wait for but the L tile), solves in registers and streams it back.
+// Otherwise (edge panels): rows are staged through shared memory element by element.
+template <bool FULL>
 __global__ void __launch_bounds__(TRSM_ROWS)
 trsm_panel_kernel(const double* __restrict__ L, int nb, int64_t ldl, double* __restrict__ B, int64_t M,
                   int64_t ldb) {
   extern __shared__ __align__(16) double tsm[];
   double* LsT = tsm;                 // NB x NB, LsT[j*NB + i] = L[i][j] (column j contiguous), zero padded
   double* dinv = tsm + NB * NB;      // 1 / L[j][j]
-  double* Bs = dinv + NB;            // TRSM_ROWS x NB_PITCH
+  double* Bs = dinv + NB;            // TRSM_ROWS x NB_PITCH (edge path only)
   const int tid = threadIdx.x;
   const int64_t r0 = (int64_t)blockIdx.x * TRSM_ROWS;
+  const int64_t gr = r0 + tid;
+  double x[NB];
+  if (FULL) {
+    if (gr < M) {
+      const double2* row = reinterpret_cast<const double2*>(B + gr * ldb);
+#pragma unroll
+      for (int j = 0; j < NB / 2; ++j) { const double2 v = row[j]; x[2 * j] = v.x; x[2 * j + 1] = v.y; }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) x[j] = 0.0;
+    }
+  }
+#pragma unroll 16
   for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
     const int i = idx / NB, j = idx % NB;  // coalesced along j
     double v = 0.0;
@@ -272,15 +333,18 @@ trsm_panel_kernel(const double* __restrict__ L, int nb, int64_t ldl, double* __r
     LsT[j * NB + i] = v;
   }
   if (tid < NB) dinv[tid] = (tid < nb) ? 1.0 / L[(int64_t)tid * ldl + tid] : 1.0;
-  for (int idx = tid; idx < TRSM_ROWS * NB; idx += TRSM_ROWS) {
-    const int r = idx / NB, j = idx % NB;
-    const int64_t gr = r0 + r;
-    Bs[r * NB_PITCH + j] = (gr < M && j < nb) ? B[gr * ldb + j] : 0.0;
+  if (!FULL) {
+    for (int idx = tid; idx < TRSM_ROWS * NB; idx += TRSM_ROWS) {
+      const int r = idx / NB, j = idx % NB;
+      const int64_t g2 = r0 + r;
+      Bs[r * NB_PITCH + j] = (g2 < M && j < nb) ? B[g2 * ldb + j] : 0.0;
+    }
   }
   __syncthreads();
-  double x[NB];
+  if (!FULL) {
 #pragma unroll
-  for (int j = 0; j < NB; ++j) x[j] = Bs[tid * NB_PITCH + j];
+    for (int j = 0; j < NB; ++j) x[j] = Bs[tid * NB_PITCH + j];
+  }
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
     x[j] *= dinv[j];
@@ -292,13 +356,21 @@ trsm_panel_kernel(const double* __restrict__ L, int nb, int64_t ldl, double* __r
       x[ip + 1] = fma(nx, l.y, x[ip + 1]);
     }
   }
+  if (FULL) {
+    if (gr < M) {
+      double2* row = reinterpret_cast<double2*>(B + gr * ldb);
 #pragma unroll
-  for (int j = 0; j < NB; ++j) Bs[tid * NB_PITCH + j] = x[j];
-  __syncthreads();
-  for (int idx = tid; idx < TRSM_ROWS * NB; idx += TRSM_ROWS) {
-    const int r = idx / NB, j = idx % NB;
-    const int64_t gr = r0 + r;
-    if (gr < M && j < nb) B[gr * ldb + j] = Bs[r * NB_PITCH + j];
+      for (int j = 0; j < NB / 2; ++j) row[j] = make_double2(x[2 * j], x[2 * j + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NB; ++j) Bs[tid * NB_PITCH + j] = x[j];
+    __syncthreads();
+    for (int idx = tid; idx < TRSM_ROWS * NB; idx += TRSM_ROWS) {
+      const int r = idx / NB, j = idx % NB;
+      const int64_t g2 = r0 + r;
+      if (g2 < M && j < nb) B[g2 * ldb + j] = Bs[r * NB_PITCH + j];
+    }
   }
 }
 
@@ -307,10 +379,17 @@ static int trsm_panel_launch(const double* L, int nb, int64_t ldl, double* B, in
   if (M <= 0 || nb <= 0) return TGP_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    TGP_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
+    TGP_CUDA(cudaFuncSetAttribute(trsm_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
+    TGP_CUDA(cudaFuncSetAttribute(trsm_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
+    TGP_CUDA(cudaFuncSetAttribute(trsm_panel_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    TGP_CUDA(cudaFuncSetAttribute(trsm_panel_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    TGP_CUDA(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
-  trsm_panel_kernel<<<(unsigned)tgp_cdiv(M, TRSM_ROWS), TRSM_ROWS, TRSM_SMEM, st>>>(L, nb, ldl, B, M, ldb);
+  const bool full = (nb == NB) && ((ldb & 1) == 0) && (((uintptr_t)B & 15) == 0);
+  const unsigned grid = (unsigned)tgp_cdiv(M, TRSM_ROWS);
+  if (full) trsm_panel_kernel<true><<<grid, TRSM_ROWS, TRSM_SMEM, st>>>(L, nb, ldl, B, M, ldb);
+  else trsm_panel_kernel<false><<<grid, TRSM_ROWS, TRSM_SMEM, st>>>(L, nb, ldl, B, M, ldb);
   TGP_LAUNCH_CHECK();
   return TGP_OK;
 }
@@ -367,7 +446,7 @@ static int potrf_rec(double* A, int64_t n, int64_t ld, int bs, int32_t* info, in
     double* Akk = A + k * ld + k;
     int rc;
     if (bs == NB) {
-      potf2_kernel<<<1, NB, 0, st>>>(Akk, (int)w, ld, info, goff + k);
+      potf2_kernel<<<1, 256, 0, st>>>(Akk, (int)w, ld, info, goff + k);
       TGP_LAUNCH_CHECK();
       rc = TGP_OK;
     } else {
