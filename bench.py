@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--gp-predict", type=int, default=1_000_000)
     ap.add_argument("--skip-gp", action="store_true", help="only the 2PCF part (used for ncu captures)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-other", action="store_true", help="skip the configs[1] / configs[4] side measurements")
     ap.add_argument("--cpu-rows", type=int, default=20000, help="rows of the pair matrix in the CPU sample")
     return ap.parse_args()
 
@@ -286,6 +287,8 @@ def run_ours(args):
     if not args.skip_gp:
         line["gp_fit_predict"] = run_gp(args, treegp, backend, dist, rank, world, dev, barrier, max_over_ranks,
                                         hbm_peak, dmma_tf)
+        if rank == 0 and not args.skip_other:
+            line["other_configs"] = run_other_configs(args, treegp, backend, dmma_tf)
 
     # ---------------- CPU baseline (rank 0, bounded sample) ----------------
     if rank == 0 and not args.skip_cpu:
@@ -415,6 +418,75 @@ def run_gp(args, treegp, backend, dist, rank, world, dev, barrier, max_over_rank
                           "note": "lower-triangle build, algorithmic bytes 4 N^2; von Karman is FP64-ALU bound"},
         "predict_mean_kernel_evals_per_s": len(Xs_local) * n / t_mean,
     })
+    return out
+
+
+def run_other_configs(args, treegp, backend, dmma_tf):
+    """Side measurements for the remaining BASELINE.json configs (rank 0, single GPU):
+    configs[1]  2-D AnisotropicRBF GP, N = 10,000, optimizer='log-likelihood' (FP64 Cholesky + marginal likelihood
+                inside scipy's L-BFGS-B loop): whole-fit time, evaluation count, time per evaluation;
+    configs[4]  robust 2PCF fit ingredients at N = 200,000: one pair count + 100 batched bootstrap resamples."""
+    import torch
+    from treegp_b200.kernels import lower_kernel
+    from treegp_b200.two_pcf import get_correlation_length_matrix
+
+    out = {}
+    rng = np.random.default_rng(7)
+    # ---- configs[1] ----
+    n = 10_000
+    L = 80.0 * np.sqrt(n / 16000.0)
+    inv = np.linalg.inv(get_correlation_length_matrix(0.5, 0.2, 0.2))
+    kstr = "4.0 * AnisotropicRBF(invLam=array([[%.17g, %.17g], [%.17g, %.17g]]))" % (inv[0, 0], inv[0, 1], inv[1, 0], inv[1, 1])
+    X = rng.uniform(-L / 2, L / 2, size=(n, 2))
+    kern = treegp.eval_kernel(kstr)
+    desc = lower_kernel(kern, 2)
+    ws = backend.kmat_sym(X, desc, diag_add=backend.to_device(np.full(n, 1e-8)), lower_only=True)
+    backend.potrf(ws, n)
+    z = torch.as_tensor(rng.normal(size=n), device=ws.device)
+    y = (torch.tril(ws[:, :n]) @ z).cpu().numpy() + rng.normal(scale=0.01, size=n)
+    del ws
+    y_err = np.full(n, 0.01)
+    gp = treegp.GPInterpolation(kernel=kstr, optimizer="log-likelihood", normalize=True)
+    gp.initialize(X, y, y_err=y_err)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    gp.solve()
+    torch.cuda.synchronize()
+    t_fit = time.perf_counter() - t0
+    nev = gp._optimizer.n_evaluations
+    out["loglike_fit_N10k"] = {
+        "workload": "2D AnisotropicRBF GP, N=10000, optimizer='log-likelihood' (configs[1])",
+        "fit_wall_s": t_fit, "likelihood_evaluations": nev, "s_per_evaluation": t_fit / max(nev, 1),
+        "potrf_tflops_per_evaluation_upper_bound": n ** 3 / 3.0 / (t_fit / max(nev, 1)) / 1e12,
+        "fitted_theta": [float(v) for v in gp.kernel.theta], "true_theta": [float(v) for v in kern.theta],
+        "logL": float(gp._optimizer._logL)}
+    # ---- configs[4] ----
+    n = 200_000
+    Lf = 1000.0 * np.sqrt(n / 1e6)
+    X = rng.uniform(-Lf / 2, Lf / 2, size=(n, 2))
+    yv = rng.normal(size=n)
+    tp = treegp.two_pcf(X, yv, np.zeros(n), 0.0, np.sqrt(2.0) * Lf / 2.0, nbins=21, anisotropic=True)
+    tp.group = False
+    tp.comp_2pcf(X, yv, np.zeros(n))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tp.comp_2pcf(X, yv, np.zeros(n))
+    torch.cuda.synchronize()
+    t_one = time.perf_counter() - t0
+    B = 100
+    t0 = time.perf_counter()
+    cov = tp.comp_xi_covariance(n_bootstrap=B, mask=None, seed=610639139)
+    torch.cuda.synchronize()
+    t_boot = time.perf_counter() - t0
+    pairs = n * (n - 1) / 2
+    out["bootstrap_2pcf_N200k"] = {
+        "workload": "anisotropic 2PCF, N=200000, nbins=21, default max_sep: 1 pair count + %d batched bootstrap "
+                    "resamples (configs[4])" % B,
+        "pair_count_wall_s": t_one, "pairs_per_s": pairs / t_one,
+        "bootstrap_wall_s": t_boot, "resamples": B,
+        "resample_pairs_per_s": B * pairs / t_boot,
+        "note": "a resample keeps ~63% of the distinct points (weights = multiplicities): ~40% of the pairs per resample",
+        "cov_shape": list(cov.shape)}
     return out
 
 

@@ -111,27 +111,36 @@ __device__ __forceinline__ unsigned warp_sum_u(unsigned v) {
   return v;
 }
 
-// Per-lane register accumulators of the 2 x 2 window, forward (dx,dy) and mirrored (-dx,-dy) entry.
+// Per-lane register accumulators of the 2 x 2 window.
 // With px = "column bit" and py = "row bit" of a pair inside the window, the lane keeps
 //   tot = sum kk,  sx = sum kk [px],  sy = sum kk [py],  sxy = sum kk [px & py]
-// (masks applied as a multiplication by 0.0 / 1.0 inside one FMA, so there is no branch and no select
-// on the 64-bit data path) and the same three counters as integers.  The four window bins follow by
-// inclusion-exclusion at flush time: exact for the counts, and of the size of ordinary summation
-// rounding for the FP64 sums.
+// (masks applied as a multiplication by 0.0 / 1.0 inside one FMA: no branch, no 64-bit select) and the same
+// three counters as integers; the four window bins follow by inclusion-exclusion at flush time (exact for
+// the counts, of the size of ordinary summation rounding for the FP64 sums).
+//
+// Mirrored entry.  Every pair is also entered at (-dx,-dy).  The grid is point symmetric, so the mirrored
+// bin of a pair is "almost always" the mirror image (nbins-1-ix, nbins-1-iy) of its forward bin; it can
+// differ only when a displacement sits within rounding of a bin edge, because the thresholds of the
+// TreeCorr formula are not exactly symmetric in floating point.  The window of the mirrored entry is
+// therefore fixed to the mirror image of the forward window, the exact mirrored bits qx, qy are still
+// evaluated for every pair, and `mmc` counts the pairs for which (qx, qy) != (!px, !py).  The forward
+// registers are flushed into both the forward bins and their mirror images; blocks with mmc != 0 are
+// rescanned and the (rare) inconsistent pairs moved from the assumed to the exact mirrored bin.
 template <bool WEIGHTED>
 struct RegAcc {
-  double tot, fsx, fsy, fsxy, rsx, rsy, rsxy;
-  double wtot, fwx, fwy, fwxy, rwx, rwy, rwxy;   // weights (WEIGHTED only)
-  unsigned fcx, fcy, fcxy, rcx, rcy, rcxy, nin;
-  int fx0, fy0, rx0, ry0;    // window origins (bins); fx0 == -1: no open window
-  long long ownerI;          // row tile the per-lane thresholds were derived for
+  double tot, fsx, fsy, fsxy;
+  double wtot, fwx, fwy, fwxy;   // weights (WEIGHTED only)
+  unsigned fcx, fcy, fcxy, nin, mmc;
+  int fx0, fy0;              // forward window origin (bins); fx0 == -1: no open window.  Mirrored window
+                             // origin: (nbins-2-fx0, nbins-2-fy0)
+  long long ownerI;          // row block the per-lane thresholds were derived for
   // Per-lane thresholds on the COLUMN point's coordinates, equivalent to the bin thresholds on the
   // displacement because rounding is monotone:  fl(xj - xi) >= t  <=>  xj >= Tx(xi, t).
-  double Tx, Ty, RTx, RTy;   // forward: px = xj >= Tx ; mirrored: px = xj <= RTx
+  double Tx, Ty, RTx, RTy;   // forward: px = xj >= Tx ; mirrored: qx = xj <= RTx
   __device__ __forceinline__ void zero() {
-    tot = fsx = fsy = fsxy = rsx = rsy = rsxy = 0.0;
-    wtot = fwx = fwy = fwxy = rwx = rwy = rwxy = 0.0;
-    fcx = fcy = fcxy = rcx = rcy = rcxy = nin = 0u;
+    tot = fsx = fsy = fsxy = 0.0;
+    wtot = fwx = fwy = fwxy = 0.0;
+    fcx = fcy = fcxy = nin = mmc = 0u;
   }
 };
 
@@ -179,86 +188,73 @@ __device__ __forceinline__ double pb_coord_le(double xi, double t, bool& ok) {
 }
 
 // One pair into the window registers.  Written in PTX: four compares give the window bits of the
-// forward and of the mirrored entry, each masked sum is one FMA with a 0.0 / 1.0 mask, and each counter
-// one predicated integer add (nvcc's code for the equivalent C++ needs ~2x the instructions).
+// forward entry and the exact bits of the mirrored entry, each masked sum is one FMA with a 0.0 / 1.0
+// mask, each counter one predicated integer add (nvcc's code for the equivalent C++ needs ~2x the
+// instructions).
 #define PB_ONE "0d3FF0000000000000"
 #define PB_ZERO "0d0000000000000000"
 #define PB_PAIR(A, XJ, YJ, KK)                                                                      \
   asm volatile(                                                                                     \
       "{\n\t"                                                                                       \
-      ".reg .pred px, py, qx, qy, pxy, qxy;\n\t"                                                    \
-      ".reg .f64 m0, m1, m2, m3, m4, m5;\n\t"                                                       \
-      "setp.ge.f64 px, %14, %16;\n\t"                                                               \
-      "setp.ge.f64 py, %15, %17;\n\t"                                                               \
-      "setp.le.f64 qx, %14, %18;\n\t"                                                               \
-      "setp.le.f64 qy, %15, %19;\n\t"                                                               \
+      ".reg .pred px, py, qx, qy, pxy, cx, cy, mm;\n\t"                                             \
+      ".reg .f64 m0, m1, m2;\n\t"                                                                   \
+      "setp.ge.f64 px, %9, %11;\n\t"                                                                \
+      "setp.ge.f64 py, %10, %12;\n\t"                                                               \
+      "setp.le.f64 qx, %9, %13;\n\t"                                                                \
+      "setp.le.f64 qy, %10, %14;\n\t"                                                               \
       "and.pred pxy, px, py;\n\t"                                                                   \
-      "and.pred qxy, qx, qy;\n\t"                                                                   \
+      "xor.pred cx, px, qx;\n\t"                                                                    \
+      "xor.pred cy, py, qy;\n\t"                                                                    \
+      "and.pred mm, cx, cy;\n\t"                                                                    \
+      "not.pred mm, mm;\n\t"                                                                        \
       "selp.f64 m0, " PB_ONE ", " PB_ZERO ", px;\n\t"                                               \
       "selp.f64 m1, " PB_ONE ", " PB_ZERO ", py;\n\t"                                               \
       "selp.f64 m2, " PB_ONE ", " PB_ZERO ", pxy;\n\t"                                              \
-      "selp.f64 m3, " PB_ONE ", " PB_ZERO ", qx;\n\t"                                               \
-      "selp.f64 m4, " PB_ONE ", " PB_ZERO ", qy;\n\t"                                               \
-      "selp.f64 m5, " PB_ONE ", " PB_ZERO ", qxy;\n\t"                                              \
-      "add.f64 %0, %0, %13;\n\t"                                                                    \
-      "fma.rn.f64 %1, %13, m0, %1;\n\t"                                                             \
-      "fma.rn.f64 %2, %13, m1, %2;\n\t"                                                             \
-      "fma.rn.f64 %3, %13, m2, %3;\n\t"                                                             \
-      "fma.rn.f64 %4, %13, m3, %4;\n\t"                                                             \
-      "fma.rn.f64 %5, %13, m4, %5;\n\t"                                                             \
-      "fma.rn.f64 %6, %13, m5, %6;\n\t"                                                             \
-      "@px add.u32 %7, %7, 1;\n\t"                                                                  \
-      "@py add.u32 %8, %8, 1;\n\t"                                                                  \
-      "@pxy add.u32 %9, %9, 1;\n\t"                                                                 \
-      "@qx add.u32 %10, %10, 1;\n\t"                                                                \
-      "@qy add.u32 %11, %11, 1;\n\t"                                                                \
-      "@qxy add.u32 %12, %12, 1;\n\t"                                                               \
+      "add.f64 %0, %0, %8;\n\t"                                                                     \
+      "fma.rn.f64 %1, %8, m0, %1;\n\t"                                                              \
+      "fma.rn.f64 %2, %8, m1, %2;\n\t"                                                              \
+      "fma.rn.f64 %3, %8, m2, %3;\n\t"                                                              \
+      "@px add.u32 %4, %4, 1;\n\t"                                                                  \
+      "@py add.u32 %5, %5, 1;\n\t"                                                                  \
+      "@pxy add.u32 %6, %6, 1;\n\t"                                                                 \
+      "@mm add.u32 %7, %7, 1;\n\t"                                                                  \
       "}\n"                                                                                         \
-      : "+d"(A.tot), "+d"(A.fsx), "+d"(A.fsy), "+d"(A.fsxy), "+d"(A.rsx), "+d"(A.rsy), "+d"(A.rsxy), \
-        "+r"(A.fcx), "+r"(A.fcy), "+r"(A.fcxy), "+r"(A.rcx), "+r"(A.rcy), "+r"(A.rcxy)              \
+      : "+d"(A.tot), "+d"(A.fsx), "+d"(A.fsy), "+d"(A.fsxy), "+r"(A.fcx), "+r"(A.fcy), "+r"(A.fcxy), \
+        "+r"(A.mmc)                                                                                 \
       : "d"(KK), "d"(XJ), "d"(YJ), "d"(A.Tx), "d"(A.Ty), "d"(A.RTx), "d"(A.RTy))
 
 #define PB_PAIR_W(A, XJ, YJ, KK, WW)                                                                \
   asm volatile(                                                                                     \
       "{\n\t"                                                                                       \
-      ".reg .pred px, py, qx, qy, pxy, qxy;\n\t"                                                    \
-      ".reg .f64 m0, m1, m2, m3, m4, m5;\n\t"                                                       \
-      "setp.ge.f64 px, %22, %24;\n\t"                                                               \
-      "setp.ge.f64 py, %23, %25;\n\t"                                                               \
-      "setp.le.f64 qx, %22, %26;\n\t"                                                               \
-      "setp.le.f64 qy, %23, %27;\n\t"                                                               \
+      ".reg .pred px, py, qx, qy, pxy, cx, cy, mm;\n\t"                                             \
+      ".reg .f64 m0, m1, m2;\n\t"                                                                   \
+      "setp.ge.f64 px, %14, %16;\n\t"                                                               \
+      "setp.ge.f64 py, %15, %17;\n\t"                                                               \
+      "setp.le.f64 qx, %14, %18;\n\t"                                                               \
+      "setp.le.f64 qy, %15, %19;\n\t"                                                               \
       "and.pred pxy, px, py;\n\t"                                                                   \
-      "and.pred qxy, qx, qy;\n\t"                                                                   \
+      "xor.pred cx, px, qx;\n\t"                                                                    \
+      "xor.pred cy, py, qy;\n\t"                                                                    \
+      "and.pred mm, cx, cy;\n\t"                                                                    \
+      "not.pred mm, mm;\n\t"                                                                        \
       "selp.f64 m0, " PB_ONE ", " PB_ZERO ", px;\n\t"                                               \
       "selp.f64 m1, " PB_ONE ", " PB_ZERO ", py;\n\t"                                               \
       "selp.f64 m2, " PB_ONE ", " PB_ZERO ", pxy;\n\t"                                              \
-      "selp.f64 m3, " PB_ONE ", " PB_ZERO ", qx;\n\t"                                               \
-      "selp.f64 m4, " PB_ONE ", " PB_ZERO ", qy;\n\t"                                               \
-      "selp.f64 m5, " PB_ONE ", " PB_ZERO ", qxy;\n\t"                                              \
-      "add.f64 %0, %0, %20;\n\t"                                                                    \
-      "fma.rn.f64 %1, %20, m0, %1;\n\t"                                                             \
-      "fma.rn.f64 %2, %20, m1, %2;\n\t"                                                             \
-      "fma.rn.f64 %3, %20, m2, %3;\n\t"                                                             \
-      "fma.rn.f64 %4, %20, m3, %4;\n\t"                                                             \
-      "fma.rn.f64 %5, %20, m4, %5;\n\t"                                                             \
-      "fma.rn.f64 %6, %20, m5, %6;\n\t"                                                             \
-      "add.f64 %7, %7, %21;\n\t"                                                                    \
-      "fma.rn.f64 %8, %21, m0, %8;\n\t"                                                             \
-      "fma.rn.f64 %9, %21, m1, %9;\n\t"                                                             \
-      "fma.rn.f64 %10, %21, m2, %10;\n\t"                                                           \
-      "fma.rn.f64 %11, %21, m3, %11;\n\t"                                                           \
-      "fma.rn.f64 %12, %21, m4, %12;\n\t"                                                           \
-      "fma.rn.f64 %13, %21, m5, %13;\n\t"                                                           \
-      "@px add.u32 %14, %14, 1;\n\t"                                                                \
-      "@py add.u32 %15, %15, 1;\n\t"                                                                \
-      "@pxy add.u32 %16, %16, 1;\n\t"                                                               \
-      "@qx add.u32 %17, %17, 1;\n\t"                                                                \
-      "@qy add.u32 %18, %18, 1;\n\t"                                                                \
-      "@qxy add.u32 %19, %19, 1;\n\t"                                                               \
+      "add.f64 %0, %0, %12;\n\t"                                                                    \
+      "fma.rn.f64 %1, %12, m0, %1;\n\t"                                                             \
+      "fma.rn.f64 %2, %12, m1, %2;\n\t"                                                             \
+      "fma.rn.f64 %3, %12, m2, %3;\n\t"                                                             \
+      "add.f64 %4, %4, %13;\n\t"                                                                    \
+      "fma.rn.f64 %5, %13, m0, %5;\n\t"                                                             \
+      "fma.rn.f64 %6, %13, m1, %6;\n\t"                                                             \
+      "fma.rn.f64 %7, %13, m2, %7;\n\t"                                                             \
+      "@px add.u32 %8, %8, 1;\n\t"                                                                  \
+      "@py add.u32 %9, %9, 1;\n\t"                                                                  \
+      "@pxy add.u32 %10, %10, 1;\n\t"                                                               \
+      "@mm add.u32 %11, %11, 1;\n\t"                                                                \
       "}\n"                                                                                         \
-      : "+d"(A.tot), "+d"(A.fsx), "+d"(A.fsy), "+d"(A.fsxy), "+d"(A.rsx), "+d"(A.rsy), "+d"(A.rsxy), \
-        "+d"(A.wtot), "+d"(A.fwx), "+d"(A.fwy), "+d"(A.fwxy), "+d"(A.rwx), "+d"(A.rwy), "+d"(A.rwxy), \
-        "+r"(A.fcx), "+r"(A.fcy), "+r"(A.fcxy), "+r"(A.rcx), "+r"(A.rcy), "+r"(A.rcxy)              \
+      : "+d"(A.tot), "+d"(A.fsx), "+d"(A.fsy), "+d"(A.fsxy), "+d"(A.wtot), "+d"(A.fwx), "+d"(A.fwy), \
+        "+d"(A.fwxy), "+r"(A.fcx), "+r"(A.fcy), "+r"(A.fcxy), "+r"(A.mmc)                           \
       : "d"(KK), "d"(WW), "d"(XJ), "d"(YJ), "d"(A.Tx), "d"(A.Ty), "d"(A.RTx), "d"(A.RTy))
 
 enum { PB_OUT = 0, PB_REG_FULL = 1, PB_REG_CHECK = 2, PB_GENERIC = 3 };
@@ -333,37 +329,29 @@ pairbin_kernel(PBParams P) {
     if (A.fx0 >= 0) {
       const unsigned n_in = warp_sum_u(A.nin);
       const unsigned fcx = warp_sum_u(A.fcx), fcy = warp_sum_u(A.fcy), fcxy = warp_sum_u(A.fcxy);
-      const unsigned rcx = warp_sum_u(A.rcx), rcy = warp_sum_u(A.rcy), rcxy = warp_sum_u(A.rcxy);
       const double tot = warp_sum(A.tot);
       const double fsx = warp_sum(A.fsx), fsy = warp_sum(A.fsy), fsxy = warp_sum(A.fsxy);
-      const double rsx = warp_sum(A.rsx), rsy = warp_sum(A.rsy), rsxy = warp_sum(A.rsxy);
-      double wtot = 0, fwx = 0, fwy = 0, fwxy = 0, rwx = 0, rwy = 0, rwxy = 0;
+      double wtot = 0, fwx = 0, fwy = 0, fwxy = 0;
       if constexpr (WEIGHTED) {
         wtot = warp_sum(A.wtot);
         fwx = warp_sum(A.fwx); fwy = warp_sum(A.fwy); fwxy = warp_sum(A.fwxy);
-        rwx = warp_sum(A.rwx); rwy = warp_sum(A.rwy); rwxy = warp_sum(A.rwxy);
       }
       if (lane == 0 && n_in) {
         // inclusion-exclusion per window bin (index = bx + 2*by)
         const unsigned fc[4] = {n_in - fcx - fcy + fcxy, fcx - fcxy, fcy - fcxy, fcxy};
-        const unsigned rc[4] = {n_in - rcx - rcy + rcxy, rcx - rcxy, rcy - rcxy, rcxy};
         const double fs[4] = {(tot - fsx) - (fsy - fsxy), fsx - fsxy, fsy - fsxy, fsxy};
-        const double rs[4] = {(tot - rsx) - (rsy - rsxy), rsx - rsxy, rsy - rsxy, rsxy};
         const double fw[4] = {(wtot - fwx) - (fwy - fwxy), fwx - fwxy, fwy - fwxy, fwxy};
-        const double rw[4] = {(wtot - rwx) - (rwy - rwxy), rwx - rwxy, rwy - rwxy, rwxy};
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           if (fc[b]) {  // a non-empty bin is always inside the grid; the histogram is private to this warp
-            const int o = (A.fy0 + (b >> 1)) * nbins + A.fx0 + (b & 1);
+            const int bx = A.fx0 + (b & 1), by = A.fy0 + (b >> 1);
+            const int o = by * nbins + bx;                                 // forward entry
+            const int om = (nbins - 1 - by) * nbins + (nbins - 1 - bx);    // mirrored entry
             my_c[o] += fc[b];
             my_s[o] += fs[b];
-            if constexpr (WEIGHTED) my_w[o] += fw[b];
-          }
-          if (rc[b]) {
-            const int o = (A.ry0 + (b >> 1)) * nbins + A.rx0 + (b & 1);
-            my_c[o] += rc[b];
-            my_s[o] += rs[b];
-            if constexpr (WEIGHTED) my_w[o] += rw[b];
+            my_c[om] += fc[b];
+            my_s[om] += fs[b];
+            if constexpr (WEIGHTED) { my_w[o] += fw[b]; my_w[om] += fw[b]; }
           }
         }
       }
@@ -371,6 +359,38 @@ pairbin_kernel(PBParams P) {
       A.zero();
       A.fx0 = -1;
     }
+  };
+  // Rare: some pair of the block just processed has a mirrored bin that is not the mirror image of its
+  // forward bin.  Rescan the block and move those pairs from the assumed to the exact mirrored bin.
+  auto fix_mirror = [&](int j0, int jn, bool check, double xi, double yi, double ki, double wi) {
+    if (!__any_sync(0xffffffffu, A.mmc != 0u)) return;
+    if (A.mmc) {
+      const int rx0 = nbins - 2 - A.fx0, ry0 = nbins - 2 - A.fy0;
+      for (int jj = j0; jj < j0 + jn; ++jj) {
+        const double2 pj = cxy[jj];
+        if (check) {
+          const double dx = pj.x - xi, dy = pj.y - yi;
+          const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+          if (!(r2 >= P.lo2 && fabs(dx) < P.hi && fabs(dy) < P.hi)) continue;
+        }
+        const bool px = pj.x >= A.Tx, py = pj.y >= A.Ty, qx = pj.x <= A.RTx, qy = pj.y <= A.RTy;
+        if ((px != qx) && (py != qy)) continue;  // consistent
+        const int assumed = (nbins - 1 - (A.fy0 + (py ? 1 : 0))) * nbins + (nbins - 1 - (A.fx0 + (px ? 1 : 0)));
+        const int exact = (ry0 + (qy ? 1 : 0)) * nbins + (rx0 + (qx ? 1 : 0));
+        const double kk = ki * ck[jj];
+        atomicAdd(my_c + assumed, 0xffffffffu);  // -1 (mod 2^32); the +1 arrives with the register flush
+        atomicAdd(my_c + exact, 1u);
+        atomicAdd(my_s + assumed, -kk);
+        atomicAdd(my_s + exact, kk);
+        if constexpr (WEIGHTED) {
+          const double ww = wi * cw[jj];
+          atomicAdd(my_w + assumed, -ww);
+          atomicAdd(my_w + exact, ww);
+        }
+      }
+      A.mmc = 0u;
+    }
+    __syncwarp();
   };
   // Warp-private shared histogram -> global (red.global), then clear.
   auto flush_hist = [&](int cat) {
@@ -591,18 +611,31 @@ pairbin_kernel(PBParams P) {
           // ---- register path: make sure the open window covers this block ----
           const int x0 = bw[0] & 0xffff, x1 = x0 + (bw[0] >> 16), y0 = bw[1] & 0xffff, y1 = y0 + (bw[1] >> 16);
           const int rx0 = bw[2] & 0xffff, rx1 = rx0 + (bw[2] >> 16), ry0 = bw[3] & 0xffff, ry1 = ry0 + (bw[3] >> 16);
-          const bool fits = A.fx0 >= 0 && A.ownerI == owner && x0 >= A.fx0 && x1 <= A.fx0 + 1 && y0 >= A.fy0 &&
-                            y1 <= A.fy0 + 1 && rx0 >= A.rx0 && rx1 <= A.rx0 + 1 && ry0 >= A.ry0 && ry1 <= A.ry0 + 1;
+          // the mirrored window is the mirror image [n-2-f0, n-1-f0] of the forward window [f0, f0+1]
+          auto covers = [&](int fx0, int fy0) {
+            return fx0 >= 0 && fy0 >= 0 && x0 >= fx0 && x1 <= fx0 + 1 && y0 >= fy0 && y1 <= fy0 + 1 &&
+                   rx0 >= nbins - 2 - fx0 && rx1 <= nbins - 1 - fx0 && ry0 >= nbins - 2 - fy0 && ry1 <= nbins - 1 - fy0;
+          };
+          const bool fits = A.fx0 >= 0 && A.ownerI == owner && covers(A.fx0, A.fy0);
           if (!fits) {
             flush_regs();
-            // a window [b0, b0+1] must stay inside the grid unless nbins == 1
-            A.fx0 = min(x0, max(nbins - 2, 0)); A.fy0 = min(y0, max(nbins - 2, 0));
-            A.rx0 = min(rx0, max(nbins - 2, 0)); A.ry0 = min(ry0, max(nbins - 2, 0));
+            // candidate origins: the block's lowest bin, or one below it (a window must stay inside the grid
+            // unless nbins == 1)
+            const int hi0 = max(nbins - 2, 0);
+            int fx0 = min(x0, hi0), fy0 = min(y0, hi0);
+            if (!covers(fx0, fy0)) {
+              const int ax = (x1 == x0 && x0 >= 1) ? x0 - 1 : fx0, ay = (y1 == y0 && y0 >= 1) ? y0 - 1 : fy0;
+              if (covers(ax, fy0)) fx0 = ax;
+              else if (covers(fx0, ay)) fy0 = ay;
+              else if (covers(ax, ay)) { fx0 = ax; fy0 = ay; }
+              else { generic_block(j0, jn, 0, xi, yi, ki, wi, live); continue; }  // edge asymmetry: exact path
+            }
+            A.fx0 = fx0; A.fy0 = fy0;
             A.ownerI = owner;
-            // bit = (bin >= b0 + 1): forward dx >= ed[b0+1]; mirrored -dx >= ed[b0+1] <=> dx <= -ed[b0+1];
-            // turned into thresholds on the column coordinate for this lane's row point
-            const double tx = (nbins > 1) ? ed[A.fx0 + 1] : INFINITY, ty = (nbins > 1) ? ed[A.fy0 + 1] : INFINITY;
-            const double ntx = (nbins > 1) ? -ed[A.rx0 + 1] : -INFINITY, nty = (nbins > 1) ? -ed[A.ry0 + 1] : -INFINITY;
+            // bit = (bin >= b0 + 1): forward dx >= ed[b0+1]; mirrored -dx >= ed[r0+1] <=> dx <= -ed[r0+1] with
+            // r0 = nbins-2-b0; turned into thresholds on the column coordinate for this lane's row point
+            const double tx = (nbins > 1) ? ed[fx0 + 1] : INFINITY, ty = (nbins > 1) ? ed[fy0 + 1] : INFINITY;
+            const double ntx = -ed[nbins - 1 - fx0], nty = -ed[nbins - 1 - fy0];   // ed[0] = -inf when nbins == 1
             bool okl = true;
             A.Tx = pb_coord_ge(xi, tx, okl);
             A.Ty = pb_coord_ge(yi, ty, okl);
@@ -628,6 +661,8 @@ pairbin_kernel(PBParams P) {
               }
             }
             A.nin += live ? (unsigned)jn : 0u;
+            if (!live) A.mmc = 0u;  // dead lanes (NaN coordinates) compare false everywhere: not a mismatch
+            fix_mirror(j0, jn, false, xi, yi, ki, wi);
           } else {
 #pragma unroll 2
             for (int jj = j0; jj < j0 + jn; ++jj) {
@@ -646,6 +681,7 @@ pairbin_kernel(PBParams P) {
                 A.nin += 1u;
               }
             }
+            fix_mirror(j0, jn, true, xi, yi, ki, wi);
           }
         }
       }
