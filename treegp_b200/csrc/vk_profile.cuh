@@ -8,8 +8,8 @@
 //
 // Algebra:  with z = 2 pi d,  f = 2^(1/6)/Gamma(5/6) * z^(5/6) K_{5/6}(z).
 //   z <  1 : ascending series in u = z^2/4 = pi^2 q:  f = A(u) - u^(5/6) B(u)      (no sqrt of q needed)
-//   z >= 1 : f = C_INF * cbrt(z) * exp(-z) * phi(z), phi tabulated per binade of z as a
-//            polynomial in the mantissa (no division, no iteration).
+//   z >= 1 : f = C_INF * exp(-z) * psi(z), psi = z^(1/3) phi(z) tabulated per binade of z as a
+//            polynomial in the mantissa (no cube root, no division, no iteration).
 // Tables come from tools/gen_vk_tables.py (mpmath, 60 digits).  Measured error vs mpmath: see
 // tests/test_vk_profile.py (a few ulp relative over the whole range).
 //
@@ -94,7 +94,7 @@ TGP_HD double tgp_vk_large(double z, const double* __restrict__ phi) {
   double acc = c[TGP_VK_PHI_STRIDE - 1];
 #pragma unroll
   for (int k = TGP_VK_PHI_STRIDE - 2; k >= 0; --k) acc = tgp_fma(acc, s, c[k]);
-  return TGP_VK_C_INF * cbrt(z) * exp(-z) * acc;
+  return TGP_VK_C_INF * exp(-z) * acc;
 }
 
 // f(q); q >= 0.  q == 0 returns exactly 1 (reference: kernels.py:260-262, :275, :367, :380).
