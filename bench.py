@@ -115,6 +115,9 @@ def load_peaks():
 # ------------------------------------------------------------------------------------------------
 def cpu_pairbin_sample(X, y, min_sep, max_sep, rows):
     """Time the oracle (C, OpenMP, all host cores) on rows [0, rows) of the pair matrix."""
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU baseline is meant to use all host cores
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 or "OMP_NUM_THREADS" not in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     from oracle import pairbin_oracle as po
 
     n = len(y)
