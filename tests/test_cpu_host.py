@@ -225,3 +225,71 @@ def test_product_path_never_falls_back_to_cpu():
     gp.initialize(np.zeros((3, 2)), np.zeros(3))
     with pytest.raises(_cabi.TgpError):
         gp.predict(np.zeros((2, 2)))
+
+
+# ---- mean function producer and E/B diagnostics (SURVEY 8f "next" rows, host-side) ---------------------
+@pytest.mark.parametrize("stat", ["mean", "median", "weighted"])
+def test_meanify_matches_binned_statistic(stat, tmp_path):
+    """tests/test_meanify.py:43-64 shape: many fields, paraboloid mean, bin_spacing 40."""
+    from scipy.stats import binned_statistic_2d
+    import treegp_b200 as treegp
+    from treegp_b200.meanify import read_average
+
+    rng = np.random.default_rng(0)
+    m = treegp.meanify(bin_spacing=40.0, statistics=stat)
+    C, P, E = [], [], []
+    for _ in range(30):
+        c = rng.uniform(-1000, 1000, (500, 2))
+        p = 1e-6 * (c[:, 0] ** 2 + c[:, 1] ** 2) + rng.normal(0, 0.01, 500)
+        e = 0.01 * rng.uniform(0.5, 2, 500)
+        m.add_field(c, p, params_err=e if stat == "weighted" else None)
+        C.append(c); P.append(p); E.append(e)
+    m.meanify()
+    c, p, e = np.concatenate(C), np.concatenate(P), np.concatenate(E)
+    b = [np.linspace(c[:, 0].min(), c[:, 0].max(), int((c[:, 0].max() - c[:, 0].min()) / 40.0)),
+         np.linspace(c[:, 1].min(), c[:, 1].max(), int((c[:, 1].max() - c[:, 1].min()) / 40.0))]
+    if stat == "weighted":
+        w = 1 / e ** 2
+        with np.errstate(invalid="ignore"):
+            ref = (binned_statistic_2d(c[:, 0], c[:, 1], w * p, bins=b, statistic="sum")[0]
+                   / binned_statistic_2d(c[:, 0], c[:, 1], w, bins=b, statistic="sum")[0])
+    else:
+        ref = binned_statistic_2d(c[:, 0], c[:, 1], p, bins=b, statistic=stat)[0]
+    np.testing.assert_allclose(m._average, ref.T, rtol=0, atol=1e-14, equal_nan=True)
+    truth = 1e-6 * (m.coords0[:, 0] ** 2 + m.coords0[:, 1] ** 2)
+    np.testing.assert_allclose(m.params0, truth, atol=0.2)   # reference tolerance, tests/test_meanify.py:59-60
+    path = str(tmp_path / "mean.fits")
+    m.save_results(path)
+    X0, y0 = read_average(path)
+    np.testing.assert_array_equal(X0, m.coords0)
+    np.testing.assert_array_equal(y0, m.params0)
+    with pytest.raises(ValueError):
+        treegp.meanify(statistics="mode")
+    with pytest.raises(ValueError):
+        treegp.meanify().add_field(np.zeros((3, 1)), np.zeros(3))
+
+
+def test_eb_decomposition_matches_all_pairs_formula():
+    """utils.vcorr (utils.py:5-74) restated without materialising all index pairs."""
+    import treegp_b200 as treegp
+    from treegp_b200.utils import vcorr
+
+    rng = np.random.default_rng(2)
+    n = 500
+    x, y, dx, dy = rng.uniform(0, 1, n), rng.uniform(0, 1, n), rng.normal(size=n), rng.normal(size=n)
+    lr, xp, xm, xc, xz = vcorr(x, y, dx, dy, rmin=0.01, rmax=1.0, dlogr=0.2)
+    i1, i2 = np.triu_indices(n, 1)
+    dr = (x[i2] - x[i1]) + 1j * (y[i2] - y[i1])
+    ld = np.log(np.abs(dr))
+    bins = int(np.ceil(np.log(1 / 0.01) / 0.2))
+    hr = (np.log(0.01), np.log(0.01) + bins * 0.2)
+    cnt = np.histogram(ld, bins=bins, range=hr)[0]
+    v = dx + 1j * dy
+    np.testing.assert_allclose(xp, np.histogram(ld, bins=bins, range=hr, weights=dx[i1] * dx[i2] + dy[i1] * dy[i2])[0] / cnt, atol=1e-13)
+    vv = v[i1] * v[i2] * np.conj(dr) ** 2 / np.abs(dr) ** 2
+    np.testing.assert_allclose(xm, np.histogram(ld, bins=bins, range=hr, weights=vv.real)[0] / cnt, atol=1e-13)
+    np.testing.assert_allclose(xc, np.histogram(ld, bins=bins, range=hr, weights=vv.imag)[0] / cnt, atol=1e-13)
+    xie, xib, logr = treegp.comp_eb(x, y, dx, dy, rmin=0.01, rmax=1.0, dlogr=0.2)
+    xie2, xib2, logr2 = treegp.comp_eb_treecorr(x, y, dx, dy, rmin=0.01, rmax=1.0, dlogr=0.2)
+    assert xie.shape == xib.shape == logr.shape == xie2.shape == (bins,)
+    np.testing.assert_allclose(xie + xib, xp, atol=1e-13)

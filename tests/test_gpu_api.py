@@ -193,3 +193,42 @@ def test_two_pcf_matches_oracle_and_bootstrap_is_batched(gpu_ready):
         xis = np.array(xis)
         d = xis - xis.mean(axis=0)
         np.testing.assert_allclose(cov, d.T @ d / (B - 1.0), rtol=0, atol=1e-12)
+
+
+def test_gpinterp_around_a_meanify_mean_function(gpu_ready, tmp_path):
+    """tests/test_meanify.py:68-129 shape: a GP on top of a spatial average read from a meanify FITS table
+    (KNN(4) lookup, gp_interp.py:229-243); the mean file is produced by treegp_b200.meanify itself."""
+    import treegp_b200 as treegp
+
+    rng = np.random.default_rng(11)
+
+    def mean_fn(c):
+        return 0.1 + 2e-3 * (c[:, 0] ** 2 + c[:, 1] ** 2) / 100.0
+
+    m = treegp.meanify(bin_spacing=1.0, statistics="mean")
+    for _ in range(40):
+        c = rng.uniform(-10, 10, (2000, 2))
+        m.add_field(c, mean_fn(c) + rng.normal(0, 0.002, 2000))
+    m.meanify()
+    path = str(tmp_path / "mean_gp.fits")
+    m.save_results(path)
+
+    kernel = _aniso_kernel_string(0.1, "AnisotropicRBF", 0.8, 0.1, 0.1)
+    truth = treegp.eval_kernel(kernel)
+    x, y, y_err = make_grf(truth, 2, 1500, noise=0.005)
+    y = y + mean_fn(x)
+    gp = treegp.GPInterpolation(kernel=kernel, optimizer="anisotropic", normalize=True, average_fits=path, nbins=21,
+                                min_sep=0.0, max_sep=1.6, p0=[0.5, 0.0, 0.0])
+    gp.initialize(x, y, y_err=y_err)
+    assert np.std(y - gp._spatial_average) < 0.7 * np.std(y)  # the mean function was removed
+    gp.solve()
+    np.testing.assert_allclose(truth.theta, gp.kernel.theta, atol=5e-1)
+    y_predict, y_cov = gp.predict(x, return_cov=True)
+    pull = y - y_predict
+    assert abs(np.mean(pull)) < 3.0 * np.std(pull) / np.sqrt(len(y))
+    far = np.array([[9.5, 9.5], [-9.0, 3.0]])
+    # where the GP has nothing to say (sigma^2 = 0.01 vs the mean's range of 0.4) predictions follow the mean
+    yp = gp.predict(far)
+    np.testing.assert_allclose(yp, mean_fn(far), atol=0.35)
+    with pytest.raises(NotImplementedError):
+        treegp.GPInterpolation(kernel=kernel, optimizer="none").plot_fitted_kernel()

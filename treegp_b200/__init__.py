@@ -9,6 +9,8 @@ from .kernels import AnisotropicRBF, AnisotropicVonKarman, VonKarman, eval_kerne
 from .log_likelihood import log_likelihood
 from .two_pcf import two_pcf
 from .gp_interp import GPInterpolation
+from .meanify import meanify
+from .utils import comp_eb, comp_eb_treecorr
 
 __version__ = "0.1.0"
 
@@ -21,4 +23,7 @@ __all__ = [
     "VonKarman",
     "AnisotropicVonKarman",
     "eval_kernel",
+    "meanify",
+    "comp_eb",
+    "comp_eb_treecorr",
 ]

@@ -276,3 +276,41 @@ class GPInterpolation(object):
             kernel = kernel.clone_with_theta(theta)
         logl = log_likelihood(self._X, self._y - self._mean - self._spatial_average, self._y_err)
         return logl.log_likelihood(kernel)
+
+    def plot_fitted_kernel(self):
+        """Figure with the measured 2-D 2-point correlation function, the fitted kernel and their
+        difference (gp_interp.py:293-377).  Host-only; needs matplotlib (imported lazily, as in the
+        reference -- an ImportError surfaces if it is not installed)."""
+        if self.optimizer in ["none", "log-likehood", "two-pcf"]:
+            raise NotImplementedError("This method is only available for anisotropic optimizer")
+        import os
+
+        if os.getenv("GITHUB_ACTIONS") == "true":
+            import matplotlib
+
+            matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+
+        opt = self._optimizer
+        lag = opt._2pcf_dist
+        extent = [lag[:, 0].min(), lag[:, 0].max(), lag[:, 1].min(), lag[:, 1].max()]
+        n = int(np.sqrt(len(opt._2pcf)))
+        vmax = np.max(opt._2pcf)
+        panels = [(opt._2pcf.reshape(n, n), "Measured 2-PCF", "$\\xi$"),
+                  (opt._2pcf_fit.reshape(n, n), "Fitted 2-PCF", "$\\xi'$"),
+                  (opt._2pcf.reshape(n, n) - opt._2pcf_fit.reshape(n, n), "Difference", "$\\xi - \\xi'$")]
+        fig = plt.figure(figsize=(14, 4))
+        plt.subplots_adjust(wspace=0.5, left=0.07, right=0.95, bottom=0.1, top=0.92)
+        for i, (img, title, label) in enumerate(panels, start=1):
+            plt.subplot(1, 3, i)
+            plt.imshow(img, extent=extent, interpolation="nearest", origin="lower", vmin=-vmax, vmax=vmax,
+                       cmap=plt.cm.seismic)
+            cbar = plt.colorbar()
+            cbar.formatter.set_powerlimits((0, 0))
+            cbar.update_ticks()
+            cbar.set_label(label, fontsize=16)
+            plt.xlabel(r"$\Delta x$", fontsize=16)
+            if i == 1:
+                plt.ylabel(r"$\Delta y$", fontsize=16)
+            plt.title(title, fontsize=16)
+        return fig
