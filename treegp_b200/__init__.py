@@ -5,12 +5,15 @@ Public names mirror /root/reference/treegp/__init__.py:23-36: ``GPInterpolation`
 All O(N^2)/O(N^3) arithmetic runs in hand-written CUDA behind the C ABI of include/treegp_b200.h;
 there is no CPU fallback.
 """
-from .kernels import AnisotropicRBF, AnisotropicVonKarman, VonKarman, eval_kernel
-from .log_likelihood import log_likelihood
-from .two_pcf import two_pcf
-from .gp_interp import GPInterpolation
-from .meanify import meanify
-from .utils import comp_eb, comp_eb_treecorr
+from . import kernels as _k, log_likelihood as _ll, two_pcf as _tp, gp_interp as _gi, meanify as _mf, utils as _ut
+
+AnisotropicRBF, AnisotropicVonKarman, VonKarman, eval_kernel = (
+    _k.AnisotropicRBF, _k.AnisotropicVonKarman, _k.VonKarman, _k.eval_kernel)
+GPInterpolation = _gi.GPInterpolation
+# as in the reference, these two names are the classes (they shadow the sub-modules of the same name)
+log_likelihood, two_pcf = _ll.log_likelihood, _tp.two_pcf
+meanify = _mf.meanify
+comp_eb, comp_eb_treecorr = _ut.comp_eb, _ut.comp_eb_treecorr
 
 __version__ = "0.1.0"
 

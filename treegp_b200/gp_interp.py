@@ -23,26 +23,21 @@ from .two_pcf import two_pcf
 
 
 class GPInterpolation(object):
-    """
-    An interpolator that uses 2-point correlation function informations
-    or Maximum Likelihood informations to do a gaussian process to interpolate
-    a single surface.
+    """Gaussian-process interpolation of one scalar surface sampled at scattered 1-D or 2-D positions.
 
-    :param kernel:       A string that can be `eval`ed to make a
-                         sklearn.gaussian_process.kernels.Kernel object.  [default: 'RBF(1)']
-    :param optimizer:    "none", "two-pcf" (1-D 2-point correlation function fit), "anisotropic"
-                         (2-D 2-point correlation function fit) or "log-likelihood".
-    :param normalize:    Whether to subtract the mean of the data.  [default: True]
-    :param p0:           Starting point [size, g1, g2] of the robust anisotropic fit.
-    :param white_noise:  Extra uncorrelated noise added in quadrature to y_err. [default: 0.]
-    :param n_neighbors:  Number of neighbours of the KNeighbors interpolation of the spatial
-                         average.  Used only if average_fits is not None. [default: 4]
-    :param average_fits: FITS file with the spatial average (meanify output). [default: None]
-    :param indice_meanify: Column of the average to use. [default: None]
-    :param nbins:        Number of bins (1-D) or its square root (2-D) of the 2-point correlation
-                         function. [default: 20]
-    :param min_sep:      Minimum separation of the 2-point correlation function. [default: None]
-    :param max_sep:      Maximum separation of the 2-point correlation function. [default: None]
+    Constructor keywords (names, order and defaults as in the reference):
+
+    kernel          kernel string, evaluated by `eval_kernel` (e.g. "4.0 * AnisotropicRBF(invLam=array(...))")
+    optimizer       "none" keeps the kernel as given; "two-pcf" / "anisotropic" fit it to the isotropic /
+                    two-dimensional 2-point correlation function; "log-likelihood" maximises the marginal
+                    likelihood
+    normalize       subtract the mean of the (mean-function-subtracted) data before solving
+    p0              start [size, g1, g2] of the robust anisotropic fit
+    white_noise     extra uncorrelated noise, added in quadrature to y_err
+    n_neighbors     neighbours averaged when looking up the mean function (average_fits only)
+    average_fits    FITS table written by `meanify` holding the mean function; indice_meanify picks a column
+    nbins           bins of the 1-D correlation function, or bins per axis of the 2-D one
+    min_sep,max_sep separation range of the correlation function (defaults chosen from the data)
     """
 
     def __init__(
@@ -93,7 +88,7 @@ class GPInterpolation(object):
 
     # ---------------------------------------------------------------------------------------
     def _fit(self, kernel, X, y, y_err):
-        """Update the Kernel with data (gp_interp.py:111-141)."""
+        """Run the configured optimizer on (X, y, y_err) and return the fitted kernel (gp_interp.py:111-141)."""
         self._alpha = None
         self._factor = None
         if self.optimizer in ["two-pcf", "anisotropic"]:
@@ -115,11 +110,8 @@ class GPInterpolation(object):
         return kernel
 
     def predict(self, X, return_cov=False):
-        """Predict responses to given coordinates.
-
-        :param X:  The coordinates at which to interpolate.  (n_samples, 1 or 2).
-        :returns:  Regressed parameters  (n_samples) [, covariance (n_samples, n_samples)]
-        """
+        """Posterior mean at the positions X (m, 1|2), plus the full (m, m) posterior covariance when
+        return_cov is set (gp_interp.py:143-166)."""
         y_interp, y_cov = self.return_gp_predict(
             self._y - self._mean - self._spatial_average,
             self._X,
@@ -165,14 +157,8 @@ class GPInterpolation(object):
         self._alpha = alpha.cpu().numpy()
 
     def return_gp_predict(self, y, X1, X2, kernel, y_err, return_cov=False):
-        """Compute interpolation with gaussian process for a given kernel (gp_interp.py:168-194).
-
-        :param y:      Values of the field.  (n_samples)
-        :param X1:     The coodinates of the field.  (n_samples, 1 or 2)
-        :param X2:     The coordinates at which to interpolate.  (n_samples, 1 or 2)
-        :param kernel: sklearn.gaussian_process kernel.
-        :param y_err:  Error of y. (n_samples)
-        """
+        """GP algebra for residuals y at X1 with errors y_err, evaluated at X2 with `kernel`
+        (gp_interp.py:168-194): returns (mean, covariance-or-None)."""
         self._ensure_solved(y, X1, kernel, y_err)
         Xd, desc, ws = self._factor
         n = Xd.shape[0]
@@ -189,13 +175,9 @@ class GPInterpolation(object):
         return y_predict, cov[:, :m].cpu().numpy()
 
     def initialize(self, X, y, y_err=None):
-        """Initialize both the interpolator to some state prefatory to any solve iterations and
-        initialize the field values for use with this interpolator (gp_interp.py:196-227).
-
-        :param X:     The coodinates of the field.  (n_samples, 1 or 2)
-        :param y:     Values of the field.  (n_samples)
-        :param y_err: Error of y. (n_samples)
-        """
+        """Attach the data: positions X (n, 1|2), values y (n,), optional errors y_err (n,); looks up the
+        mean function, folds in the white noise, computes the normalising mean and drops any cached
+        solve (gp_interp.py:196-227)."""
         self.kernel = copy.deepcopy(self.kernel_template)
         self._X = X
         self._y = y
@@ -221,11 +203,8 @@ class GPInterpolation(object):
         self._factor = None
 
     def _build_average_meanify(self, X):
-        """Spatial average from meanify output at the given coordinates: uniform mean of the
-        ``n_neighbors`` nearest grid values; zeros if no average_fits was given (gp_interp.py:229-243).
-
-        :param X: Coordinates where to interpolate. (n_samples, 1 or 2)
-        """
+        """Mean function at X: uniform mean of the `n_neighbors` nearest grid values of the meanify table,
+        or zeros when no table was given (gp_interp.py:229-243)."""
         X = np.asarray(X)
         if np.count_nonzero(self._X0) == 0:
             return np.zeros(len(X[:, 0]))
@@ -237,10 +216,7 @@ class GPInterpolation(object):
         return average
 
     def solve(self):
-        """Set up this GPInterp object.
-        Solve for hyperparameters if requested using 2-point correlation
-        function method or maximum likelihood (gp_interp.py:245-258).
-        """
+        """Fit the kernel hyper-parameters with the configured optimizer (gp_interp.py:245-258)."""
         self._init_theta = [copy.deepcopy(self.kernel).theta]
         self.kernel = self._fit(
             self.kernel,
@@ -250,9 +226,8 @@ class GPInterpolation(object):
         )
 
     def return_2pcf(self):
-        """
-        Return 2-point correlation function and its variance using Bootstrap (gp_interp.py:260-275).
-        """
+        """xi, its weight matrix, separations, bin coordinates and mask for the current data
+        (gp_interp.py:260-275)."""
         pcf = two_pcf(
             self._X,
             self._y - self._mean - self._spatial_average,
@@ -265,12 +240,8 @@ class GPInterpolation(object):
         return pcf.return_2pcf()
 
     def return_log_likelihood(self, theta=None):
-        """
-        Return of log likehood of gaussian process
-        for given hyperparameters (gp_interp.py:277-291).
-
-        :param theta: Array of hyperparamters. (default: None)
-        """
+        """Marginal log-likelihood of the current data for the current kernel, or for `theta` if given
+        (gp_interp.py:277-291)."""
         kernel = copy.deepcopy(self.kernel)
         if theta is not None:
             kernel = kernel.clone_with_theta(theta)

@@ -16,11 +16,10 @@ from .kernels import lower_kernel
 
 
 class log_likelihood(object):
-    """Return and optimize (if requested) the log likelihood of gaussian process.
+    """Marginal log-likelihood of a GP for a kernel, and its maximiser over the kernel's theta.
 
-    :param X:      Coordinates of the field.  (n_samples, 1 or 2)
-    :param y:      Values of the field.  (n_samples)
-    :param y_err:  Error of y. (n_samples)
+    X: (n, 1|2) positions; y: (n,) residual field values; y_err: (n,) one-sigma errors added in quadrature
+    on the diagonal.  Same constructor as the reference class of the same name.
     """
 
     def __init__(self, X, y, y_err):
@@ -41,12 +40,8 @@ class log_likelihood(object):
         return self._dev
 
     def log_likelihood(self, kernel):
-        """
-        Return of log likehood of gaussian process
-        for given hyperparameters.
-
-        :param kernel: Sklearn kernel object.
-        """
+        """log p(y | X, kernel) = -chi2/2 - n/2 ln(2 pi) - ln|K|/2, or -inf when K + diag(y_err^2) is not
+        positive definite.  `kernel` is a scikit-learn style kernel object."""
         Xd, yd, e2, work = self._device_state()
         desc = lower_kernel(kernel, Xd.shape[1])
         # a non-finite hyper-parameter cannot be factorised: the reference's try/except returns -inf
@@ -58,12 +53,8 @@ class log_likelihood(object):
         return float(out[0].item())  # -inf when the factorisation failed (info != 0)
 
     def optimizer(self, kernel):
-        """
-        Fit hyperparameter using maximum likelihood fit.
-        Used minimization with L-BFGS-B method from scipy.
-
-        :param kernel: sklearn.gaussian_process kernel.
-        """
+        """Maximise the likelihood over theta starting from `kernel.theta` (scipy L-BFGS-B, no bounds,
+        forward-difference gradient) and return the fitted kernel; keeps `_kernel` and `_logL`."""
 
         def minus_logl(theta):
             return -self.log_likelihood(kernel.clone_with_theta(theta))

@@ -32,13 +32,8 @@ from .migrad import Migrad
 
 
 def get_correlation_length_matrix(size, e1, e2):
-    """
-    Produce correlation matrix to introduce anisotropy in kernel (weak-lensing shear
-    parameterisation: an anisotropic kernel has an elliptical shape).
-
-    :param size:   Correlation lenght of the kernel.
-    :param e1, e2: Shear applied to isotropic kernel.
-    """
+    """2 x 2 correlation-length matrix of an elliptical kernel in the weak-lensing shear parameterisation:
+    `size` along the major axis, axis ratio (1-e)/(1+e) with e = |(e1, e2)|, position angle atan2(e2, e1)/2."""
     if abs(e1) > 1 or abs(e2) > 1:
         raise ValueError("abs value of e1 and e2 must be lower than one")
     e = np.sqrt(e1 ** 2 + e2 ** 2)
@@ -54,12 +49,8 @@ _ANISOTROPIC = (kernels.AnisotropicVonKarman, kernels.AnisotropicRBF)
 
 
 def get_kernel_class(A):
-    """
-    Check that the given kernel is an AnisotropicVonKarman or an AnisotropicRBF kernel (possibly
-    inside a Product) and return that class.
-
-    :param A: sklearn.gaussian_process.kernels
-    """
+    """Class of the anisotropic factor (AnisotropicRBF / AnisotropicVonKarman) of kernel A, which may be
+    that factor itself or a Product containing it; ValueError otherwise."""
     msg = "Work only with treegp.kernels.AnisotropicVonKarman and treegp.kernels.AnisotropicRBF"
     if isinstance(A, sklearn.gaussian_process.kernels.Product):
         found = [v.__class__ for v in vars(A).values() if v.__class__ in _ANISOTROPIC]
@@ -72,17 +63,10 @@ def get_kernel_class(A):
 
 
 class robust_2dfit(object):
-    """
-    Fit hyperparameters on 2D two-point correlation when the analytical profil can
-    be discribed as a Radial Basis Function such as a Gaussian kernel or a
-    von Karman kernel.
+    """Chi-square fit of (size, g1, g2) of an anisotropic kernel to a measured 2-D correlation function.
 
-    :param kernel:    sklearn.gaussian_process.kernels
-    :param x:         x coordinates of the 2D two point correlation function.
-    :param y:         y coordinates of the 2D two point correlation function.
-    :param flat_data: flatten 2D two point correlation function.
-    :param W:         Inverse of the covariance matrix got from Bootstrap.
-    :param mask:      Mask symetric area for Radial basi Function.
+    kernel: template kernel (selects the family); flat_data: flattened xi; x, y: lag of every pixel;
+    W: inverse covariance of the masked pixels; mask: pixels used (one half-plane of the symmetric map).
     """
 
     def __init__(self, kernel, flat_data, x, y, W, mask=None):
@@ -134,11 +118,7 @@ class robust_2dfit(object):
         return self.chi2_value[0]
 
     def _minimize_minuit(self, p0=[3000.0, 0.2, 0.2]):
-        """
-        Launch a single variable-metric (MIGRAD) minimization from a starting point.
-
-        :param p0: List of starting points.
-        """
+        """One variable-metric minimisation started at p0 = [size, g1, g2]."""
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             self.m = Migrad(self.chi2, p0)
@@ -151,12 +131,8 @@ class robust_2dfit(object):
         self.result = [np.sqrt(self.alpha[0][0]), results[0], results[1], results[2], self.alpha[1][0]]
 
     def minimize_minuit(self, p0=[3000.0, 0.2, 0.2]):
-        """
-        Launch the minimization given a starting point; restart on a 3x3x3 grid of starting points
-        if the minimiser did not converge (two_pcf.py:178-206).
-
-        :param p0: List of starting points.
-        """
+        """Minimise from p0; if that did not converge retry from a 3 x 3 x 3 grid of starts
+        (two_pcf.py:178-206)."""
         self._minimize_minuit(p0=p0)
 
         if not self._fit_ok:
@@ -175,19 +151,11 @@ class robust_2dfit(object):
 
 
 class two_pcf(object):
-    """
-    Fit statistical uncertaintie on two-point correlation function using bootstraping.
+    """2-point correlation function of a scalar field, its bootstrap covariance, and the kernel fit to it.
 
-    :param X:           Coordinates of the field.  (n_samples, 1 or 2)
-    :param y:           Values of the field. (n_samples)
-    :param y_err:       Error of y. (n_samples)
-    :param min_sep:     Minimum bin separation. (float)
-    :param max_sep:     Maximum bin separation. (float)
-    :param nbins:       Number of bins (1D) or square root of the number of bins (2D). [default: 20]
-    :param anisotropic: 2D 2-point correlation function (Boolean)
-    :param robust_fit:  Used the variable-metric robust fit; only if anisotropic is True. (Boolean)
-    :param p0:          Starting point of the robust fit.
-    :param seed:        Seed to use for random number generator.
+    X (n, 1|2), y (n,), y_err (n,): the field; min_sep, max_sep, nbins: binning (nbins per axis when
+    anisotropic); anisotropic: two-dimensional (dx, dy) map instead of log-r bins; robust_fit: variable-metric
+    fit of (size, g1, g2) with analytic amplitude/offset (anisotropic only), started at p0; seed: bootstrap seed.
     """
 
     def __init__(
@@ -232,9 +200,7 @@ class two_pcf(object):
         return self._rng
 
     def resample_bootstrap(self):
-        """
-        Make a single bootstrap resampling on data (two_pcf.py:269-281).
-        """
+        """One resample with replacement: (u, v, y, y_err) of the drawn points (two_pcf.py:269-281)."""
         npsfs = len(self.y)
         ind_object = self.rng.integers(0, npsfs - 1, size=npsfs)
         return (self.X[:, 0][ind_object], self.X[:, 1][ind_object], self.y[ind_object],
@@ -281,13 +247,8 @@ class two_pcf(object):
         return xi, distance, coord, np.ones_like(xi, dtype=bool)
 
     def comp_2pcf(self, X, y, y_err):
-        """
-        Estimate 2-point correlation function (two_pcf.py:283-340).
-
-        :param X:  Coordinates of the field. (n_samples, 2)
-        :param y:  Values of the field. (n_samples)
-        :param y_err: Error of y. (n_samples)
-        """
+        """xi, separations, bin coordinates and mask for the catalogue (X (n, 2), y, y_err)
+        (two_pcf.py:283-340)."""
         X = np.asarray(X, dtype=np.float64)
         y = np.asarray(y, dtype=np.float64)
         y_err = np.asarray(y_err, dtype=np.float64)
@@ -304,12 +265,8 @@ class two_pcf(object):
         return self._assemble(xi[0], None if meanr is None else meanr[0])
 
     def comp_xi_covariance(self, n_bootstrap=1000, mask=None, seed=610639139):
-        """
-        Estimate 2-point correlation function covariance matrix using Bootstrap
-        (two_pcf.py:342-362), all resamples in one batched launch.
-
-        :param seed: seed of the random generator.
-        """
+        """Sample covariance of xi[mask] over n_bootstrap resamples (two_pcf.py:342-362); all resamples go
+        through one batched launch."""
         self.seed = seed
         self._rng = None
         xi_bootstrap = self._bootstrap_xi(int(n_bootstrap))
@@ -363,11 +320,8 @@ class two_pcf(object):
         return np.concatenate(out, axis=0)
 
     def return_2pcf(self, seed=610639139):
-        """
-        Return 2-point correlation function and its variance using Bootstrap (two_pcf.py:364-391).
-
-        :param seed: seed of the random generator.
-        """
+        """xi, its weight matrix (de-biased inverse bootstrap covariance, or 1/var(y) when isotropic),
+        separations, bin coordinates and mask (two_pcf.py:364-391)."""
         xi, distance, coord, mask = self.comp_2pcf(self.X, self.y, self.y_err)
         if self.anisotropic:
             # number of resamples from Taylor et al. 2012 (https://doi.org/10.1093/mnras/stt270) eq. 35:
@@ -386,11 +340,7 @@ class two_pcf(object):
         return xi, xi_weight, distance, coord, mask
 
     def optimizer(self, kernel):
-        """
-        Fit hyperparameter using two-point correlation function (two_pcf.py:393-464).
-
-        :param kernel: sklearn.gaussian_process kernel.
-        """
+        """Fit `kernel` to the measured correlation function and return it (two_pcf.py:393-464)."""
         size_x = np.max(self.X[:, 0]) - np.min(self.X[:, 0])
         if self.ndim == 2:
             size_y = np.max(self.X[:, 1]) - np.min(self.X[:, 1])
