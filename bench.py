@@ -264,7 +264,9 @@ def run_ours(args):
     peak_gops = dfma_tf * 1e3 / 2.0
     roofline = {"bound": "fp64_alu", "kernel": "pairbin_kernel<TwoD, unweighted>", "achieved": ach_gops,
                 "peak": peak_gops, "unit": "Gop/s (FP64 instructions x lanes)", "frac": ach_gops / peak_gops,
-                "traffic": None,
+                # dram__bytes_read + dram__bytes_write of one launch, from the ncu --set full capture summarised in
+                # profiles/r1_pairbin_v3_N1M.ncu.txt (N = 1e6; algorithmic input 24 MB + 1 MB chunk boxes)
+                "traffic": 25.28e6 if (n == 1_000_000 and world == 1) else None,
                 "note": "neither HBM- nor tensor-bound: 24 N bytes in, N^2/2 pair evaluations; peak = measured "
                         "DFMA issue rate (tgp_microbench_fp64), algorithmic 10 FP64 ops per unordered pair",
                 "dram_GBs_for_reference": 24.0 * n / (float(np.mean(kern_ms)) * 1e-3) / 1e9,

@@ -58,6 +58,36 @@ def _worker(rank, world, port, ret):
             full = po.pairbin(X[:, 0], X[:, 1], y - y.mean(), 1 / y_err ** 2, mn, mx, nb, "TwoD" if aniso else "Log")
             np.testing.assert_array_equal(t._last_npairs[0], full["npairs"])  # counts exact for any world size
 
+        # ---- distributed forward-difference gradient of the likelihood search (opt-in) ----
+        from treegp_b200 import log_likelihood as llmod
+        import treegp_b200.log_likelihood  # noqa: F401
+        import sys
+        mod = sys.modules["treegp_b200.log_likelihood"]
+        calls = []
+
+        def fake_loglike(self, kernel):   # smooth stand-in for the device evaluation
+            th = np.asarray(kernel.theta)
+            calls.append(1)
+            return -float(np.sum((th - np.array([0.3, -0.2])) ** 2 * np.array([1.0, 3.0])))
+
+        mod.log_likelihood.log_likelihood = fake_loglike
+        k0 = treegp.eval_kernel("1.0 * RBF(1.0)")
+        serial = mod.log_likelihood(np.zeros((4, 1)), np.zeros(4), np.zeros(4))
+        ks = serial.optimizer(k0)
+        n_serial = len(calls)
+        del calls[:]
+        mod.DISTRIBUTED_FD = True
+        par = mod.log_likelihood(np.zeros((4, 1)), np.zeros(4), np.zeros(4))
+        kp = par.optimizer(k0)
+        mod.DISTRIBUTED_FD = False
+        np.testing.assert_allclose(kp.theta, [0.3, -0.2], atol=1e-5)
+        np.testing.assert_allclose(kp.theta, ks.theta, atol=1e-6)
+        assert len(calls) < 0.75 * n_serial            # each rank evaluated only its share of the probes
+        th = torch.tensor(kp.theta)
+        both = [torch.zeros_like(th) for _ in range(world)]
+        tdist.all_gather(both, th)
+        assert torch.equal(both[0], both[1])           # identical iterates on every rank
+
         # ---- slabs and gather ----
         m = 1001
         lo, hi = dist.slab(m, rank, world)

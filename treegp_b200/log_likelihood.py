@@ -14,6 +14,14 @@ from scipy import optimize
 from . import backend
 from .kernels import lower_kernel
 
+# Multi-GPU: the (n_theta + 1) likelihood evaluations of one forward-difference gradient
+# are independent.  With DISTRIBUTED_FD = True (or env TREEGP_B200_DIST_FD=1) and an initialised process group,
+# every rank runs the same L-BFGS-B loop on replicated data and evaluates only its share of the probes; the
+# values are exchanged with one tiny all-reduce per gradient, so all ranks take identical steps.  Opt-in
+# because every rank of the group must then call optimizer() together.
+DISTRIBUTED_FD = False
+_FD_STEP = 1e-8  # scipy's default absolute forward-difference step for L-BFGS-B
+
 
 class log_likelihood(object):
     """Marginal log-likelihood of a GP for a kernel, and its maximiser over the kernel's theta.
@@ -52,6 +60,32 @@ class log_likelihood(object):
         self.n_evaluations += 1
         return float(out[0].item())  # -inf when the factorisation failed (info != 0)
 
+    @staticmethod
+    def _value_and_fd_gradient(fun, rank, world):
+        """f(theta) and its forward-difference gradient with the n_theta + 1 probes dealt round-robin to the
+        ranks (probe i on rank i % world) and combined with one all-reduce."""
+        import torch
+        import torch.distributed as tdist
+
+        on_gpu = tdist.get_backend() == "nccl"
+
+        def value_and_grad(theta):
+            theta = np.asarray(theta, dtype=float)
+            probes = [theta] + [theta + _FD_STEP * np.eye(len(theta))[i] for i in range(len(theta))]
+            vals = torch.zeros(len(probes), dtype=torch.float64)
+            for i, p in enumerate(probes):
+                if i % world == rank:
+                    v = fun(p)
+                    vals[i] = v if np.isfinite(v) else 1e300  # keep the all-reduce finite; mapped back below
+            if on_gpu:
+                vals = vals.cuda()
+            tdist.all_reduce(vals)
+            vals = vals.cpu().numpy()
+            vals = np.where(vals >= 1e300, np.inf, vals)
+            return float(vals[0]), (vals[1:] - vals[0]) / _FD_STEP
+
+        return value_and_grad
+
     def optimizer(self, kernel):
         """Maximise the likelihood over theta starting from `kernel.theta` (scipy L-BFGS-B, no bounds,
         forward-difference gradient) and return the fitted kernel; keeps `_kernel` and `_logL`."""
@@ -59,8 +93,16 @@ class log_likelihood(object):
         def minus_logl(theta):
             return -self.log_likelihood(kernel.clone_with_theta(theta))
 
-        # unbounded L-BFGS-B with scipy's forward-difference gradient, as log_likelihood.py:56-57
-        best = optimize.minimize(minus_logl, kernel.theta, method="L-BFGS-B")["x"]
+        import os
+        from . import dist
+
+        rank, world = dist.rank_world(None)
+        if world > 1 and (DISTRIBUTED_FD or os.environ.get("TREEGP_B200_DIST_FD") == "1"):
+            best = optimize.minimize(self._value_and_fd_gradient(minus_logl, rank, world), kernel.theta,
+                                     method="L-BFGS-B", jac=True)["x"]
+        else:
+            # unbounded L-BFGS-B with scipy's forward-difference gradient, as log_likelihood.py:56-57
+            best = optimize.minimize(minus_logl, kernel.theta, method="L-BFGS-B")["x"]
         kernel = kernel.clone_with_theta(best)
         self._kernel = copy.deepcopy(kernel)
         self._logL = self.log_likelihood(self._kernel)
