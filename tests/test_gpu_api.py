@@ -233,3 +233,18 @@ def test_gpinterp_around_a_meanify_mean_function(gpu_ready, tmp_path):
     np.testing.assert_allclose(yp, gp._mean + gp._build_average_meanify(far), atol=1e-6)
     with pytest.raises(NotImplementedError):
         treegp.GPInterpolation(kernel=kernel, optimizer="none").plot_fitted_kernel()
+
+
+def test_sample_grf_has_the_kernel_covariance(gpu_ready):
+    """Extension: y = L z from the library's own K build + Cholesky has covariance K."""
+    import treegp_b200 as treegp
+
+    kernel = treegp.eval_kernel(_aniso_kernel_string(1.5, "AnisotropicRBF", 2.0, 0.2, -0.1))
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-5, 5, size=(60, 2))
+    ys = np.array([treegp.sample_grf(kernel, X, seed=s)[0] for s in range(3000)])
+    K = kernel(X)
+    emp = ys.T @ ys / len(ys)
+    assert np.abs(emp - K).max() < 0.2 * K.max()      # 3000 draws: ~4 sigma of the sampling noise
+    y, y_err = treegp.sample_grf(kernel, X, noise=0.1, seed=1)
+    assert y.shape == (60,) and np.all(y_err == 0.1)

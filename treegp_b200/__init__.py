@@ -14,6 +14,7 @@ GPInterpolation = _gi.GPInterpolation
 log_likelihood, two_pcf = _ll.log_likelihood, _tp.two_pcf
 meanify = _mf.meanify
 comp_eb, comp_eb_treecorr = _ut.comp_eb, _ut.comp_eb_treecorr
+from .grf import sample_grf  # noqa: E402  (extension: device-side synthetic fields)
 
 __version__ = "0.1.0"
 

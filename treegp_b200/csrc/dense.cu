@@ -325,12 +325,29 @@ trsm_panel_kernel(const double* __restrict__ L, int nb, int64_t ldl, double* __r
       for (int j = 0; j < NB; ++j) x[j] = 0.0;
     }
   }
+  if (FULL && ((ldl & 1) == 0) && (((uintptr_t)L & 15) == 0)) {
+    // one batch of 32 independent 16-byte loads per thread: element pairs (i, 2c), (i, 2c+1) of the L tile
+    double2 lv[NB * NB / 2 / TRSM_ROWS];
+#pragma unroll
+    for (int q = 0; q < NB * NB / 2 / TRSM_ROWS; ++q) {
+      const int idx = tid + q * TRSM_ROWS;       // pair index: row i = idx / 32, column pair c = idx % 32
+      lv[q] = *reinterpret_cast<const double2*>(L + (int64_t)(idx >> 5) * ldl + 2 * (idx & 31));
+    }
+#pragma unroll
+    for (int q = 0; q < NB * NB / 2 / TRSM_ROWS; ++q) {
+      const int idx = tid + q * TRSM_ROWS;
+      const int i = idx >> 5, j = 2 * (idx & 31);
+      LsT[j * NB + i] = (j < i) ? lv[q].x : 0.0;
+      LsT[(j + 1) * NB + i] = (j + 1 < i) ? lv[q].y : 0.0;
+    }
+  } else {
 #pragma unroll 16
-  for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
-    const int i = idx / NB, j = idx % NB;  // coalesced along j
-    double v = 0.0;
-    if (i < nb && j < i) v = L[(int64_t)i * ldl + j];
-    LsT[j * NB + i] = v;
+    for (int idx = tid; idx < NB * NB; idx += TRSM_ROWS) {
+      const int i = idx / NB, j = idx % NB;  // coalesced along j
+      double v = 0.0;
+      if (i < nb && j < i) v = L[(int64_t)i * ldl + j];
+      LsT[j * NB + i] = v;
+    }
   }
   if (tid < NB) dinv[tid] = (tid < nb) ? 1.0 / L[(int64_t)tid * ldl + tid] : 1.0;
   if (!FULL) {
