@@ -357,6 +357,8 @@ def run_gp(args, treegp, backend, dist, rank, world, dev, barrier, max_over_rank
         t["solve_anisotropic_s"] = time.perf_counter() - t0
         t1 = time.perf_counter()
         ypred = gp.predict(Xs_local)
+        if world > 1:  # every rank ends up with all M predictions (all-gather of the slabs, 8 M bytes)
+            ypred = dist.gather_slabs(torch.as_tensor(ypred, device=dev), m).cpu().numpy()
         torch.cuda.synchronize()
         t["predict_s"] = time.perf_counter() - t1
         t["total_s"] = time.perf_counter() - t0
