@@ -120,6 +120,8 @@ def cpu_pairbin_sample(X, y, min_sep, max_sep, rows):
         os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     from oracle import pairbin_oracle as po
 
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        po.set_threads(os.cpu_count())  # the OpenMP runtime may already be initialised with 1 thread
     n = len(y)
     rows = min(rows, n)
     k = y - np.mean(y)

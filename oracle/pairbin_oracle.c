@@ -113,6 +113,14 @@ void oracle_pairbin_log(const double* x, const double* y, const double* k, const
   }
 }
 
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -36,6 +36,11 @@ def num_threads():
     return int(_lib().oracle_num_threads())
 
 
+def set_threads(n):
+    """Override OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1 to every rank)."""
+    _lib().oracle_set_threads(int(n))
+
+
 def _ptr(a, t=ctypes.c_double):
     return None if a is None else a.ctypes.data_as(ctypes.POINTER(t))
 
