@@ -189,7 +189,9 @@ int tgp_set_option(const char* name, int value);
 /* ---- measurement helpers --------------------------------------------------------------------- */
 
 /* FP64 micro-peaks used as roofline denominators.  kind 0: DFMA (FP64 FMA pipe), 1: DMMA
- * (mma.sync m8n8k4 f64).  Synchronous.  Writes achieved TFLOP/s to *tflops (host). */
+ * (mma.sync m8n8k4 f64).  Synchronous.  Writes achieved TFLOP/s to *tflops (host).
+ * kind 2 / 3: launch-latency probe -- microseconds per launch of a chain of `iters` dependent empty kernels,
+ * plain / with programmatic dependent launch (returned through *tflops). */
 int tgp_microbench_fp64(int kind, int iters, double* tflops /*host*/);
 
 #ifdef __cplusplus

@@ -161,6 +161,7 @@ gemm_nt_sub_kernel(double* __restrict__ C, int64_t M, int64_t Nc, int64_t ldc,
 }
 
 static int g_lookahead = 1;  // 0 disables the two-stream look-ahead Cholesky driver
+static int g_ob_large = 0;   // outer block of the look-ahead driver: 0 = automatic, else a multiple of 512 (option "potrf_ob")
 static int g_gemm_config = -1;  // -1: pick by shape; 0: 128x128; 1: 128x64 (tgp_set_option for experiments)
 
 template <int BN_, int WARPS_M, int WARPS_N, int MIN_CTAS>
@@ -198,6 +199,7 @@ static int gemm_nt_sub_launch(double* C, int64_t M, int64_t Nc, int64_t ldc, con
 extern "C" int tgp_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_config")) { g_gemm_config = value; return TGP_OK; }
   if (name && !strcmp(name, "potrf_lookahead")) { g_lookahead = value; return TGP_OK; }
+  if (name && !strcmp(name, "potrf_ob") && value >= 0 && value % 512 == 0) { g_ob_large = value; return TGP_OK; }
   tgp_set_error("tgp_set_option: unknown option");
   return TGP_ERR_INVALID;
 }
@@ -518,21 +520,23 @@ static LookaheadCtx& lookahead_ctx() {
 static int potrf_lookahead(double* A, int64_t n, int64_t ld, int32_t* info, cudaStream_t U, int64_t extra = 0) {
   LookaheadCtx& L = lookahead_ctx();
   cudaStream_t P = L.panel;
-  const int64_t nblk = tgp_cdiv(n, OB);
+  // K = 1024 trailing updates amortise the C read-modify-write better once the updates dominate (N >= 32k)
+  const int64_t OBL = (g_ob_large > 0) ? g_ob_large : (n >= 32768 ? 1024 : 512);
+  const int64_t nblk = tgp_cdiv(n, OBL);
   cudaEvent_t e_start = L.get(0);
   TGP_CUDA(cudaEventRecord(e_start, U));
   TGP_CUDA(cudaStreamWaitEvent(P, e_start, 0));
   // event slots: 1 + 2*b = panel(b) done, 2 + 2*b = U2(b) done
   for (int64_t b = 0; b < nblk; ++b) {
-    const int64_t k = b * OB;
-    const int64_t w = (n - k < OB) ? (n - k) : OB;
+    const int64_t k = b * OBL;
+    const int64_t w = (n - k < OBL) ? (n - k) : OBL;
     double* Akk = A + k * ld + k;
-    int rc = potrf_rec(Akk, w, ld, NB, info, k, P);
+    int rc = potrf_rec(Akk, w, ld, w > OB ? OB : NB, info, k, P);
     if (rc) return rc;
     const int64_t rest = n - k - w;
     if (rest + extra > 0) {
       double* Ark = A + (k + w) * ld + k;
-      rc = trsm_rows_halving(Akk, w, ld, Ark, rest + extra, ld, P);
+      rc = trsm_rows_rec(Akk, w, ld, Ark, rest + extra, ld, w > OB ? OB : NB, P);
       if (rc) return rc;
     }
     cudaEvent_t e_panel = L.get(1 + 2 * b);
@@ -542,7 +546,7 @@ static int potrf_lookahead(double* A, int64_t n, int64_t ld, int32_t* info, cuda
       break;
     }
     double* Ark = A + (k + w) * ld + k;
-    const int64_t w2 = (rest < OB) ? rest : OB;
+    const int64_t w2 = (rest < OBL) ? rest : OBL;
     TGP_CUDA(cudaStreamWaitEvent(U, e_panel, 0));
     if (b >= 1) TGP_CUDA(cudaStreamWaitEvent(P, L.get(2 + 2 * (b - 1)), 0));
     // U1(b): next panel's column block, all rows below the current panel (+ extra rows)

@@ -36,7 +36,55 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, 
   if (s == 123.456) out[0] = s;
 }
 
+__global__ void empty_kernel(double* out) { if (out == nullptr) return; }
+__global__ void empty_pdl_kernel(double* out) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (out == nullptr) return;
+}
+
+// kind 2 / 3: average microseconds per launch of a chain of `iters` dependent empty kernels on one stream,
+// plain (2) or with programmatic dependent launch (3).  Result returned through *tflops (as microseconds).
+static int launch_chain_probe(int kind, int iters, double* out_us) {
+  double* d = nullptr;
+  TGP_CUDA(cudaMalloc(&d, 8));
+  cudaStream_t st;
+  TGP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  cudaEvent_t e0, e1;
+  TGP_CUDA(cudaEventCreate(&e0));
+  TGP_CUDA(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    TGP_CUDA(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) {
+      if (kind == 2) {
+        empty_kernel<<<8, 256, 0, st>>>(d);
+      } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(8); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        TGP_CUDA(cudaLaunchKernelEx(&cfg, empty_pdl_kernel, d));
+      }
+    }
+    TGP_CUDA(cudaEventRecord(e1, st));
+    TGP_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    TGP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  TGP_LAUNCH_CHECK();
+  *out_us = (double)best * 1e3 / iters;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st); cudaFree(d);
+  return TGP_OK;
+}
+
 extern "C" int tgp_microbench_fp64(int kind, int iters, double* tflops) {
+  if (kind == 2 || kind == 3) {
+    TGP_CHECK_ARG(tflops && iters > 0, "iters");
+    return launch_chain_probe(kind, iters, tflops);
+  }
   TGP_CHECK_ARG(tflops && iters > 0 && (kind == 0 || kind == 1), "kind/iters");
   double* d = nullptr;
   TGP_CUDA(cudaMalloc(&d, 8));
