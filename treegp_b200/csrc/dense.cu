@@ -20,6 +20,7 @@
 #include <float.h>
 #include <math.h>
 #include <string.h>
+#include <atomic>
 #include "tgp_common.cuh"
 
 // ============================================================================================
@@ -162,6 +163,7 @@ gemm_nt_sub_kernel(double* __restrict__ C, int64_t M, int64_t Nc, int64_t ldc,
 
 static int g_lookahead = 1;  // 0 disables the two-stream look-ahead Cholesky driver
 static int g_ob_large = 0;   // outer block of the look-ahead driver: 0 = automatic, else a multiple of 512 (option "potrf_ob")
+static int g_fused_panel = 1;   // option "potrf_fused": 0 = the potf2 / trsm_panel / gemm chain per 64 columns
 static int g_gemm_config = -1;  // -1: pick by shape; 0: 128x128; 1: 128x64 (tgp_set_option for experiments)
 
 template <int BN_, int WARPS_M, int WARPS_N, int MIN_CTAS>
@@ -199,6 +201,7 @@ static int gemm_nt_sub_launch(double* C, int64_t M, int64_t Nc, int64_t ldc, con
 extern "C" int tgp_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_config")) { g_gemm_config = value; return TGP_OK; }
   if (name && !strcmp(name, "potrf_lookahead")) { g_lookahead = value; return TGP_OK; }
+  if (name && !strcmp(name, "potrf_fused")) { g_fused_panel = value; return TGP_OK; }
   if (name && !strcmp(name, "potrf_ob") && value >= 0 && value % 512 == 0) { g_ob_large = value; return TGP_OK; }
   tgp_set_error("tgp_set_option: unknown option");
   return TGP_ERR_INVALID;
@@ -216,17 +219,11 @@ constexpr int NB_PITCH = NB + 1;
 //   (ii)  one thread per row below solves its 16 entries against that sub-block,
 //   (iii) all threads apply the rank-16 update to the trailing lower triangle.
 constexpr int PF_B = 16;
-__global__ void __launch_bounds__(256)
-potf2_kernel(double* __restrict__ A, int n, int64_t ld, int32_t* __restrict__ info, int64_t global_off) {
-  __shared__ double S[NB * NB_PITCH];
-  __shared__ double rdiag[NB];   // 1 / L[j][j]
+// Factorise the NB x NB tile S (pitch NB_PITCH, identity-padded beyond n) in shared memory; all 256 threads
+// of the CTA call this.  rdiag receives 1 / L[j][j].  Ends with a CTA barrier.
+__device__ __forceinline__ void potf2_smem(double* __restrict__ S, double* __restrict__ rdiag, int n,
+                                           int32_t* __restrict__ info, int64_t global_off) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#pragma unroll 4
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int r = idx / NB, c = idx % NB;  // coalesced along c
-    S[r * NB_PITCH + c] = (r < n && c <= r) ? A[(int64_t)r * ld + c] : (r == c ? 1.0 : 0.0);
-  }
-  __syncthreads();
   for (int k0 = 0; k0 < NB; k0 += PF_B) {
     // (i) 16 x 16 diagonal sub-block, lanes 0..15 hold one row each
     if (warp == 0) {
@@ -243,12 +240,15 @@ potf2_kernel(double* __restrict__ A, int n, int64_t ld, int32_t* __restrict__ in
         // square-root call on the critical path; results agree with sqrt/divide to ~1 ulp)
         double rinv = rsqrt(d);
         rinv = fma(fma(-d * rinv, rinv, 1.0), 0.5 * rinv, rinv);    // one Newton step: full double accuracy
-        if ((lane & 15) == j) { a[j] = d * rinv; if (lane < 16) rdiag[k0 + j] = rinv; }
-        if ((lane & 15) > j) a[j] = a[j] * rinv;
+        const int l15 = lane & 15;
+        a[j] = (l15 == j) ? d * rinv : ((l15 > j) ? a[j] * rinv : a[j]);
+        if (lane == j) rdiag[k0 + j] = rinv;
 #pragma unroll
-        for (int c = j + 1; c < PF_B; ++c) {
-          const double lcj = __shfl_sync(0xffffffffu, a[j], c);       // l_cj from lane c
-          if ((lane & 15) >= c) a[c] = fma(-a[j], lcj, a[c]);
+        for (int c = 0; c < PF_B; ++c) {   // constant bounds + static predicate: keeps a[] in registers
+          if (c > j) {
+            const double lcj = __shfl_sync(0xffffffffu, a[j], c);     // l_cj from lane c
+            a[c] = (l15 >= c) ? fma(-a[j], lcj, a[c]) : a[c];
+          }
         }
       }
       if (lane < 16) {
@@ -288,11 +288,32 @@ potf2_kernel(double* __restrict__ A, int n, int64_t ld, int32_t* __restrict__ in
     }
     __syncthreads();
   }
+}
+
+// Load / store the lower triangle of an n x n (n <= NB) global block into the identity-padded tile S.
+__device__ __forceinline__ void potf2_load(double* __restrict__ S, const double* __restrict__ A, int n, int64_t ld) {
 #pragma unroll 4
-  for (int idx = tid; idx < NB * NB; idx += 256) {
+  for (int idx = threadIdx.x; idx < NB * NB; idx += 256) {
+    const int r = idx / NB, c = idx % NB;  // coalesced along c
+    S[r * NB_PITCH + c] = (r < n && c <= r) ? A[(int64_t)r * ld + c] : (r == c ? 1.0 : 0.0);
+  }
+}
+__device__ __forceinline__ void potf2_store(const double* __restrict__ S, double* __restrict__ A, int n, int64_t ld) {
+#pragma unroll 4
+  for (int idx = threadIdx.x; idx < NB * NB; idx += 256) {
     const int r = idx / NB, c = idx % NB;
     if (r < n && c <= r) A[(int64_t)r * ld + c] = S[r * NB_PITCH + c];
   }
+}
+
+__global__ void __launch_bounds__(256)
+potf2_kernel(double* __restrict__ A, int n, int64_t ld, int32_t* __restrict__ info, int64_t global_off) {
+  __shared__ double S[NB * NB_PITCH];
+  __shared__ double rdiag[NB];   // 1 / L[j][j]
+  potf2_load(S, A, n, ld);
+  __syncthreads();
+  potf2_smem(S, rdiag, n, info, global_off);
+  potf2_store(S, A, n, ld);
 }
 
 // ============================================================================================
@@ -414,6 +435,329 @@ static int trsm_panel_launch(const double* L, int nb, int64_t ldl, double* B, in
 }
 
 // ============================================================================================
+// Fused panel step.  A w-wide (w <= OB = 512) panel = the w x w diagonal block D at `Akk` plus `below` rows
+// stored under it.  ONE launch per 64-wide block column j factorises D's diagonal block (j,j) and solves every
+// row block under it, instead of the potf2 / trsm_panel / K=64 gemm chain (3 launches per block column inside D
+// plus ~15 for the rows below).  Inside the panel the off-diagonal blocks are LEFT-looking and the diagonal
+// blocks of D RIGHT-looking:
+//   CTA 0 (row block j)      : load block (j,j) -- already fully updated --, potf2 in shared memory, store,
+//                              publish a flag in global memory.
+//   CTA i > 0 (row block r)  : T = A[r, j] - A[r, 0:j] A[j, 0:j]^T  on the DMMA pipe (K = 64 j <= 448; this
+//                              overlaps with CTA 0's potf2), wait for the flag, X = T L_jj^-T by substitution
+//                              (4 threads per row), store X; if r is a row block of D also apply its own rank-64
+//                              update A[r, r] -= X X^T, so that block (j+1, j+1) is final when launch j+1 starts.
+// Waiting CTAs spin on the flag; CTA 0 is always dispatched first, so the wait cannot deadlock; the spin is
+// bounded anyway (info = -1 if it ever trips).
+// ============================================================================================
+constexpr int PL_THREADS = 256;
+constexpr int PL_P = NB + 2;                                 // pitch of the T / L tiles (even: 16-byte LDS)
+constexpr int PL_RING_D = STAGES * (NB + NB) * BK;            // operand ring, doubles
+constexpr int PL_TAIL_D = 2 * NB * PL_P + NB;                 // T tile + L tile + 1/diag (aliases the ring)
+constexpr int PL_SMEM = (PL_RING_D > PL_TAIL_D ? PL_RING_D : PL_TAIL_D) * 8;
+constexpr int PL_NFLAGS = 4096;
+__device__ unsigned g_panel_flags[PL_NFLAGS];
+
+#ifdef TGP_PANEL_TIMING   // phase timestamps of one launch (tools/panel_timing.py builds a private copy of the library)
+__device__ unsigned long long g_pl_times[32];   // [0,16): globaltimer ns, [16,32): clock64 of the same stamps
+__device__ __forceinline__ void pl_stamp(int i) {
+  if (threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_pl_times[i] = t;
+    g_pl_times[16 + i] = (unsigned long long)clock64();
+  }
+}
+#define PL_T(i) pl_stamp(i)
+extern "C" int tgp_debug_panel_times(unsigned long long* host32) {
+  return cudaMemcpyFromSymbol(host32, g_pl_times, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -2;
+}
+#else
+#define PL_T(i)
+#endif
+
+__global__ void __launch_bounds__(PL_THREADS, 2)
+panel_left_kernel(double* __restrict__ Akk, int64_t ld, int w, int64_t below, int j, int32_t* __restrict__ info,
+                  int64_t goff, unsigned slot, unsigned epoch) {
+  extern __shared__ __align__(16) double psm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ndiag = (w + NB - 1) / NB;
+  const int c0 = j * NB;
+  const int nbj = (w - c0 < NB) ? (w - c0) : NB;
+  unsigned* flag = &g_panel_flags[slot];
+
+  if (blockIdx.x == 0) {
+    double* S = psm;                       // NB x NB_PITCH
+    double* rdiag = psm + NB * NB_PITCH;
+    double* D = Akk + (int64_t)c0 * ld + c0;
+    PL_T(0);
+    potf2_load(S, D, nbj, ld);
+    __syncthreads();
+    PL_T(1);
+    potf2_smem(S, rdiag, nbj, info, goff + c0);
+    PL_T(2);
+    potf2_store(S, D, nbj, ld);
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(flag, epoch);
+    PL_T(3);
+    return;
+  }
+
+  const int rb = j + blockIdx.x;           // row block: < ndiag inside D, else among the rows below
+  const bool in_diag = rb < ndiag;
+  int64_t r0;
+  int nrows;
+  if (in_diag) {
+    r0 = (int64_t)rb * NB;
+    nrows = (w - rb * NB < NB) ? (w - rb * NB) : NB;
+  } else {
+    r0 = w + (int64_t)(rb - ndiag) * NB;
+    const int64_t left = w + below - r0;
+    nrows = left < NB ? (int)left : NB;
+  }
+  const int g = lane >> 2, t = lane & 3;
+  const int wm0 = (warp >> 2) * 32, wn0 = (warp & 3) * 16;   // warp tile 32 x 16 of the 64 x 64 block
+#ifdef TGP_PANEL_TIMING
+  const bool stamp = blockIdx.x == 1;
+#undef PL_T
+#define PL_T(i) if (stamp) pl_stamp(i)
+#endif
+  PL_T(8);
+
+  // ---- T = A[r, j] (prefetched) - A[r, 0:c0] A[j, 0:c0]^T ------------------------------------
+  double cv[4][2][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = wm0 + i * 8 + g;
+#pragma unroll
+    for (int jn = 0; jn < 2; ++jn) {
+      const int c = wn0 + jn * 8 + 2 * t;
+      const double* p = Akk + (r0 + r) * ld + c0 + c;
+      double v0 = 0.0, v1 = 0.0;
+      if (r < nrows) {
+        if (c + 1 < nbj) {
+          const double2 v = *reinterpret_cast<const double2*>(p);
+          v0 = v.x;
+          v1 = v.y;
+        } else if (c < nbj) {
+          v0 = p[0];
+        }
+      }
+      cv[i][jn][0] = v0;
+      cv[i][jn][1] = v1;
+    }
+  }
+  const int KT_ = c0 / BK;
+  if (KT_ > 0) {
+    double acc[4][2][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jn = 0; jn < 2; ++jn) acc[i][jn][0] = acc[i][jn][1] = 0.0;
+    constexpr int STAGE_D = (NB + NB) * BK;
+    auto issue = [&](int kt) {
+      if (kt < KT_) {
+        double* sa = psm + (kt % STAGES) * STAGE_D;
+        double* sb = sa + NB * BK;
+        load_operand_stage<NB>(sa, Akk, ld, r0, r0 + nrows, (int64_t)kt * BK, c0, tid);
+        load_operand_stage<NB>(sb, Akk, ld, c0, w, (int64_t)kt * BK, c0, tid);
+      }
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) issue(s);
+    const int swz = (g & 1) << 2;
+    for (int kt = 0; kt < KT_; ++kt) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      issue(kt + STAGES - 1);
+      const double* sa = psm + (kt % STAGES) * STAGE_D;
+      const double* sb = sa + NB * BK;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int pc = (h * 4 + t) ^ swz;
+        double2 af[4], bf[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          af[i] = *reinterpret_cast<const double2*>(sa + ((wm0 + i * 8 + g) * 8 + pc) * 2);
+#pragma unroll
+        for (int jn = 0; jn < 2; ++jn)
+          bf[jn] = *reinterpret_cast<const double2*>(sb + ((wn0 + jn * 8 + g) * 8 + pc) * 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int jn = 0; jn < 2; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], af[i].x, bf[jn].x);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int jn = 0; jn < 2; ++jn) dmma884(acc[i][jn][0], acc[i][jn][1], af[i].y, bf[jn].y);
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();   // the ring is dead from here on; its storage becomes the T / L tiles
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int jn = 0; jn < 2; ++jn) {
+        cv[i][jn][0] -= acc[i][jn][0];
+        cv[i][jn][1] -= acc[i][jn][1];
+      }
+  }
+  double* Ts = psm;                        // NB x PL_P
+  double* Ls = psm + NB * PL_P;            // NB x PL_P, Ls[i][c] = L_jj[i][c]
+  double* dinv = Ls + NB * PL_P;           // 1 / L_jj[c][c]
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int jn = 0; jn < 2; ++jn) {
+      const int r = wm0 + i * 8 + g, c = wn0 + jn * 8 + 2 * t;
+      *reinterpret_cast<double2*>(Ts + r * PL_P + c) = make_double2(cv[i][jn][0], cv[i][jn][1]);
+    }
+
+  PL_T(9);
+  // ---- wait for the diagonal block ---------------------------------------------------------
+  if (tid == 0) {
+    unsigned spins = 0;
+    while (*reinterpret_cast<volatile unsigned*>(flag) != epoch) {
+      __nanosleep(40);
+      if (++spins > (1u << 26)) {          // seconds: something is badly wrong, do not hang the GPU
+        atomicExch(info, -1);
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  PL_T(10);
+  const double* Lg = Akk + (int64_t)c0 * ld + c0;
+#pragma unroll 4
+  for (int idx = tid; idx < NB * NB; idx += PL_THREADS) {
+    const int i = idx / NB, c = idx % NB;
+    Ls[i * PL_P + c] = (i < nbj && c < i) ? __ldcg(Lg + (int64_t)i * ld + c) : 0.0;
+  }
+  if (tid < NB) dinv[tid] = (tid < nbj) ? 1.0 / __ldcg(Lg + (int64_t)tid * ld + tid) : 1.0;
+  __syncthreads();
+  PL_T(11);
+
+  // ---- X = T L^-T: 4 threads per row, thread q owns columns q, q+4, ..., two pivots per step -----------
+  {
+    const int row = warp * 8 + g, q = t;
+    const int lbase = lane & ~3;
+    double x[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) x[m] = Ts[row * PL_P + q + 4 * m];
+#pragma unroll
+    for (int mj = 0; mj < 16; ++mj) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int ja = 4 * mj + 2 * h, qa = 2 * h;          // pivots ja (thread qa) and ja + 1 (thread qa + 1)
+        double xa = x[mj] * dinv[ja];
+        xa = __shfl_sync(0xffffffffu, xa, lbase | qa);
+        double xb = fma(-xa, Ls[(ja + 1) * PL_P + ja], x[mj]) * dinv[ja + 1];
+        xb = __shfl_sync(0xffffffffu, xb, lbase | (qa + 1));
+        if (q == qa) x[mj] = xa;
+        if (q == qa + 1) x[mj] = xb;
+        {
+          const double2 l = *reinterpret_cast<const double2*>(Ls + (q + 4 * mj) * PL_P + ja);
+          if (q > qa + 1) x[mj] = fma(-xb, l.y, fma(-xa, l.x, x[mj]));
+        }
+#pragma unroll
+        for (int m = mj + 1; m < 16; ++m) {
+          const double2 l = *reinterpret_cast<const double2*>(Ls + (q + 4 * m) * PL_P + ja);
+          x[m] = fma(-xb, l.y, fma(-xa, l.x, x[m]));
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) Ts[row * PL_P + q + 4 * m] = x[m];
+  }
+  __syncthreads();
+  PL_T(12);
+
+  // ---- own rank-64 update of the diagonal block (r, r) of D (prefetch, DMMA, write back) -----------------
+  // warps 0..3 take block rows (warp, 7 - warp) of the 8 x 8 grid of 8x8 blocks: 9 lower blocks each.
+  if (in_diag && warp < 4) {
+    double* Dg = Akk + r0 * ld + r0;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int bi = pass ? 7 - warp : warp;
+      const int r = bi * 8 + g;
+      double d[8][2], acc[8][2];
+#pragma unroll
+      for (int bj = 0; bj < 8; ++bj) {
+        acc[bj][0] = acc[bj][1] = 0.0;
+        d[bj][0] = d[bj][1] = 0.0;
+        if (bj <= bi && r < nrows) {
+          const int c = bj * 8 + 2 * t;
+          const double* p = Dg + (int64_t)r * ld + c;
+          if (c + 1 <= r) {
+            const double2 v = *reinterpret_cast<const double2*>(p);
+            d[bj][0] = v.x;
+            d[bj][1] = v.y;
+          } else if (c <= r) {
+            d[bj][0] = p[0];
+          }
+        }
+      }
+#pragma unroll 4
+      for (int k4 = 0; k4 < NB / 4; ++k4) {
+        const double a = Ts[r * PL_P + k4 * 4 + t];
+#pragma unroll
+        for (int bj = 0; bj < 8; ++bj) {
+          if (bj <= bi) {
+            const double b = Ts[(bj * 8 + g) * PL_P + k4 * 4 + t];
+            dmma884(acc[bj][0], acc[bj][1], a, b);
+          }
+        }
+      }
+#pragma unroll
+      for (int bj = 0; bj < 8; ++bj) {
+        if (bj <= bi && r < nrows) {
+          const int c = bj * 8 + 2 * t;
+          double* p = Dg + (int64_t)r * ld + c;
+          if (c + 1 <= r) *reinterpret_cast<double2*>(p) = make_double2(d[bj][0] - acc[bj][0], d[bj][1] - acc[bj][1]);
+          else if (c <= r) p[0] = d[bj][0] - acc[bj][0];
+        }
+      }
+    }
+  }
+
+  PL_T(13);
+  // ---- store X -----------------------------------------------------------------------------
+#pragma unroll 4
+  for (int idx = tid; idx < NB * NB; idx += PL_THREADS) {
+    const int r = idx / NB, c = idx % NB;
+    if (r < nrows && c < nbj) Akk[(r0 + r) * ld + c0 + c] = Ts[r * PL_P + c];
+  }
+  PL_T(14);
+}
+
+
+// Factorise the w x w (w <= OB) diagonal block at Akk and solve the `below` rows under it (L21 = A21 L11^-T).
+static int panel_factor(double* Akk, int64_t w, int64_t ld, int64_t below, int32_t* info, int64_t goff,
+                        cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    TGP_CUDA(cudaFuncSetAttribute(panel_left_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM));
+    TGP_CUDA(cudaFuncSetAttribute(panel_left_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
+    attr_set = true;
+  }
+  static std::atomic<unsigned> counter{0};
+  const int ndiag = (int)tgp_cdiv(w, NB);
+  const int64_t nbelow = tgp_cdiv(below, NB);
+  for (int j = 0; j < ndiag; ++j) {
+    unsigned epoch = counter.fetch_add(1u) + 1u;
+    if (epoch == 0) epoch = counter.fetch_add(1u) + 1u;   // 0 is the value of a never-used flag
+    const unsigned grid = (unsigned)((ndiag - j) + nbelow);
+    panel_left_kernel<<<grid, PL_THREADS, PL_SMEM, st>>>(Akk, ld, (int)w, below, j, info, goff,
+                                                         epoch % PL_NFLAGS, epoch);
+    TGP_LAUNCH_CHECK();
+  }
+  return TGP_OK;
+}
+
+// ============================================================================================
 // Blocked drivers (two levels: OB-wide outer blocks whose updates run on DMMA with Kd = OB,
 // NB-wide inner blocks handled by the FP64-ALU kernels above).
 // ============================================================================================
@@ -460,27 +804,33 @@ static int trsm_rows_rec(const double* L, int64_t n, int64_t ldl, double* B, int
 // trailing updates, so that on exit they hold Y L^-T (= L^-1 y per row): the forward substitution at DMMA speed.
 static int potrf_rec(double* A, int64_t n, int64_t ld, int bs, int32_t* info, int64_t goff, cudaStream_t st,
                      int64_t extra = 0) {
+  if (g_fused_panel) bs = OB;   // the fused panel kernel handles everything below the OB level
   for (int64_t k = 0; k < n; k += bs) {
     const int64_t w = (n - k < bs) ? (n - k) : bs;
     double* Akk = A + k * ld + k;
-    int rc;
-    if (bs == NB) {
-      potf2_kernel<<<1, 256, 0, st>>>(Akk, (int)w, ld, info, goff + k);
-      TGP_LAUNCH_CHECK();
-      rc = TGP_OK;
-    } else {
-      rc = potrf_rec(Akk, w, ld, NB, info, goff + k, st);
-    }
-    if (rc) return rc;
     const int64_t rest = n - k - w;
-    if (rest + extra > 0) {
-      double* Ark = A + (k + w) * ld + k;  // rows below the diagonal block (+ the extra right-hand-side rows)
-      rc = trsm_rows_rec(Akk, w, ld, Ark, rest + extra, ld, NB, st);
+    int rc;
+    if (g_fused_panel) {
+      rc = panel_factor(Akk, w, ld, rest + extra, info, goff + k, st);
       if (rc) return rc;
-      if (rest > 0) {
-        rc = gemm_nt_sub_launch(A + (k + w) * ld + (k + w), rest + extra, rest, ld, Ark, ld, Ark, ld, w, 1, st);
+    } else {
+      if (bs == NB) {
+        potf2_kernel<<<1, 256, 0, st>>>(Akk, (int)w, ld, info, goff + k);
+        TGP_LAUNCH_CHECK();
+        rc = TGP_OK;
+      } else {
+        rc = potrf_rec(Akk, w, ld, NB, info, goff + k, st);
+      }
+      if (rc) return rc;
+      if (rest + extra > 0) {
+        rc = trsm_rows_rec(Akk, w, ld, A + (k + w) * ld + k, rest + extra, ld, NB, st);
         if (rc) return rc;
       }
+    }
+    if (rest > 0) {
+      double* Ark = A + (k + w) * ld + k;  // rows below the diagonal block (+ the extra right-hand-side rows)
+      rc = gemm_nt_sub_launch(A + (k + w) * ld + (k + w), rest + extra, rest, ld, Ark, ld, Ark, ld, w, 1, st);
+      if (rc) return rc;
     }
   }
   return TGP_OK;
@@ -531,13 +881,32 @@ static int potrf_lookahead(double* A, int64_t n, int64_t ld, int32_t* info, cuda
     const int64_t k = b * OBL;
     const int64_t w = (n - k < OBL) ? (n - k) : OBL;
     double* Akk = A + k * ld + k;
-    int rc = potrf_rec(Akk, w, ld, w > OB ? OB : NB, info, k, P);
-    if (rc) return rc;
+    int rc = TGP_OK;
     const int64_t rest = n - k - w;
-    if (rest + extra > 0) {
-      double* Ark = A + (k + w) * ld + k;
-      rc = trsm_rows_rec(Akk, w, ld, Ark, rest + extra, ld, w > OB ? OB : NB, P);
+    if (g_fused_panel) {
+      // OB-wide sub-panels, each solved against ALL rows below it; the columns of the later sub-panels of this
+      // outer block are brought up to date by one K = OB update in between
+      for (int64_t s = 0; s < w; s += OB) {
+        const int64_t ws = (w - s < OB) ? (w - s) : OB;
+        double* Ass = A + (k + s) * ld + (k + s);
+        const int64_t below_s = (n - (k + s) - ws) + extra;
+        rc = panel_factor(Ass, ws, ld, below_s, info, k + s, P);
+        if (rc) return rc;
+        const int64_t rem = w - s - ws;
+        if (rem > 0) {
+          double* Aop = A + (k + s + ws) * ld + (k + s);
+          rc = gemm_nt_sub_launch(A + (k + s + ws) * ld + (k + s + ws), below_s, rem, ld, Aop, ld, Aop, ld, ws, 1, P);
+          if (rc) return rc;
+        }
+      }
+    } else {
+      rc = potrf_rec(Akk, w, ld, w > OB ? OB : NB, info, k, P);
       if (rc) return rc;
+      if (rest + extra > 0) {
+        double* Ark = A + (k + w) * ld + k;
+        rc = trsm_rows_rec(Akk, w, ld, Ark, rest + extra, ld, w > OB ? OB : NB, P);
+        if (rc) return rc;
+      }
     }
     cudaEvent_t e_panel = L.get(1 + 2 * b);
     TGP_CUDA(cudaEventRecord(e_panel, P));
