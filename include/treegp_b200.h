@@ -119,6 +119,18 @@ int tgp_loglike(const double* X, const double* y, const double* yerr2, int64_t N
 int tgp_predict_mean(const double* Xs, int64_t M, const double* X, int64_t N,
                      const tgp_kernel* k /*host*/, const double* alpha, double* mean, void* stream);
 
+/* Same sum with compact-support truncation: groups of 128 training points whose bounding box lies farther
+ * than q_cut (f(q_cut) = 1e-40, tgp_profile_qcut) from the bounding box of a block of 256 test points are
+ * skipped, which changes mean[m] by at most 1e-40 * sum_n |amp alpha_n|.  Correct for any point order; fast
+ * when Xs and X (with alpha) are both stored along a space-filling curve (tgp_hilbert_keys).
+ * work: device scratch of tgp_predict_work_doubles(N) doubles (bounding boxes). */
+int tgp_predict_mean_trunc(const double* Xs, int64_t M, const double* X, int64_t N,
+                           const tgp_kernel* k /*host*/, const double* alpha, double* mean, double* work,
+                           void* stream);
+int64_t tgp_predict_work_doubles(int64_t N);
+/* q beyond which the correlation profile of `family` is below 1e-40. */
+double tgp_profile_qcut(int32_t family);
+
 /* var[m] = amp - || L^-1 K(X, Xs_m) ||^2, the diagonal of gp_interp.py:190-191.
  * work: 16-byte aligned device buffer of at least chunk*(N+1) doubles; `chunk` test points are
  * processed at a time (K(Xs_chunk, X) is materialised there, then solved in place on the DMMA pipe). */

@@ -293,3 +293,28 @@ def test_eb_decomposition_matches_all_pairs_formula():
     xie2, xib2, logr2 = treegp.comp_eb_treecorr(x, y, dx, dy, rmin=0.01, rmax=1.0, dlogr=0.2)
     assert xie.shape == xib.shape == logr.shape == xie2.shape == (bins,)
     np.testing.assert_allclose(xie + xib, xp, atol=1e-13)
+
+
+def test_truncation_thresholds_are_below_1e_minus_40():
+    """tgp_profile_qcut (host function of the library; csrc/predict.cu): f(q_cut) <= 1e-40 for every family, f decreasing
+    beyond -- the bound tgp_predict_mean_trunc's skip rule rests on.  Checked with mpmath (60 digits)."""
+    import mpmath as mp
+    from treegp_b200 import _cabi
+
+    lib = _cabi.load()
+    mp.mp.dps = 60
+
+    def vk(q):
+        z = 2 * mp.pi * mp.sqrt(q)
+        lim0 = mp.gamma(mp.mpf(5) / 6) / (2 * mp.pi ** (mp.mpf(5) / 6))
+        return mp.sqrt(q) ** (mp.mpf(5) / 6) * mp.besselk(mp.mpf(5) / 6, z) / lim0
+
+    fams = {_cabi.FAM_RBF: lambda q: mp.exp(-q / 2), _cabi.FAM_VONKARMAN: vk,
+            _cabi.FAM_MATERN12: lambda q: mp.exp(-mp.sqrt(q)),
+            _cabi.FAM_MATERN32: lambda q: (1 + mp.sqrt(3 * q)) * mp.exp(-mp.sqrt(3 * q)),
+            _cabi.FAM_MATERN52: lambda q: (1 + mp.sqrt(5 * q) + 5 * q / 3) * mp.exp(-mp.sqrt(5 * q))}
+    for fam, f in fams.items():
+        qc = mp.mpf(lib.tgp_profile_qcut(fam))
+        assert f(qc) <= mp.mpf("1e-40")
+        assert f(qc * 0.98) > mp.mpf("1e-41")     # not wastefully large
+        assert f(qc * 1.5) < f(qc) and f(qc * 4) < f(qc * 1.5)

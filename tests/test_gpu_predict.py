@@ -63,3 +63,49 @@ def test_predict_var_chunked(gpu_ready):
     K = go.kmat("rbf", X, amp=2.0, invLam=Mi) + np.diag(yerr2)
     ref = go.predictive_variance(K, go.kmat("rbf", Xs, X, amp=2.0, invLam=Mi), 2.0)
     np.testing.assert_allclose(var, ref, rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("ndim", [1, 2])
+@pytest.mark.parametrize("fam", ["rbf", "vonkarman", "matern32"])
+def test_predict_mean_truncated_support(gpu_ready, fam, ndim):
+    """tgp_predict_mean_trunc (Hilbert-sorted, far blocks skipped) against the full sum and the oracle on a field
+    much larger than the correlation length, where most blocks ARE skipped.  Bound: 1e-40 * sum|amp alpha|
+    plus summation order (asserted at 1e-13 of sum|amp alpha|)."""
+    from treegp_b200 import backend, eval_kernel
+    from treegp_b200.kernels import lower_kernel
+
+    rng = np.random.default_rng(17 + ndim)
+    n, m, half = 4000, 3000, 400.0
+    X = rng.uniform(-half, half, size=(n, ndim))
+    Xs = rng.uniform(-half, half, size=(m, ndim))
+    alpha = rng.normal(size=n) * 10.0 ** rng.uniform(-3, 3, size=n)
+    if ndim == 2:
+        Mi = np.array([[0.8, -0.1], [-0.1, 0.5]])
+        s = {"rbf": "3.0 * AnisotropicRBF(invLam=array([[0.8, -0.1], [-0.1, 0.5]]))",
+             "vonkarman": "3.0 * AnisotropicVonKarman(invLam=array([[0.8, -0.1], [-0.1, 0.5]]))",
+             "matern32": "3.0 * Matern(length_scale=1.5, nu=1.5)"}[fam]
+        okw = dict(length_scale=1.5) if fam == "matern32" else dict(invLam=Mi)
+    else:
+        s = {"rbf": "3.0 * RBF(length_scale=0.7)", "vonkarman": "3.0 * VonKarman(length_scale=0.7)",
+             "matern32": "3.0 * Matern(length_scale=0.7, nu=1.5)"}[fam]
+        okw = dict(length_scale=0.7)
+    desc = lower_kernel(eval_kernel(s), ndim)
+    a = backend.to_device(alpha)
+    full = backend.predict_mean(Xs, X, desc, a, truncate=False).cpu().numpy()
+    trunc = backend.predict_mean(Xs, X, desc, a, truncate=True).cpu().numpy()
+    ref = go.kmat(fam, Xs, X, amp=3.0, **okw) @ alpha
+    tol = 1e-13 * 3.0 * np.abs(alpha).sum()
+    np.testing.assert_allclose(trunc, full, rtol=0, atol=tol)
+    np.testing.assert_allclose(trunc, ref, rtol=0, atol=1e-11 * np.abs(alpha).sum())
+    # any point order is valid input for the C entry point (the boxes just get large): unsorted call
+    import ctypes, torch
+    from treegp_b200 import _cabi
+    lib = _cabi.load()
+    Xd, Xsd = backend.as_points(X), backend.as_points(Xs)
+    out = torch.empty(m, dtype=torch.float64, device=Xd.device)
+    work = torch.empty(int(lib.tgp_predict_work_doubles(n)), dtype=torch.float64, device=Xd.device)
+    _cabi.check(lib.tgp_predict_mean_trunc(ctypes.c_void_p(Xsd.data_ptr()), m, ctypes.c_void_p(Xd.data_ptr()), n,
+                                           ctypes.byref(desc), ctypes.c_void_p(a.data_ptr()),
+                                           ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(work.data_ptr()),
+                                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    np.testing.assert_allclose(out.cpu().numpy(), full, rtol=0, atol=tol)

@@ -43,6 +43,9 @@ SIGNATURES = {
     "tgp_logdet_chi2": [_vp, _i64, _i64, _vp, _vp, _vp, _vp],
     "tgp_loglike": [_vp, _vp, _vp, _i64, _kp, _vp, _i64, _vp, ctypes.c_int, _vp, _vp, _vp],
     "tgp_predict_mean": [_vp, _i64, _vp, _i64, _kp, _vp, _vp, _vp],
+    "tgp_predict_mean_trunc": [_vp, _i64, _vp, _i64, _kp, _vp, _vp, _vp, _vp],
+    "tgp_predict_work_doubles": [_i64],
+    "tgp_profile_qcut": [_i32],
     "tgp_predict_var": [_vp, _i64, _vp, _i64, _kp, _vp, _i64, _vp, _i64, _vp, _vp],
     "tgp_pairbin": [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _f64, _f64, _i32, _i32,
                     _vp, _vp, _vp, _vp, _vp, _vp],
@@ -52,7 +55,8 @@ SIGNATURES = {
     "tgp_set_option": [ctypes.c_char_p, ctypes.c_int],
     "tgp_microbench_fp64": [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)],
 }
-_RESTYPES = {"tgp_last_error": ctypes.c_char_p, "tgp_pairbin_work_doubles": ctypes.c_int64}
+_RESTYPES = {"tgp_last_error": ctypes.c_char_p, "tgp_pairbin_work_doubles": ctypes.c_int64,
+             "tgp_predict_work_doubles": ctypes.c_int64, "tgp_profile_qcut": ctypes.c_double}
 
 _lib = None
 

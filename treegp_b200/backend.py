@@ -127,13 +127,36 @@ def loglike(X, y, yerr2, kdesc, work=None, want_alpha=False):
     return out, info, alpha, work
 
 
-def predict_mean(Xs, X, kdesc, alpha, out=None):
+TRUNC_MIN_M, TRUNC_MIN_N = 16384, 2048   # below this the plain kernel is launch-bound anyway
+
+
+def predict_mean(Xs, X, kdesc, alpha, out=None, truncate=None):
+    """mean = K(Xs, X) . alpha without materialising K(Xs, X) (gp_interp.py:177,183).
+
+    truncate=True (default for large problems): both point sets are put in Hilbert-curve order (torch argsort /
+    gather: plumbing) and tgp_predict_mean_trunc skips blocks of pairs whose correlation is provably below
+    1e-40; the result differs from the full sum by at most 1e-40 * sum|amp alpha| (and by summation order)."""
     Xs, X = as_points(Xs), as_points(X)
-    M = Xs.shape[0]
+    M, N = Xs.shape[0], X.shape[0]
     if out is None:
         out = torch.empty(M, dtype=F64, device=X.device)
-    check(_cabi.load().tgp_predict_mean(_p(Xs), M, _p(X), X.shape[0], ctypes.byref(kdesc), _p(alpha), _p(out),
-                                        _stream()), "tgp_predict_mean")
+    lib = _cabi.load()
+    if truncate is None:
+        truncate = M >= TRUNC_MIN_M and N >= TRUNC_MIN_N
+    if not truncate:
+        check(lib.tgp_predict_mean(_p(Xs), M, _p(X), N, ctypes.byref(kdesc), _p(alpha), _p(out), _stream()),
+              "tgp_predict_mean")
+        return out
+    two_d = X.shape[1] == 2
+    zt, zs = torch.zeros(N, dtype=F64, device=X.device), torch.zeros(M, dtype=F64, device=X.device)
+    ot = hilbert_order(X[:, 0].contiguous(), X[:, 1].contiguous() if two_d else zt)
+    os_ = hilbert_order(Xs[:, 0].contiguous(), Xs[:, 1].contiguous() if two_d else zs)
+    Xt, at, Xss = X[ot].contiguous(), alpha[ot].contiguous(), Xs[os_].contiguous()
+    work = torch.empty(int(lib.tgp_predict_work_doubles(N)), dtype=F64, device=X.device)
+    tmp = torch.empty(M, dtype=F64, device=X.device)
+    check(lib.tgp_predict_mean_trunc(_p(Xss), M, _p(Xt), N, ctypes.byref(kdesc), _p(at), _p(tmp), _p(work),
+                                     _stream()), "tgp_predict_mean_trunc")
+    out[os_] = tmp
     return out
 
 
