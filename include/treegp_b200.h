@@ -191,6 +191,16 @@ int64_t tgp_pairbin_work_doubles(int64_t total_points, int32_t ncat);
 int tgp_hilbert_keys(const double* x, const double* y, int64_t n, double xmin, double ymin, double extent,
                      int32_t order, int64_t* keys, void* stream);
 
+/* HOST function (no device work): multiplicities of `b` bootstrap resamples of n points, bit-identical to
+ * b successive numpy `Generator(PCG64).integers(0, n-1, size=n)` calls -- the draws of resample_bootstrap
+ * (two_pcf.py:266,269-281; index n-1 is never drawn).
+ *  state : host uint64[6] = {state_hi, state_lo, inc_hi, inc_lo, has_uint32, uinteger} taken from numpy's
+ *          `bit_generator.state`; updated on return to the state numpy would be in after the same calls.
+ *  pos   : host int64[n] or NULL; draws of point i are counted at column pos[i] (e.g. its rank along the
+ *          Hilbert curve, so the multiplicities come out in storage order).
+ *  mult  : host uint8[b * n], overwritten.  More than 255 draws of one point -> TGP_ERR_UNSUPPORTED. */
+int tgp_bootstrap_multiplicities(uint64_t* state, int64_t n, int64_t b, const int64_t* pos, uint8_t* mult);
+
 /* Points per pair block: 32 (informational). */
 int tgp_pairbin_tile(void);
 

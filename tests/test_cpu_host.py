@@ -318,3 +318,53 @@ def test_truncation_thresholds_are_below_1e_minus_40():
         assert f(qc) <= mp.mpf("1e-40")
         assert f(qc * 0.98) > mp.mpf("1e-41")     # not wastefully large
         assert f(qc * 1.5) < f(qc) and f(qc * 4) < f(qc * 1.5)
+
+
+def _pcg_state(rng):
+    st = rng.bit_generator.state
+    v, inc = st["state"]["state"], st["state"]["inc"]
+    m64 = (1 << 64) - 1
+    return np.array([v >> 64, v & m64, inc >> 64, inc & m64, st["has_uint32"], st["uinteger"]], dtype=np.uint64)
+
+
+@pytest.mark.parametrize("seed", [610639139, 1, 2])
+@pytest.mark.parametrize("n,b", [(2, 3), (3, 5), (7, 11), (1000, 13), (40001, 7), (40000, 60), (1 << 22, 2)])
+def test_bootstrap_generator_is_numpy_bit_for_bit(seed, n, b):
+    """csrc/hostrng.cu against numpy itself: the multiplicities of b resamples equal the bincount of b successive
+    default_rng(seed).integers(0, n - 1, size=n) calls (two_pcf.py:266,275), also from an odd position in the
+    32-bit stream and through a storage permutation, and the generator state afterwards is numpy's."""
+    from treegp_b200 import _cabi
+
+    lib = _cabi.load()
+    r1, r2 = np.random.default_rng(seed), np.random.default_rng(seed)
+    r1.integers(0, 5, size=3)
+    r2.integers(0, 5, size=3)          # leaves half a 64-bit word buffered
+    idx = np.stack([r1.integers(0, n - 1, size=n) for _ in range(b)])
+    perm = np.random.default_rng(5).permutation(n)
+    ref = np.stack([np.bincount(perm[row], minlength=n) for row in idx])
+    st = _pcg_state(r2)
+    mult = np.empty((b, n), dtype=np.uint8)
+    assert lib.tgp_bootstrap_multiplicities(st.ctypes.data, n, b, perm.ctypes.data, mult.ctypes.data) == 0
+    assert np.array_equal(ref, mult)
+    assert np.array_equal(st, _pcg_state(r1))
+    assert not (ref[:, perm[n - 1]] != 0).any()      # the reference's quirk: index n-1 is never drawn
+
+
+def test_draw_multiplicities_continues_the_python_generator():
+    """two_pcf._draw_multiplicities hands the advanced PCG64 state back, so resample_bootstrap() afterwards
+    returns what it would have after the same number of numpy draws."""
+    import treegp_b200 as treegp
+
+    rng = np.random.default_rng(3)
+    n = 500
+    X, y, e = rng.uniform(size=(n, 2)), rng.normal(size=n), np.full(n, 0.1)
+    a = treegp.two_pcf(X, y, e, 0.0, 0.3, nbins=5, anisotropic=True)
+    b = treegp.two_pcf(X, y, e, 0.0, 0.3, nbins=5, anisotropic=True)
+    mult = a._draw_multiplicities(4, n, None).numpy()
+    for r in range(4):
+        u, v, yy, ee = b.resample_bootstrap()
+        assert np.array_equal(np.bincount(np.searchsorted(np.sort(y), yy), minlength=n)[np.argsort(np.argsort(y))],
+                              mult[r])
+    ua, _, ya, _ = a.resample_bootstrap()
+    ub, _, yb, _ = b.resample_bootstrap()
+    assert np.array_equal(ua, ub) and np.array_equal(ya, yb)

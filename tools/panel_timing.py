@@ -24,6 +24,9 @@ def run(n, reps=20):
     buf = (ctypes.c_ulonglong * 32)()
     assert lib.tgp_debug_panel_times(buf) == 0
     t = np.array(buf[:], dtype=np.int64)
+    pf = (ctypes.c_ulonglong * 4)()
+    assert lib.tgp_debug_potf2_cycles(pf) == 0
+    print("potf2 phase cycles (last diagonal block): (i) 16x16 pivots %d, (ii) rows below %d, (iii) trailing update %d" % (pf[0], pf[1], pf[2]))
     err = (torch.linalg.cholesky(K) - torch.tril(ws[:n])).abs().max().item()
     return t, err
 names = {0: "diag start", 1: "diag loaded", 2: "diag potf2 done", 3: "diag stored+flag",

@@ -219,11 +219,21 @@ constexpr int NB_PITCH = NB + 1;
 //   (ii)  one thread per row below solves its 16 entries against that sub-block,
 //   (iii) all threads apply the rank-16 update to the trailing lower triangle.
 constexpr int PF_B = 16;
+#ifdef TGP_PANEL_TIMING
+__device__ unsigned long long g_pf_cycles[4];   // accumulated cycles of potf2 phases (i), (ii), (iii)
+#define PF_T(k) if (threadIdx.x == 0) { const long long t_ = clock64(); g_pf_cycles[k] += t_ - pf_t0; pf_t0 = t_; }
+#else
+#define PF_T(k)
+#endif
 // Factorise the NB x NB tile S (pitch NB_PITCH, identity-padded beyond n) in shared memory; all 256 threads
 // of the CTA call this.  rdiag receives 1 / L[j][j].  Ends with a CTA barrier.
 __device__ __forceinline__ void potf2_smem(double* __restrict__ S, double* __restrict__ rdiag, int n,
                                            int32_t* __restrict__ info, int64_t global_off) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef TGP_PANEL_TIMING
+  long long pf_t0 = clock64();
+  if (tid == 0) g_pf_cycles[0] = g_pf_cycles[1] = g_pf_cycles[2] = 0;
+#endif
   for (int k0 = 0; k0 < NB; k0 += PF_B) {
     // (i) 16 x 16 diagonal sub-block, lanes 0..15 hold one row each
     if (warp == 0) {
@@ -238,8 +248,7 @@ __device__ __forceinline__ void potf2_smem(double* __restrict__ S, double* __res
           atomicCAS(info, 0, (int32_t)(global_off + k0 + j + 1));     // keep the first failure
         // one reciprocal square root per pivot: l_jj = d * rsqrt(d), l_ij = a_ij * rsqrt(d) (no FP64 divide or
         // square-root call on the critical path; results agree with sqrt/divide to ~1 ulp)
-        double rinv = rsqrt(d);
-        rinv = fma(fma(-d * rinv, rinv, 1.0), 0.5 * rinv, rinv);    // one Newton step: full double accuracy
+        const double rinv = rsqrt(d);                                 // CUDA's rsqrt is accurate to 1 ulp
         const int l15 = lane & 15;
         a[j] = (l15 == j) ? d * rinv : ((l15 > j) ? a[j] * rinv : a[j]);
         if (lane == j) rdiag[k0 + j] = rinv;
@@ -257,6 +266,7 @@ __device__ __forceinline__ void potf2_smem(double* __restrict__ S, double* __res
       }
     }
     __syncthreads();
+    PF_T(0);
     // (ii) rows below: x <- x * L11^-T (thread per row)
     const int below = NB - k0 - PF_B;
     if (tid < below) {
@@ -274,6 +284,7 @@ __device__ __forceinline__ void potf2_smem(double* __restrict__ S, double* __res
       for (int c = 0; c < PF_B; ++c) S[r * NB_PITCH + k0 + c] = x[c];
     }
     __syncthreads();
+    PF_T(1);
     // (iii) trailing update: S[i][c] -= sum_k S[i][k0+k] S[c][k0+k], k0+16 <= c <= i < 64; 16 x 16 thread grid
     if (below > 0) {
       const int ty = tid >> 4, tx = tid & 15;
@@ -287,6 +298,7 @@ __device__ __forceinline__ void potf2_smem(double* __restrict__ S, double* __res
       }
     }
     __syncthreads();
+    PF_T(2);
   }
 }
 
@@ -456,6 +468,13 @@ constexpr int PL_TAIL_D = 2 * NB * PL_P + NB;                 // T tile + L tile
 constexpr int PL_SMEM = (PL_RING_D > PL_TAIL_D ? PL_RING_D : PL_TAIL_D) * 8;
 constexpr int PL_NFLAGS = 4096;
 __device__ unsigned g_panel_flags[PL_NFLAGS];
+// every flag-synchronised launch takes a fresh (slot, epoch) pair: a stale value in a reused slot never matches
+static unsigned next_flag_epoch() {
+  static std::atomic<unsigned> counter{0};
+  unsigned e = counter.fetch_add(1u) + 1u;
+  if (e == 0) e = counter.fetch_add(1u) + 1u;   // 0 is the value of a never-used flag
+  return e;
+}
 
 #ifdef TGP_PANEL_TIMING   // phase timestamps of one launch (tools/panel_timing.py builds a private copy of the library)
 __device__ unsigned long long g_pl_times[32];   // [0,16): globaltimer ns, [16,32): clock64 of the same stamps
@@ -470,6 +489,9 @@ __device__ __forceinline__ void pl_stamp(int i) {
 #define PL_T(i) pl_stamp(i)
 extern "C" int tgp_debug_panel_times(unsigned long long* host32) {
   return cudaMemcpyFromSymbol(host32, g_pl_times, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -2;
+}
+extern "C" int tgp_debug_potf2_cycles(unsigned long long* host4) {
+  return cudaMemcpyFromSymbol(host4, g_pf_cycles, sizeof(unsigned long long) * 4) == cudaSuccess ? 0 : -2;
 }
 #else
 #define PL_T(i)
@@ -630,12 +652,19 @@ panel_left_kernel(double* __restrict__ Akk, int64_t ld, int w, int64_t below, in
   __syncthreads();
   PL_T(10);
   const double* Lg = Akk + (int64_t)c0 * ld + c0;
+  {
+    // Ls[i][c] = L[i][c] / L[c][c]: with the columns pre-scaled the substitution below runs on the UNSCALED
+    // unknowns u_c = x_c L_cc, so its critical path is one shuffle + one DFMA per pivot (no multiply, no
+    // shared-memory load); x = u / diag at the end.  Every thread only ever touches column c = tid % 64.
+    const int c = tid & (NB - 1);
+    const double dc = (c < nbj) ? 1.0 / __ldcg(Lg + (int64_t)c * ld + c) : 1.0;
 #pragma unroll 4
-  for (int idx = tid; idx < NB * NB; idx += PL_THREADS) {
-    const int i = idx / NB, c = idx % NB;
-    Ls[i * PL_P + c] = (i < nbj && c < i) ? __ldcg(Lg + (int64_t)i * ld + c) : 0.0;
+    for (int idx = tid; idx < NB * NB; idx += PL_THREADS) {
+      const int i = idx / NB;
+      Ls[i * PL_P + c] = (i < nbj && c < i) ? __ldcg(Lg + (int64_t)i * ld + c) * dc : 0.0;
+    }
+    if (tid < NB) dinv[tid] = dc;
   }
-  if (tid < NB) dinv[tid] = (tid < nbj) ? 1.0 / __ldcg(Lg + (int64_t)tid * ld + tid) : 1.0;
   __syncthreads();
   PL_T(11);
 
@@ -651,23 +680,23 @@ panel_left_kernel(double* __restrict__ Akk, int64_t ld, int w, int64_t below, in
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int ja = 4 * mj + 2 * h, qa = 2 * h;          // pivots ja (thread qa) and ja + 1 (thread qa + 1)
-        double xa = x[mj] * dinv[ja];
-        xa = __shfl_sync(0xffffffffu, xa, lbase | qa);
-        double xb = fma(-xa, Ls[(ja + 1) * PL_P + ja], x[mj]) * dinv[ja + 1];
-        xb = __shfl_sync(0xffffffffu, xb, lbase | (qa + 1));
-        if (q == qa) x[mj] = xa;
-        if (q == qa + 1) x[mj] = xb;
+        const double ua = __shfl_sync(0xffffffffu, x[mj], lbase | qa);
+        double ub = fma(-ua, Ls[(ja + 1) * PL_P + ja], x[mj]);
+        ub = __shfl_sync(0xffffffffu, ub, lbase | (qa + 1));
+        if (q == qa + 1) x[mj] = ub;
         {
           const double2 l = *reinterpret_cast<const double2*>(Ls + (q + 4 * mj) * PL_P + ja);
-          if (q > qa + 1) x[mj] = fma(-xb, l.y, fma(-xa, l.x, x[mj]));
+          if (q > qa + 1) x[mj] = fma(-ub, l.y, fma(-ua, l.x, x[mj]));
         }
 #pragma unroll
         for (int m = mj + 1; m < 16; ++m) {
           const double2 l = *reinterpret_cast<const double2*>(Ls + (q + 4 * m) * PL_P + ja);
-          x[m] = fma(-xb, l.y, fma(-xa, l.x, x[m]));
+          x[m] = fma(-ub, l.y, fma(-ua, l.x, x[m]));
         }
       }
     }
+#pragma unroll
+    for (int m = 0; m < 16; ++m) x[m] *= dinv[q + 4 * m];
 #pragma unroll
     for (int m = 0; m < 16; ++m) Ts[row * PL_P + q + 4 * m] = x[m];
   }
@@ -743,12 +772,10 @@ static int panel_factor(double* Akk, int64_t w, int64_t ld, int64_t below, int32
                                   cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
-  static std::atomic<unsigned> counter{0};
   const int ndiag = (int)tgp_cdiv(w, NB);
   const int64_t nbelow = tgp_cdiv(below, NB);
   for (int j = 0; j < ndiag; ++j) {
-    unsigned epoch = counter.fetch_add(1u) + 1u;
-    if (epoch == 0) epoch = counter.fetch_add(1u) + 1u;   // 0 is the value of a never-used flag
+    const unsigned epoch = next_flag_epoch();
     const unsigned grid = (unsigned)((ndiag - j) + nbelow);
     panel_left_kernel<<<grid, PL_THREADS, PL_SMEM, st>>>(Akk, ld, (int)w, below, j, info, goff,
                                                          epoch % PL_NFLAGS, epoch);
@@ -977,168 +1004,191 @@ extern "C" int tgp_gemm_nt_sub(double* C, int64_t M, int64_t Nc, int64_t ldc, co
 
 // ============================================================================================
 // Single right-hand-side solves  L w = b  (forward) and  L^T x = w  (backward).
-// Outer blocks of TV rows: a one-CTA kernel solves the TV x TV diagonal block, then one wide,
-// HBM-bound update kernel touches the rest of the panel exactly once (4 N^2 bytes per sweep).
+// One launch per TB = 128 unknowns.  CTA 0 stages the 128 x 128 diagonal block in shared memory and solves it
+// (32-wide chunks: warp-shuffle substitution on pre-scaled columns, one shuffle + one DFMA per unknown on the
+// critical path), then publishes the 128 new unknowns behind a flag.  Every other CTA owns a tile of the
+// 128-wide strip that the new unknowns update; it issues ALL its loads (32 per thread) before it looks at the
+// flag, so the HBM traffic of the strip -- the 4 N^2 bytes per sweep that bound this operation -- streams in
+// while the diagonal block is being solved.
 // ============================================================================================
-constexpr int TV = 256;
+constexpr int TB = 128;
+constexpr int TB_P = TB + 1;
+constexpr int TRSV_SMEM = (TB * TB_P + 2 * TB) * 8;
 
-// forward: solve L[k0:k0+w, k0:k0+w] x = b[k0:k0+w] in place; one CTA of TV threads, thread i <-> row i.
-// 32-column chunks: the owning warp solves its 32x32 triangle in registers with shuffles, publishes
-// x, then every later row applies the 32-column update.
-__global__ void __launch_bounds__(TV)
-trsv_diag_fwd_kernel(const double* __restrict__ L, int64_t ld, int64_t k0, int w, double* __restrict__ b) {
-  __shared__ double xs[TV];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const double* Lb = L + k0 * ld + k0;
-  double bi = (tid < w) ? b[k0 + tid] : 0.0;
-  for (int c0 = 0; c0 < w; c0 += 32) {
-    if (warp == (c0 >> 5)) {
-      const int i = c0 + lane;
-      const bool valid = i < w;
-      double lrow[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) lrow[j] = (valid && j < lane) ? Lb[(int64_t)i * ld + c0 + j] : 0.0;
-      const double dinv = valid ? 1.0 / Lb[(int64_t)i * ld + i] : 0.0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (lane == j) bi *= dinv;
-        const double xj = __shfl_sync(0xffffffffu, bi, j);
-        bi = fma(-lrow[j], xj, bi);  // lrow[j] == 0 for lanes <= j
-      }
-      xs[i] = bi;
+__device__ __forceinline__ void wait_flag(unsigned* flag, unsigned epoch) {
+  if (threadIdx.x == 0) {
+    unsigned spins = 0;
+    while (*reinterpret_cast<volatile unsigned*>(flag) != epoch) {
+      __nanosleep(40);
+      if (++spins > (1u << 26)) break;       // seconds: never hang the GPU
     }
-    __syncthreads();
-    if (tid >= c0 + 32 && tid < w) {
-      const double* row = Lb + (int64_t)tid * ld + c0;
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        s0 = fma(row[j], xs[c0 + j], s0);
-        s1 = fma(row[j + 1], xs[c0 + j + 1], s1);
-      }
-      bi -= (s0 + s1);
-    }
-    __syncthreads();
+    __threadfence();
   }
-  if (tid < w) b[k0 + tid] = bi;
-}
-
-// forward update: b[r] -= L[r, k0:k0+w] . x[k0:k0+w] for r >= k0+w.  Warp per row, 8 rows per CTA.
-__global__ void __launch_bounds__(256)
-trsv_update_fwd_kernel(const double* __restrict__ L, int64_t ld, int64_t N, int64_t k0, int w,
-                       double* __restrict__ b) {
-  __shared__ double xs[TV];
-  const int tid = threadIdx.x;
-  if (tid < TV) xs[tid] = (tid < w) ? b[k0 + tid] : 0.0;
   __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31;
-  const int64_t r = k0 + w + (int64_t)blockIdx.x * 8 + warp;
-  if (r >= N) return;
-  const double* row = L + r * ld + k0;
-  double s = 0.0;
-#pragma unroll
-  for (int j = lane; j < TV; j += 32) {
-    if (j < w) s = fma(row[j], xs[j], s);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) b[r] -= s;
 }
 
-// backward: solve L[k0:k0+w, k0:k0+w]^T x = b[k0:k0+w] in place; one CTA, thread j <-> unknown j.
-// Chunks of 32 from the bottom: lane j keeps column j of the 32x32 block (L[c0+i][c0+j], i > j) in
-// registers; once x_i is final every j < i subtracts L[i][j] x_i; earlier columns then apply the
-// 32-row update reading rows of L (coalesced across threads).
-__global__ void __launch_bounds__(TV)
-trsv_diag_bwd_kernel(const double* __restrict__ L, int64_t ld, int64_t k0, int w, double* __restrict__ b) {
-  __shared__ double xs[TV];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const double* Lb = L + k0 * ld + k0;
-  double bj = (tid < w) ? b[k0 + tid] : 0.0;
-  const int nchunk = (w + 31) >> 5;
-  for (int ch = nchunk - 1; ch >= 0; --ch) {
-    const int c0 = ch << 5;
-    if (warp == ch) {
-      const int j = c0 + lane;
-      const bool valid = j < w;
-      double lcol[32];
-#pragma unroll
-      for (int i = 0; i < 32; ++i) lcol[i] = (valid && i > lane && c0 + i < w) ? Lb[(int64_t)(c0 + i) * ld + j] : 0.0;
-      const double dinv = valid ? 1.0 / Lb[(int64_t)j * ld + j] : 0.0;
-#pragma unroll
-      for (int i = 31; i >= 0; --i) {
-        if (lane == i) bj *= dinv;
-        const double xi = __shfl_sync(0xffffffffu, bj, i);
-        bj = fma(-lcol[i], xi, bj);  // lcol[i] == 0 for lanes >= i
-      }
-      xs[j] = bj;
-    }
-    __syncthreads();
-    if (tid < c0) {
-      const int rows = (w - c0 < 32) ? (w - c0) : 32;
-      double s0 = 0.0, s1 = 0.0;
-      int i = 0;
-      for (; i + 2 <= rows; i += 2) {
-        s0 = fma(Lb[(int64_t)(c0 + i) * ld + tid], xs[c0 + i], s0);
-        s1 = fma(Lb[(int64_t)(c0 + i + 1) * ld + tid], xs[c0 + i + 1], s1);
-      }
-      if (i < rows) s0 = fma(Lb[(int64_t)(c0 + i) * ld + tid], xs[c0 + i], s0);
-      bj -= (s0 + s1);
-    }
-    __syncthreads();
-  }
-  if (tid < w) b[k0 + tid] = bj;
-}
-
-// backward update: b[j] -= sum_{r in [k0,k0+w)} L[r][j] x[r] for j < k0.  Thread per column j.
+template <bool FWD>
 __global__ void __launch_bounds__(256)
-trsv_update_bwd_kernel(const double* __restrict__ L, int64_t ld, int64_t k0, int w, double* __restrict__ b) {
-  __shared__ double xs[TV];
-  const int tid = threadIdx.x;
-  if (tid < TV) xs[tid] = (tid < w) ? b[k0 + tid] : 0.0;
-  __syncthreads();
-  const int64_t j = (int64_t)blockIdx.x * 256 + tid;
-  if (j >= k0) return;
-  const double* col = L + k0 * ld + j;
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int r = 0;
-  for (; r + 4 <= w; r += 4) {
-    s0 = fma(col[(int64_t)(r + 0) * ld], xs[r + 0], s0);
-    s1 = fma(col[(int64_t)(r + 1) * ld], xs[r + 1], s1);
-    s2 = fma(col[(int64_t)(r + 2) * ld], xs[r + 2], s2);
-    s3 = fma(col[(int64_t)(r + 3) * ld], xs[r + 3], s3);
+trsv_step_kernel(const double* __restrict__ L, int64_t ld, int64_t N, int64_t k0, int w, double* __restrict__ b,
+                 unsigned slot, unsigned epoch) {
+  extern __shared__ __align__(16) double vsm[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned* flag = &g_panel_flags[slot];
+
+  if (blockIdx.x == 0) {
+    // ---- diagonal block ---------------------------------------------------------------------
+    double* Ls = vsm;                 // TB x TB_P, identity padded
+    double* xs = vsm + TB * TB_P;     // right-hand side -> unknowns
+    double* dinv = xs + TB;
+    const double* Lb = L + k0 * ld + k0;
+#pragma unroll 8
+    for (int idx = tid; idx < TB * TB; idx += 256) {
+      const int r = idx / TB, c = idx % TB;
+      Ls[r * TB_P + c] = (r < w && c <= r) ? Lb[(int64_t)r * ld + c] : (r == c ? 1.0 : 0.0);
+    }
+    if (tid < TB) xs[tid] = (tid < w) ? b[k0 + tid] : 0.0;
+    __syncthreads();
+    if (tid < TB) dinv[tid] = 1.0 / Ls[tid * TB_P + tid];
+    __syncthreads();
+    for (int s = 0; s < TB / 32; ++s) {
+      const int ch = FWD ? s : TB / 32 - 1 - s;
+      const int c0 = ch * 32;
+      if (warp == 0) {
+        // unscaled unknowns u_i = x_i L_ii; coefficients pre-scaled by 1 / L_kk of the pivot they multiply
+        double coef[32];
+        double u = xs[c0 + lane];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          // forward : u_lane -= (L[lane][k] / L[k][k]) u_k, k < lane;  backward: u_lane -= (L[k][lane] / L[k][k]) u_k, k > lane
+          const double l = FWD ? Ls[(c0 + lane) * TB_P + c0 + k] : Ls[(c0 + k) * TB_P + c0 + lane];
+          const bool on = FWD ? (k < lane) : (k > lane);
+          coef[k] = on ? l * dinv[c0 + k] : 0.0;
+        }
+#pragma unroll
+        for (int s2 = 0; s2 < 32; ++s2) {
+          const int k = FWD ? s2 : 31 - s2;
+          const double uk = __shfl_sync(0xffffffffu, u, k);
+          u = fma(-coef[k], uk, u);
+        }
+        xs[c0 + lane] = u * dinv[c0 + lane];
+      }
+      __syncthreads();
+      // the other unknowns of the block absorb the 32 new values
+      const bool mine = FWD ? (tid >= c0 + 32 && tid < TB) : (tid < c0);
+      if (mine) {
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < 32; k += 2) {
+          const double l0 = FWD ? Ls[tid * TB_P + c0 + k] : Ls[(c0 + k) * TB_P + tid];
+          const double l1 = FWD ? Ls[tid * TB_P + c0 + k + 1] : Ls[(c0 + k + 1) * TB_P + tid];
+          a0 = fma(l0, xs[c0 + k], a0);
+          a1 = fma(l1, xs[c0 + k + 1], a1);
+        }
+        xs[tid] -= (a0 + a1);
+      }
+      __syncthreads();
+    }
+    if (tid < w) b[k0 + tid] = xs[tid];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicExch(flag, epoch);
+    return;
   }
-  for (; r < w; ++r) s0 = fma(col[(int64_t)r * ld], xs[r], s0);
-  b[j] -= (s0 + s1) + (s2 + s3);
+
+  double* xs = vsm;             // TB unknowns
+  double* red = vsm + TB;       // partial sums
+  const int64_t tile = blockIdx.x - 1;
+  if (FWD) {
+    // rows r0 .. r0+63 below the block; warp -> 8 rows, lane -> columns 4 lane .. 4 lane + 3 of the strip
+    const int64_t r0 = k0 + w + tile * 64 + warp * 8;
+    const bool vec = ((ld & 1) == 0) && ((((uintptr_t)L) & 15) == 0);
+    double2 v[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = r0 + i;
+      const double* p = L + r * ld + k0 + 4 * lane;
+      v[i][0] = v[i][1] = make_double2(0.0, 0.0);
+      if (r < N) {
+        if (vec && 4 * lane + 3 < w) {
+          v[i][0] = *reinterpret_cast<const double2*>(p);
+          v[i][1] = *reinterpret_cast<const double2*>(p + 2);
+        } else {
+          if (4 * lane < w) v[i][0].x = p[0];
+          if (4 * lane + 1 < w) v[i][0].y = p[1];
+          if (4 * lane + 2 < w) v[i][1].x = p[2];
+          if (4 * lane + 3 < w) v[i][1].y = p[3];
+        }
+      }
+    }
+    wait_flag(flag, epoch);
+    if (tid < TB) xs[tid] = (tid < w) ? __ldcg(b + k0 + tid) : 0.0;
+    __syncthreads();
+    const double x0 = xs[4 * lane], x1 = xs[4 * lane + 1], x2 = xs[4 * lane + 2], x3 = xs[4 * lane + 3];
+    double sums[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sums[i] = fma(v[i][0].x, x0, v[i][0].y * x1) + fma(v[i][1].x, x2, v[i][1].y * x3);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sums[i] += __shfl_xor_sync(0xffffffffu, sums[i], o);
+    if (lane < 8) {
+      double sv = sums[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) sv = (lane == i) ? sums[i] : sv;
+      const int64_t r = r0 + lane;
+      if (r < N) b[r] -= sv;
+    }
+  } else {
+    // columns j0 .. j0+63 left of the block; thread (c = tid % 64, rg = tid / 64) holds rows 32 rg .. 32 rg + 31
+    const int c = tid & 63, rg = tid >> 6;
+    const int64_t j = tile * 64 + c;
+    double v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int r = rg * 32 + i;
+      v[i] = (r < w && j < k0) ? L[(k0 + r) * ld + j] : 0.0;
+    }
+    wait_flag(flag, epoch);
+    if (tid < TB) xs[tid] = (tid < w) ? __ldcg(b + k0 + tid) : 0.0;
+    __syncthreads();
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      a0 = fma(v[i], xs[rg * 32 + i], a0);
+      a1 = fma(v[i + 1], xs[rg * 32 + i + 1], a1);
+    }
+    red[rg * 64 + c] = a0 + a1;
+    __syncthreads();
+    if (tid < 64 && j < k0) b[j] -= (red[c] + red[64 + c]) + (red[128 + c] + red[192 + c]);
+  }
+}
+
+template <bool FWD>
+static int trsv_sweep(const double* L, int64_t N, int64_t ld, double* b, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    TGP_CUDA(cudaFuncSetAttribute(trsv_step_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
+    attr_set = true;
+  }
+  const int64_t nblk = tgp_cdiv(N, TB);
+  for (int64_t s = 0; s < nblk; ++s) {
+    const int64_t kb = FWD ? s : nblk - 1 - s;
+    const int64_t k0 = kb * TB;
+    const int w = (int)((N - k0 < TB) ? (N - k0) : TB);
+    const int64_t other = FWD ? (N - k0 - w) : k0;          // rows below / columns left of the block
+    const unsigned epoch = next_flag_epoch();
+    trsv_step_kernel<FWD><<<(unsigned)(1 + tgp_cdiv(other, 64)), 256, TRSV_SMEM, st>>>(L, ld, N, k0, w, b,
+                                                                                     epoch % PL_NFLAGS, epoch);
+    TGP_LAUNCH_CHECK();
+  }
+  return TGP_OK;
 }
 
 static int trsv_forward(const double* L, int64_t N, int64_t ld, double* b, cudaStream_t st) {
-  for (int64_t k0 = 0; k0 < N; k0 += TV) {
-    const int w = (int)((N - k0 < TV) ? (N - k0) : TV);
-    trsv_diag_fwd_kernel<<<1, TV, 0, st>>>(L, ld, k0, w, b);
-    TGP_LAUNCH_CHECK();
-    const int64_t rest = N - k0 - w;
-    if (rest > 0) {
-      trsv_update_fwd_kernel<<<(unsigned)tgp_cdiv(rest, 8), 256, 0, st>>>(L, ld, N, k0, w, b);
-      TGP_LAUNCH_CHECK();
-    }
-  }
-  return TGP_OK;
+  return trsv_sweep<true>(L, N, ld, b, st);
 }
-
 static int trsv_backward(const double* L, int64_t N, int64_t ld, double* b, cudaStream_t st) {
-  const int64_t nblk = tgp_cdiv(N, TV);
-  for (int64_t kb = nblk - 1; kb >= 0; --kb) {
-    const int64_t k0 = kb * TV;
-    const int w = (int)((N - k0 < TV) ? (N - k0) : TV);
-    trsv_diag_bwd_kernel<<<1, TV, 0, st>>>(L, ld, k0, w, b);
-    TGP_LAUNCH_CHECK();
-    if (k0 > 0) {
-      trsv_update_bwd_kernel<<<(unsigned)tgp_cdiv(k0, 256), 256, 0, st>>>(L, ld, k0, w, b);
-      TGP_LAUNCH_CHECK();
-    }
-  }
-  return TGP_OK;
+  return trsv_sweep<false>(L, N, ld, b, st);
 }
 
 extern "C" int tgp_potrs_vec(const double* L, int64_t N, int64_t ld, double* b, void* stream) {

@@ -145,9 +145,10 @@ class GPInterpolation(object):
         n = Xd.shape[0]
         desc = lower_kernel(kernel, Xd.shape[1])
         e2 = backend.to_device(np.asarray(y_err, dtype=np.float64).reshape(-1) ** 2)
-        ws = backend.kmat_sym(Xd, desc, diag_add=e2, lower_only=True)
-        info = backend.potrf(ws, n)
-        alpha = backend.potrs_vec(ws, n, backend.to_device(np.asarray(y, dtype=np.float64).reshape(-1)).clone())
+        # one call: K (lower) -> L with y riding through the factorisation as an extra row (forward substitution
+        # for free), then the backward sweep (tgp_loglike, want_alpha)
+        yd = backend.to_device(np.asarray(y, dtype=np.float64).reshape(-1))
+        _, info, alpha, ws = backend.loglike(Xd, yd, e2, desc, want_alpha=True)
         bad = int(info.item())
         if bad != 0:
             # scipy.linalg.cholesky raises LinAlgError here (gp_interp.py:181)

@@ -276,6 +276,35 @@ class two_pcf(object):
         dxi = xi_bootstrap - np.mean(xi_bootstrap, axis=0)
         return 1.0 / (len(dxi) - 1.0) * np.dot(dxi.T, dxi)
 
+    def _draw_multiplicities(self, b, n, pos):
+        """(b, n) uint8 host tensor: how often each point (column = storage position pos[i]) occurs in each of
+        the next `b` resamples -- the same draws as `b` calls of resample_bootstrap(), i.e.
+        rng.integers(0, n - 1, size=n) (two_pcf.py:275).  The C generator (csrc/hostrng.cu) continues numpy's
+        PCG64 stream bit for bit and hands the advanced state back to self.rng."""
+        bg = self.rng.bit_generator
+        st = bg.state
+        if st.get("bit_generator") == "PCG64" and 2 <= n <= (1 << 22):
+            v, inc = st["state"]["state"], st["state"]["inc"]
+            m64 = (1 << 64) - 1
+            cs = np.array([v >> 64, v & m64, inc >> 64, inc & m64, st["has_uint32"], st["uinteger"]], dtype=np.uint64)
+            mult = torch.empty((b, n), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+            _cabi.check(_cabi.load().tgp_bootstrap_multiplicities(
+                cs.ctypes.data, n, b, None if pos is None else pos.ctypes.data, mult.data_ptr()),
+                "tgp_bootstrap_multiplicities")
+            st["state"]["state"] = (int(cs[0]) << 64) | int(cs[1])
+            st["has_uint32"], st["uinteger"] = int(cs[4]), int(cs[5])
+            bg.state = st
+            return mult
+        # other generators / very large catalogues: numpy draws, counted on the host
+        idx = self.rng.integers(0, n - 1, size=(b, n))       # same stream as b successive calls
+        if pos is not None:
+            idx = pos[idx]
+        rows = np.repeat(np.arange(b, dtype=np.int64), n)
+        cnt = np.bincount(rows * n + idx.reshape(-1), minlength=b * n).reshape(b, n)
+        if cnt.max() > 255:
+            raise _cabi.TgpError("a point was drawn more than 255 times in one resample")
+        return torch.as_tensor(cnt.astype(np.uint8))
+
     def _bootstrap_xi(self, n_bootstrap, batch_points=1 << 26):
         """xi of `n_bootstrap` resamples, shape (n_bootstrap, nb)."""
         n = len(self.y)
@@ -292,15 +321,15 @@ class two_pcf(object):
         done = 0
         if order is not None:
             x, yy, val, err_d = x[order], yy[order], val[order], err_d[order]
+        # storage position of every original point (identity without the Hilbert sort)
+        pos = None
+        if order is not None:
+            pos = np.empty(n, dtype=np.int64)
+            pos[order.cpu().numpy()] = np.arange(n, dtype=np.int64)
         while done < n_bootstrap:
             b = min(per_batch, n_bootstrap - done)
-            # same stream of draws as `b` successive resample_bootstrap() calls
-            idx = np.stack([self.rng.integers(0, n - 1, size=n) for _ in range(b)])
-            idx_d = torch.as_tensor(idx, device=dev)
-            mult = torch.zeros((b, n), dtype=torch.float64, device=dev)
-            mult.scatter_add_(1, idx_d, torch.ones_like(idx_d, dtype=torch.float64))
-            if order is not None:
-                mult = mult[:, order]
+            # multiplicities of `b` successive resample_bootstrap() draws, in storage order
+            mult = self._draw_multiplicities(b, n, pos).to(dev, non_blocking=True).to(torch.float64)
             ybar = (mult * val).sum(dim=1) / n                      # mean of the resampled values
             # weights: None in the reference iff the resampled errors sum to 0 (two_pcf.py:291-294)
             esum = (mult * err_d).sum(dim=1)
