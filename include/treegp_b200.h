@@ -204,8 +204,15 @@ int tgp_bootstrap_multiplicities(uint64_t* state, int64_t n, int64_t b, const in
 /* Points per pair block: 32 (informational). */
 int tgp_pairbin_tile(void);
 
+/* Diagnostics: how many pairs (32 x columns per processed block) of all tgp_pairbin launches since the last
+ * reset went through each path: host8[0] closed form (whole block in one bin and its mirror image), [1] one
+ * varying axis, [2] 2 x 2 window, all in range, [3] 2 x 2 window with per-pair range test, [4] generic
+ * (per-pair bin search + shared atomics; includes the diagonal blocks' sub-blocks).  Synchronous. */
+int tgp_pairbin_stats(unsigned long long* host8 /*host*/, int reset);
+
 /* Tuning knobs for experiments (not needed for normal use).  "gemm_config": -1 automatic,
- * 0 = 128x128 CTA tile (1 CTA/SM), 1 = 128x64 CTA tile (2 CTAs/SM). */
+ * 0 = 128x128 CTA tile (1 CTA/SM), 1 = 128x64 CTA tile (2 CTAs/SM); "potrf_fused": 0 = unfused panel chain;
+ * "pairbin_block_sums": 0 = every pair of every in-range block is evaluated individually (no block forms). */
 int tgp_set_option(const char* name, int value);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "tgp_hilbert_keys": [_vp, _vp, _i64, _f64, _f64, _f64, _i32, _vp, _vp],
     "tgp_bootstrap_multiplicities": [_vp, _i64, _i64, _vp, _vp],
     "tgp_pairbin_tile": [],
+    "tgp_pairbin_stats": [_vp, ctypes.c_int],
     "tgp_set_option": [ctypes.c_char_p, ctypes.c_int],
     "tgp_microbench_fp64": [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)],
 }

@@ -58,7 +58,13 @@ struct PBParams {
   int64_t my_items;       // number of work items of this rank
   int32_t run;            // column chunks per work item (multiple of 32)
   int32_t ncat, nbins, nb, warps, rank, nranks;
+  int32_t block_sums;     // 1: blocks whose pairs provably share a window bit use the block forms (default)
 };
+
+// Which path the pairs of all launches since the last reset took (in pairs): [0] closed form (block in one bin),
+// [1] one varying axis, [2] 2 x 2 window in range, [3] 2 x 2 window with per-pair range test, [4] generic
+// (atomics), [5] blocks skipped as out of range (pairs never looked at).  Diagnostics for bench.py / DESIGN.md.
+__device__ unsigned long long g_pb_stats[8];
 
 __device__ __forceinline__ int pb_bin_twod(double d, double hi, double inv_bin, int nbins,
                                            const double* __restrict__ ed) {
@@ -134,6 +140,7 @@ struct RegAcc {
   int fx0, fy0;              // forward window origin (bins); fx0 == -1: no open window.  Mirrored window
                              // origin: (nbins-2-fx0, nbins-2-fy0)
   long long ownerI;          // row block the per-lane thresholds were derived for
+  double rki, rwi;           // this lane's row-point factors k_i w_i and w_i, applied to the sums at flush time
   // Per-lane thresholds on the COLUMN point's coordinates, equivalent to the bin thresholds on the
   // displacement because rounding is monotone:  fl(xj - xi) >= t  <=>  xj >= Tx(xi, t).
   double Tx, Ty, RTx, RTy;   // forward: px = xj >= Tx ; mirrored: qx = xj <= RTx
@@ -190,11 +197,14 @@ __device__ __forceinline__ double pb_coord_le(double xi, double t, bool& ok) {
 // One pair into the window registers.  Written in PTX: four compares give the window bits of the
 // forward entry and the exact bits of the mirrored entry, each masked sum is one FMA with a 0.0 / 1.0
 // mask, each counter one predicated integer add (nvcc's code for the equivalent C++ needs ~2x the
-// instructions).
+// instructions; ptxas turns a predicated FP64 add into add + two selects, so the mask form is the shortest).
+// What is summed is the COLUMN point's value k_j w_j (and w_j): the row point's factor k_i w_i (w_i) is
+// constant for a lane while a window is open and is applied once, when the registers are flushed.
+// TOT = "add.f64 tot, tot, kj" for blocks that need the range test per pair; blocks that are entirely in
+// range add the chunk sum once instead.
 #define PB_ONE "0d3FF0000000000000"
 #define PB_ZERO "0d0000000000000000"
-#define PB_PAIR(A, XJ, YJ, KK)                                                                      \
-  asm volatile(                                                                                     \
+#define PB_PAIR_BODY(TOT)                                                                           \
       "{\n\t"                                                                                       \
       ".reg .pred px, py, qx, qy, pxy, cx, cy, mm;\n\t"                                             \
       ".reg .f64 m0, m1, m2;\n\t"                                                                   \
@@ -210,7 +220,7 @@ __device__ __forceinline__ double pb_coord_le(double xi, double t, bool& ok) {
       "selp.f64 m0, " PB_ONE ", " PB_ZERO ", px;\n\t"                                               \
       "selp.f64 m1, " PB_ONE ", " PB_ZERO ", py;\n\t"                                               \
       "selp.f64 m2, " PB_ONE ", " PB_ZERO ", pxy;\n\t"                                              \
-      "add.f64 %0, %0, %8;\n\t"                                                                     \
+      TOT                                                                                           \
       "fma.rn.f64 %1, %8, m0, %1;\n\t"                                                              \
       "fma.rn.f64 %2, %8, m1, %2;\n\t"                                                              \
       "fma.rn.f64 %3, %8, m2, %3;\n\t"                                                              \
@@ -218,13 +228,15 @@ __device__ __forceinline__ double pb_coord_le(double xi, double t, bool& ok) {
       "@py add.u32 %5, %5, 1;\n\t"                                                                  \
       "@pxy add.u32 %6, %6, 1;\n\t"                                                                 \
       "@mm add.u32 %7, %7, 1;\n\t"                                                                  \
-      "}\n"                                                                                         \
+      "}\n"
+#define PB_PAIR_OPS(A, XJ, YJ, KJ)                                                                  \
       : "+d"(A.tot), "+d"(A.fsx), "+d"(A.fsy), "+d"(A.fsxy), "+r"(A.fcx), "+r"(A.fcy), "+r"(A.fcxy), \
         "+r"(A.mmc)                                                                                 \
-      : "d"(KK), "d"(XJ), "d"(YJ), "d"(A.Tx), "d"(A.Ty), "d"(A.RTx), "d"(A.RTy))
+      : "d"(KJ), "d"(XJ), "d"(YJ), "d"(A.Tx), "d"(A.Ty), "d"(A.RTx), "d"(A.RTy)
+#define PB_PAIR(A, XJ, YJ, KJ) asm volatile(PB_PAIR_BODY("add.f64 %0, %0, %8;\n\t") PB_PAIR_OPS(A, XJ, YJ, KJ))
+#define PB_PAIR_NT(A, XJ, YJ, KJ) asm volatile(PB_PAIR_BODY("") PB_PAIR_OPS(A, XJ, YJ, KJ))
 
-#define PB_PAIR_W(A, XJ, YJ, KK, WW)                                                                \
-  asm volatile(                                                                                     \
+#define PB_PAIR_W_BODY(TOT)                                                                         \
       "{\n\t"                                                                                       \
       ".reg .pred px, py, qx, qy, pxy, cx, cy, mm;\n\t"                                             \
       ".reg .f64 m0, m1, m2;\n\t"                                                                   \
@@ -240,11 +252,10 @@ __device__ __forceinline__ double pb_coord_le(double xi, double t, bool& ok) {
       "selp.f64 m0, " PB_ONE ", " PB_ZERO ", px;\n\t"                                               \
       "selp.f64 m1, " PB_ONE ", " PB_ZERO ", py;\n\t"                                               \
       "selp.f64 m2, " PB_ONE ", " PB_ZERO ", pxy;\n\t"                                              \
-      "add.f64 %0, %0, %12;\n\t"                                                                    \
+      TOT                                                                                           \
       "fma.rn.f64 %1, %12, m0, %1;\n\t"                                                             \
       "fma.rn.f64 %2, %12, m1, %2;\n\t"                                                             \
       "fma.rn.f64 %3, %12, m2, %3;\n\t"                                                             \
-      "add.f64 %4, %4, %13;\n\t"                                                                    \
       "fma.rn.f64 %5, %13, m0, %5;\n\t"                                                             \
       "fma.rn.f64 %6, %13, m1, %6;\n\t"                                                             \
       "fma.rn.f64 %7, %13, m2, %7;\n\t"                                                             \
@@ -252,10 +263,49 @@ __device__ __forceinline__ double pb_coord_le(double xi, double t, bool& ok) {
       "@py add.u32 %9, %9, 1;\n\t"                                                                  \
       "@pxy add.u32 %10, %10, 1;\n\t"                                                               \
       "@mm add.u32 %11, %11, 1;\n\t"                                                                \
-      "}\n"                                                                                         \
+      "}\n"
+#define PB_PAIR_W_OPS(A, XJ, YJ, KJ, WJ)                                                            \
       : "+d"(A.tot), "+d"(A.fsx), "+d"(A.fsy), "+d"(A.fsxy), "+d"(A.wtot), "+d"(A.fwx), "+d"(A.fwy), \
         "+d"(A.fwxy), "+r"(A.fcx), "+r"(A.fcy), "+r"(A.fcxy), "+r"(A.mmc)                           \
-      : "d"(KK), "d"(WW), "d"(XJ), "d"(YJ), "d"(A.Tx), "d"(A.Ty), "d"(A.RTx), "d"(A.RTy))
+      : "d"(KJ), "d"(WJ), "d"(XJ), "d"(YJ), "d"(A.Tx), "d"(A.Ty), "d"(A.RTx), "d"(A.RTy)
+#define PB_PAIR_W(A, XJ, YJ, KJ, WJ)                                                                \
+  asm volatile(PB_PAIR_W_BODY("add.f64 %0, %0, %12;\n\tadd.f64 %4, %4, %13;\n\t") PB_PAIR_W_OPS(A, XJ, YJ, KJ, WJ))
+#define PB_PAIR_W_NT(A, XJ, YJ, KJ, WJ) asm volatile(PB_PAIR_W_BODY("") PB_PAIR_W_OPS(A, XJ, YJ, KJ, WJ))
+
+// One pair of a block whose displacements span two bins along ONE axis only (the other window bit is the same
+// for every pair of the block): CJ = the column point's coordinate on the varying axis, T / RT the lane's
+// forward / mirrored thresholds on it.  bs / bw / bc = block-local masked sums and count of the "upper bin" pairs.
+#define PB_PAIR_1D(BS, BC, MMC, CJ, KJ, T, RT)                                                      \
+  asm volatile(                                                                                     \
+      "{\n\t"                                                                                       \
+      ".reg .pred p, c;\n\t"                                                                        \
+      ".reg .f64 m;\n\t"                                                                            \
+      "setp.ge.f64 p, %3, %5;\n\t"                                                                  \
+      "setp.le.f64 c, %3, %6;\n\t"                                                                  \
+      "xor.pred c, c, p;\n\t"                                                                       \
+      "selp.f64 m, " PB_ONE ", " PB_ZERO ", p;\n\t"                                                 \
+      "fma.rn.f64 %0, %4, m, %0;\n\t"                                                               \
+      "@p add.u32 %1, %1, 1;\n\t"                                                                   \
+      "@!c add.u32 %2, %2, 1;\n\t"                                                                  \
+      "}\n"                                                                                         \
+      : "+d"(BS), "+r"(BC), "+r"(MMC)                                                               \
+      : "d"(CJ), "d"(KJ), "d"(T), "d"(RT))
+#define PB_PAIR_1D_W(BS, BW, BC, MMC, CJ, KJ, WJ, T, RT)                                            \
+  asm volatile(                                                                                     \
+      "{\n\t"                                                                                       \
+      ".reg .pred p, c;\n\t"                                                                        \
+      ".reg .f64 m;\n\t"                                                                            \
+      "setp.ge.f64 p, %4, %7;\n\t"                                                                  \
+      "setp.le.f64 c, %4, %8;\n\t"                                                                  \
+      "xor.pred c, c, p;\n\t"                                                                       \
+      "selp.f64 m, " PB_ONE ", " PB_ZERO ", p;\n\t"                                                 \
+      "fma.rn.f64 %0, %5, m, %0;\n\t"                                                               \
+      "fma.rn.f64 %1, %6, m, %1;\n\t"                                                               \
+      "@p add.u32 %2, %2, 1;\n\t"                                                                   \
+      "@!c add.u32 %3, %3, 1;\n\t"                                                                  \
+      "}\n"                                                                                         \
+      : "+d"(BS), "+d"(BW), "+r"(BC), "+r"(MMC)                                                     \
+      : "d"(CJ), "d"(KJ), "d"(WJ), "d"(T), "d"(RT))
 
 enum { PB_OUT = 0, PB_REG_FULL = 1, PB_REG_CHECK = 2, PB_GENERIC = 3 };
 
@@ -329,12 +379,13 @@ pairbin_kernel(PBParams P) {
     if (A.fx0 >= 0) {
       const unsigned n_in = warp_sum_u(A.nin);
       const unsigned fcx = warp_sum_u(A.fcx), fcy = warp_sum_u(A.fcy), fcxy = warp_sum_u(A.fcxy);
-      const double tot = warp_sum(A.tot);
-      const double fsx = warp_sum(A.fsx), fsy = warp_sum(A.fsy), fsxy = warp_sum(A.fsxy);
+      // the lane sums hold sum_j k_j w_j [mask]: times the row point's k_i w_i they are the pair sums
+      const double tot = warp_sum(A.tot * A.rki);
+      const double fsx = warp_sum(A.fsx * A.rki), fsy = warp_sum(A.fsy * A.rki), fsxy = warp_sum(A.fsxy * A.rki);
       double wtot = 0, fwx = 0, fwy = 0, fwxy = 0;
       if constexpr (WEIGHTED) {
-        wtot = warp_sum(A.wtot);
-        fwx = warp_sum(A.fwx); fwy = warp_sum(A.fwy); fwxy = warp_sum(A.fwxy);
+        wtot = warp_sum(A.wtot * A.rwi);
+        fwx = warp_sum(A.fwx * A.rwi); fwy = warp_sum(A.fwy * A.rwi); fwxy = warp_sum(A.fwxy * A.rwi);
       }
       if (lane == 0 && n_in) {
         // inclusion-exclusion per window bin (index = bx + 2*by)
@@ -450,6 +501,7 @@ pairbin_kernel(PBParams P) {
 
   const double M = P.hi, lo2 = P.lo2;
   const int R = P.run;
+  unsigned long long st_closed = 0, st_1d = 0, st_2d = 0, st_check = 0, st_generic = 0;   // per warp (uniform)
   int cur_cat = -1;
   int since_flush = 0;
   while (true) {
@@ -607,7 +659,7 @@ pairbin_kernel(PBParams P) {
             if (jn <= 0) bcls = PB_OUT;
           }
           if (bcls == PB_OUT) continue;
-          if (bcls == PB_GENERIC) { generic_block(j0, jn, 0, xi, yi, ki, wi, live); continue; }
+          if (bcls == PB_GENERIC) { generic_block(j0, jn, 0, xi, yi, ki, wi, live); st_generic += 32ull * jn; continue; }
           // ---- register path: make sure the open window covers this block ----
           const int x0 = bw[0] & 0xffff, x1 = x0 + (bw[0] >> 16), y0 = bw[1] & 0xffff, y1 = y0 + (bw[1] >> 16);
           const int rx0 = bw[2] & 0xffff, rx1 = rx0 + (bw[2] >> 16), ry0 = bw[3] & 0xffff, ry1 = ry0 + (bw[3] >> 16);
@@ -632,6 +684,8 @@ pairbin_kernel(PBParams P) {
             }
             A.fx0 = fx0; A.fy0 = fy0;
             A.ownerI = owner;
+            A.rki = ki;
+            A.rwi = wi;
             // bit = (bin >= b0 + 1): forward dx >= ed[b0+1]; mirrored -dx >= ed[r0+1] <=> dx <= -ed[r0+1] with
             // r0 = nbins-2-b0; turned into thresholds on the column coordinate for this lane's row point
             const double tx = (nbins > 1) ? ed[fx0 + 1] : INFINITY, ty = (nbins > 1) ? ed[fy0 + 1] : INFINITY;
@@ -649,21 +703,81 @@ pairbin_kernel(PBParams P) {
             }
           }
           if (bcls == PB_REG_FULL) {
+            // Every pair of the block is in range.  How many bins do its displacements span?  one_x: all dx in ONE
+            // forward bin, all -dx in ONE mirrored bin, and that bin is the mirror image (the usual case: bins are
+            // much wider than a 32-point chunk of a sorted catalogue).  Such an axis needs no per-pair decision:
+            // the window bit is the same for the whole block.
+            const bool whole = (nsub == 1) && P.block_sums;
+            const bool one_x = whole && x1 == x0 && rx1 == rx0 && rx0 == nbins - 1 - x0;
+            const bool one_y = whole && y1 == y0 && ry1 == ry0 && ry0 == nbins - 1 - y0;
+            const unsigned n_add = live ? (unsigned)jn : 0u;
+            if (one_x || one_y) {
+              // chunk sums of the column values (dead columns were staged as zero)
+              const double S = warp_sum(ck[lane]);
+              double Sw = 0.0;
+              if constexpr (WEIGHTED) Sw = warp_sum(cw[lane]);
+              const bool bx = (x0 - A.fx0) != 0, by = (y0 - A.fy0) != 0;   // window bits of the constant axes
+              double bs = 0.0, bw_ = 0.0;     // block-local sums / count of the pairs in the upper bin of the varying axis
+              unsigned bc = 0u;
+              if (one_x && one_y) {
+                // all 32 x jn pairs in one bin (and its mirror image): closed form, no per-pair work at all
+                bs = bx ? S : 0.0;
+                bw_ = bx ? Sw : 0.0;
+                bc = bx ? n_add : 0u;
+              } else if (one_y) {
+#pragma unroll 8
+                for (int jj = 0; jj < jn; ++jj) {
+                  const double cj = cxy[jj].x, kj = ck[jj];
+                  if constexpr (WEIGHTED) { const double wj = cw[jj]; PB_PAIR_1D_W(bs, bw_, bc, A.mmc, cj, kj, wj, A.Tx, A.RTx); }
+                  else PB_PAIR_1D(bs, bc, A.mmc, cj, kj, A.Tx, A.RTx);
+                }
+              } else {
+#pragma unroll 8
+                for (int jj = 0; jj < jn; ++jj) {
+                  const double cj = cxy[jj].y, kj = ck[jj];
+                  if constexpr (WEIGHTED) { const double wj = cw[jj]; PB_PAIR_1D_W(bs, bw_, bc, A.mmc, cj, kj, wj, A.Ty, A.RTy); }
+                  else PB_PAIR_1D(bs, bc, A.mmc, cj, kj, A.Ty, A.RTy);
+                }
+              }
+              // fold into the window registers.  v = the varying axis (x unless only x is constant):
+              // sum[v bit] += bs; sum[other bit] += S if that bit is set; sum[both] += bs if the other bit is set.
+              const bool vary_x = one_y;                 // (one_x && one_y): treated as "x varies" with a constant bit
+              const bool other = vary_x ? by : bx;
+              A.tot += S;
+              if constexpr (WEIGHTED) A.wtot += Sw;
+              A.nin += n_add;
+              if (vary_x) {
+                A.fsx += bs; A.fcx += bc;
+                if constexpr (WEIGHTED) A.fwx += bw_;
+                if (other) { A.fsy += S; A.fcy += n_add; if constexpr (WEIGHTED) A.fwy += Sw; }
+              } else {
+                A.fsy += bs; A.fcy += bc;
+                if constexpr (WEIGHTED) A.fwy += bw_;
+                if (other) { A.fsx += S; A.fcx += n_add; if constexpr (WEIGHTED) A.fwx += Sw; }
+              }
+              if (other) { A.fsxy += bs; A.fcxy += bc; if constexpr (WEIGHTED) A.fwxy += bw_; }
+              if (!live) A.mmc = 0u;
+              if (!(one_x && one_y)) fix_mirror(j0, jn, false, xi, yi, ki, wi);
+              if (one_x && one_y) st_closed += 32ull * jn; else st_1d += 32ull * jn;
+              continue;
+            }
 #pragma unroll 4
             for (int jj = j0; jj < j0 + jn; ++jj) {
               const double2 pj = cxy[jj];
-              const double kk = ki * ck[jj];
+              const double kj = ck[jj];
               if constexpr (WEIGHTED) {
-                const double ww = wi * cw[jj];
-                PB_PAIR_W(A, pj.x, pj.y, kk, ww);
+                const double wj = cw[jj];
+                PB_PAIR_W(A, pj.x, pj.y, kj, wj);
               } else {
-                PB_PAIR(A, pj.x, pj.y, kk);
+                PB_PAIR(A, pj.x, pj.y, kj);
               }
             }
-            A.nin += live ? (unsigned)jn : 0u;
+            A.nin += n_add;
             if (!live) A.mmc = 0u;  // dead lanes (NaN coordinates) compare false everywhere: not a mismatch
             fix_mirror(j0, jn, false, xi, yi, ki, wi);
+            st_2d += 32ull * jn;
           } else {
+            st_check += 32ull * jn;
 #pragma unroll 2
             for (int jj = j0; jj < j0 + jn; ++jj) {
               const double2 pj = cxy[jj];
@@ -671,12 +785,12 @@ pairbin_kernel(PBParams P) {
               const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
               const bool ok = r2 >= lo2 && fabs(dx) < M && fabs(dy) < M;  // false for dead lanes (NaN)
               if (ok) {
-                const double kk = ki * ck[jj];
+                const double kj = ck[jj];
                 if constexpr (WEIGHTED) {
-                  const double ww = wi * cw[jj];
-                  PB_PAIR_W(A, pj.x, pj.y, kk, ww);
+                  const double wj = cw[jj];
+                  PB_PAIR_W(A, pj.x, pj.y, kj, wj);
                 } else {
-                  PB_PAIR(A, pj.x, pj.y, kk);
+                  PB_PAIR(A, pj.x, pj.y, kj);
                 }
                 A.nin += 1u;
               }
@@ -690,6 +804,13 @@ pairbin_kernel(PBParams P) {
     flush_regs();
   }
   flush_hist(cur_cat);
+  if (lane == 0) {
+    if (st_closed) atomicAdd(&g_pb_stats[0], st_closed);
+    if (st_1d) atomicAdd(&g_pb_stats[1], st_1d);
+    if (st_2d) atomicAdd(&g_pb_stats[2], st_2d);
+    if (st_check) atomicAdd(&g_pb_stats[3], st_check);
+    if (st_generic) atomicAdd(&g_pb_stats[4], st_generic);
+  }
 }
 
 // Pre-pass: bounding box of every 32-point chunk of every catalogue (one warp per chunk).
@@ -720,6 +841,19 @@ extern "C" int64_t tgp_pairbin_work_doubles(int64_t total_points, int32_t ncat) 
   return 4 * (total_points / PB_CHUNK + (int64_t)ncat + 2);
 }
 
+static int g_pb_block_sums = 1;   // tgp_set_option("pairbin_block_sums", 0): every pair evaluated individually
+extern "C" int tgp_pairbin_set_block_sums(int on) { g_pb_block_sums = on ? 1 : 0; return TGP_OK; }
+
+extern "C" int tgp_pairbin_stats(unsigned long long* host8, int reset) {
+  TGP_CHECK_ARG(host8 != nullptr, "host8");
+  TGP_CUDA(cudaMemcpyFromSymbol(host8, g_pb_stats, sizeof(unsigned long long) * 8));
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    TGP_CUDA(cudaMemcpyToSymbol(g_pb_stats, z, sizeof(z)));
+  }
+  return TGP_OK;
+}
+
 // ring of work counters so that launches on different streams do not share one
 constexpr int PB_COUNTER_SLOTS = 64;
 __device__ unsigned long long g_pb_counters[PB_COUNTER_SLOTS];
@@ -741,6 +875,7 @@ extern "C" int tgp_pairbin(const double* px, const double* py, const double* pk,
   P.px = px; P.py = py; P.pk = pk; P.pw = pw; P.cat_off = cat_off; P.edges = edges;
   P.npairs = npairs; P.sumw = sumw; P.sumwkk = sumwkk; P.sumwr = sumwr;
   P.ncat = ncat; P.nbins = nbins; P.rank = tile_rank; P.nranks = tile_nranks;
+  P.block_sums = g_pb_block_sums;
   const bool twod = bin_type == TGP_BIN_TWOD;
   TGP_CHECK_ARG(!twod || nbins <= 4096, "nbins too large");
   P.nb = twod ? nbins * nbins : nbins;
