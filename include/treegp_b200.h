@@ -206,8 +206,8 @@ int tgp_pairbin_tile(void);
 
 /* Diagnostics: how many pairs (32 x columns per processed block) of all tgp_pairbin launches since the last
  * reset went through each path: host8[0] closed form (whole block in one bin and its mirror image), [1] one
- * varying axis, [2] 2 x 2 window, all in range, [3] 2 x 2 window with per-pair range test, [4] generic
- * (per-pair bin search + shared atomics; includes the diagonal blocks' sub-blocks).  Synchronous. */
+ * varying axis (one compare pair per pair of points), [2] pair by pair in a 2 x 2 bin window or through the
+ * generic path (the diagonal blocks are not tallied).  Synchronous. */
 int tgp_pairbin_stats(unsigned long long* host8 /*host*/, int reset);
 
 /* Tuning knobs for experiments (not needed for normal use).  "gemm_config": -1 automatic,

@@ -217,7 +217,7 @@ def pairbin_stats(reset=True):
     """Pairs per kernel path since the last reset (see tgp_pairbin_stats); synchronises the device."""
     buf = (ctypes.c_ulonglong * 8)()
     check(_cabi.load().tgp_pairbin_stats(buf, int(bool(reset))), "tgp_pairbin_stats")
-    keys = ("closed_form", "one_axis", "window_2x2", "window_2x2_range_checked", "generic")
+    keys = ("closed_form", "one_axis", "pairwise")
     return {k: int(buf[i]) for i, k in enumerate(keys)}
 
 

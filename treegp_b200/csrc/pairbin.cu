@@ -50,7 +50,7 @@ struct PBParams {
   int64_t* npairs;
   double *sumw, *sumwkk, *sumwr;
   unsigned long long* counter;  // dynamic work counter (zeroed before the launch)
-  const double* boxes;          // optional precomputed chunk bounding boxes (4 doubles per slot) or NULL
+  const double* boxes;          // optional precomputed chunk boxes + sums (8 doubles per slot) or NULL
   double lo2;       // pairs need r2 >= lo2 (= max(min_sep^2, DBL_TRUE_MIN) for TwoD; min_sep^2 for Log)
   double hi;        // TwoD: max_sep (|dx|,|dy| < hi);  Log: max_sep^2 (r2 < hi)
   double inv_bin;   // TwoD: nbins / (2 max_sep)
@@ -62,8 +62,8 @@ struct PBParams {
 };
 
 // Which path the pairs of all launches since the last reset took (in pairs): [0] closed form (block in one bin),
-// [1] one varying axis, [2] 2 x 2 window in range, [3] 2 x 2 window with per-pair range test, [4] generic
-// (atomics), [5] blocks skipped as out of range (pairs never looked at).  Diagnostics for bench.py / DESIGN.md.
+// [1] one varying axis, [2] pair by pair (2 x 2 window with or without the per-pair range test, generic
+// sub-blocks).  Diagnostics for bench.py / DESIGN.md.
 __device__ unsigned long long g_pb_stats[8];
 
 __device__ __forceinline__ int pb_bin_twod(double d, double hi, double inv_bin, int nbins,
@@ -499,9 +499,26 @@ pairbin_kernel(PBParams P) {
     __syncwarp();
   };
 
+  // per-lane open bin of the blocks booked whole at classification time (forward bin cf_bin and its mirror image)
+  int cf_bin = -1;
+  unsigned cf_cnt = 0u;
+  double cf_s = 0.0, cf_w = 0.0;
+  auto cf_spill = [&]() {
+    if (cf_bin >= 0 && cf_cnt) {
+      const int om = nb - 1 - cf_bin;      // (nbins-1-y) * nbins + (nbins-1-x)
+      atomicAdd(my_c + cf_bin, cf_cnt);
+      atomicAdd(my_c + om, cf_cnt);
+      atomicAdd(my_s + cf_bin, cf_s);
+      atomicAdd(my_s + om, cf_s);
+      if constexpr (WEIGHTED) { atomicAdd(my_w + cf_bin, cf_w); atomicAdd(my_w + om, cf_w); }
+    }
+    cf_cnt = 0u;
+    cf_s = 0.0;
+    cf_w = 0.0;
+  };
   const double M = P.hi, lo2 = P.lo2;
   const int R = P.run;
-  unsigned long long st_closed = 0, st_1d = 0, st_2d = 0, st_check = 0, st_generic = 0;   // per warp (uniform)
+  unsigned st_closed = 0, st_1d = 0, st_pw = 0;   // column counts (x 32 rows = pairs): closed form / one axis / pairwise
   int cur_cat = -1;
   int since_flush = 0;
   while (true) {
@@ -557,6 +574,11 @@ pairbin_kernel(PBParams P) {
     const double iminx = warp_min(live ? xi : INFINITY), imaxx = warp_max(live ? xi : -INFINITY);
     const double iminy = warp_min(live ? yi : INFINITY), imaxy = warp_max(live ? yi : -INFINITY);
     const long long owner = (long long)(off + ib * PB_CHUNK);
+    // row-block aggregates for the blocks that are booked whole
+    const double rowK = warp_sum(ki);
+    double rowW = 0.0;
+    if constexpr (WEIGHTED) rowW = warp_sum(wi);
+    const int nlive = __popc(__ballot_sync(0xffffffffu, live));
 
     for (int64_t sc = c_lo; sc < c_hi; sc += 32) {
       // ---- lane l classifies column chunk sc + l ----
@@ -568,7 +590,7 @@ pairbin_kernel(PBParams P) {
         const int cnt = (int)((n - j0g < PB_CHUNK) ? (n - j0g) : PB_CHUNK);
         double cminx = INFINITY, cmaxx = -INFINITY, cminy = INFINITY, cmaxy = -INFINITY;
         if (P.boxes) {
-          const double4 bb = *reinterpret_cast<const double4*>(P.boxes + 4 * ((off + j0g) / PB_CHUNK + cat));
+          const double4 bb = *reinterpret_cast<const double4*>(P.boxes + 8 * ((off + j0g) / PB_CHUNK + cat));
           cminx = bb.x; cmaxx = bb.y; cminy = bb.z; cmaxy = bb.w;
         } else {
           const double* xs = P.px + off + j0g;
@@ -598,6 +620,24 @@ pairbin_kernel(PBParams P) {
           if (mychunk == ib) cls = PB_GENERIC;
         }
         if (!(iminx <= imaxx)) cls = PB_OUT;  // no live row in this warp
+        if (BT == TGP_BIN_TWOD && cls == PB_REG_FULL && P.boxes && P.block_sums) {
+          // Whole block in ONE forward bin and in its mirror image: the classifying lane books the block itself
+          // from the chunk sums of the pre-pass (count = rows x columns, sum = (sum of the rows' k w) x (sum of the
+          // columns' k w)); the points of the chunk are never loaded.  Consecutive chunks of a lane mostly hit
+          // the same bin: the lane keeps one open bin in registers and spills to the warp histogram on a change.
+          const int x0 = win[0] & 0xffff, y0 = win[1] & 0xffff, rx0 = win[2] & 0xffff, ry0 = win[3] & 0xffff;
+          if ((win[0] >> 16) == 0 && (win[1] >> 16) == 0 && (win[2] >> 16) == 0 && (win[3] >> 16) == 0 &&
+              rx0 == nbins - 1 - x0 && ry0 == nbins - 1 - y0) {
+            const double2 sums = *reinterpret_cast<const double2*>(P.boxes + 8 * ((off + j0g) / PB_CHUNK + cat) + 4);
+            const int o = y0 * nbins + x0;
+            if (o != cf_bin) { cf_spill(); cf_bin = o; }
+            cf_cnt += (unsigned)(nlive * cnt);
+            cf_s = fma(rowK, sums.x, cf_s);
+            if constexpr (WEIGHTED) cf_w = fma(rowW, sums.y, cf_w);
+            st_closed += (unsigned)cnt;
+            cls = PB_OUT;
+          }
+        }
       }
       const unsigned todo = __ballot_sync(0xffffffffu, cls != PB_OUT);
       // ---- process the non-OUT chunks; the next chunk's points are prefetched into registers ----
@@ -659,7 +699,7 @@ pairbin_kernel(PBParams P) {
             if (jn <= 0) bcls = PB_OUT;
           }
           if (bcls == PB_OUT) continue;
-          if (bcls == PB_GENERIC) { generic_block(j0, jn, 0, xi, yi, ki, wi, live); st_generic += 32ull * jn; continue; }
+          if (bcls == PB_GENERIC) { generic_block(j0, jn, 0, xi, yi, ki, wi, live); st_pw += (unsigned)jn; continue; }
           // ---- register path: make sure the open window covers this block ----
           const int x0 = bw[0] & 0xffff, x1 = x0 + (bw[0] >> 16), y0 = bw[1] & 0xffff, y1 = y0 + (bw[1] >> 16);
           const int rx0 = bw[2] & 0xffff, rx1 = rx0 + (bw[2] >> 16), ry0 = bw[3] & 0xffff, ry1 = ry0 + (bw[3] >> 16);
@@ -758,7 +798,7 @@ pairbin_kernel(PBParams P) {
               if (other) { A.fsxy += bs; A.fcxy += bc; if constexpr (WEIGHTED) A.fwxy += bw_; }
               if (!live) A.mmc = 0u;
               if (!(one_x && one_y)) fix_mirror(j0, jn, false, xi, yi, ki, wi);
-              if (one_x && one_y) st_closed += 32ull * jn; else st_1d += 32ull * jn;
+              if (one_x && one_y) { if (lane == 0) st_closed += (unsigned)jn; } else st_1d += (unsigned)jn;
               continue;
             }
 #pragma unroll 4
@@ -775,9 +815,9 @@ pairbin_kernel(PBParams P) {
             A.nin += n_add;
             if (!live) A.mmc = 0u;  // dead lanes (NaN coordinates) compare false everywhere: not a mismatch
             fix_mirror(j0, jn, false, xi, yi, ki, wi);
-            st_2d += 32ull * jn;
+            st_pw += (unsigned)jn;
           } else {
-            st_check += 32ull * jn;
+            st_pw += (unsigned)jn;
 #pragma unroll 2
             for (int jj = j0; jj < j0 + jn; ++jj) {
               const double2 pj = cxy[jj];
@@ -801,22 +841,28 @@ pairbin_kernel(PBParams P) {
       }
     }
     // bound the per-lane 32-bit counters: registers go to shared memory at the end of every item
+    cf_spill();
+    cf_bin = -1;
+    __syncwarp();
     flush_regs();
   }
   flush_hist(cur_cat);
+  {  // blocks booked at classification time are tallied by the classifying lane
+    if (st_closed) atomicAdd(&g_pb_stats[0], 32ull * st_closed);
+  }
   if (lane == 0) {
-    if (st_closed) atomicAdd(&g_pb_stats[0], st_closed);
-    if (st_1d) atomicAdd(&g_pb_stats[1], st_1d);
-    if (st_2d) atomicAdd(&g_pb_stats[2], st_2d);
-    if (st_check) atomicAdd(&g_pb_stats[3], st_check);
-    if (st_generic) atomicAdd(&g_pb_stats[4], st_generic);
+    if (st_1d) atomicAdd(&g_pb_stats[1], 32ull * st_1d);
+    if (st_pw) atomicAdd(&g_pb_stats[2], 32ull * st_pw);
   }
 }
 
-// Pre-pass: bounding box of every 32-point chunk of every catalogue (one warp per chunk).
-// Slot of chunk c of catalogue `cat`: (cat_off[cat] + 32 c) / 32 + cat  (distinct and monotone).
+// Pre-pass: bounding box and sums of every 32-point chunk of every catalogue (one warp per chunk).
+// Slot of chunk c of catalogue `cat`: (cat_off[cat] + 32 c) / 32 + cat  (distinct and monotone); PB_SLOT doubles
+// per slot: {xmin, xmax, ymin, ymax, sum k w, sum w, -, -}.
+constexpr int PB_SLOT = 8;
 __global__ void __launch_bounds__(256)
-pairbin_boxes_kernel(const double* __restrict__ px, const double* __restrict__ py, const int64_t* __restrict__ cat_off,
+pairbin_boxes_kernel(const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pk,
+                     const double* __restrict__ pw, const int64_t* __restrict__ cat_off,
                      int32_t ncat, int64_t chunks_per_cat, double* __restrict__ boxes) {
   const int lane = threadIdx.x & 31;
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -827,18 +873,22 @@ pairbin_boxes_kernel(const double* __restrict__ px, const double* __restrict__ p
   if (c * PB_CHUNK >= n) return;
   const bool ok = j < n;
   const double x = ok ? px[off + j] : 0.0, y = ok ? py[off + j] : 0.0;
+  const double wj = ok ? (pw ? pw[off + j] : 1.0) : 0.0;
+  const double kj = ok ? pk[off + j] * wj : 0.0;
   const double a = warp_min(ok ? x : INFINITY), b = warp_max(ok ? x : -INFINITY);
   const double cc = warp_min(ok ? y : INFINITY), d = warp_max(ok ? y : -INFINITY);
+  const double sk = warp_sum(kj), sw = warp_sum(wj);
   if (lane == 0) {
-    double* o = boxes + 4 * ((off + c * PB_CHUNK) / PB_CHUNK + cat);
+    double* o = boxes + PB_SLOT * ((off + c * PB_CHUNK) / PB_CHUNK + cat);
     o[0] = a; o[1] = b; o[2] = cc; o[3] = d;
+    o[4] = sk; o[5] = sw; o[6] = 0.0; o[7] = 0.0;
   }
 }
 
 extern "C" int tgp_pairbin_tile(void) { return PB_CHUNK; }
 
 extern "C" int64_t tgp_pairbin_work_doubles(int64_t total_points, int32_t ncat) {
-  return 4 * (total_points / PB_CHUNK + (int64_t)ncat + 2);
+  return 8 * (total_points / PB_CHUNK + (int64_t)ncat + 2);   // PB_SLOT doubles per chunk slot
 }
 
 static int g_pb_block_sums = 1;   // tgp_set_option("pairbin_block_sums", 0): every pair evaluated individually
@@ -934,7 +984,8 @@ extern "C" int tgp_pairbin(const double* px, const double* py, const double* pk,
   if (work) {
     TGP_CHECK_ARG(((uintptr_t)work % 32) == 0, "work must be 32-byte aligned");
     const int64_t warps_needed = nblk * ncat;
-    pairbin_boxes_kernel<<<(unsigned)tgp_cdiv(warps_needed * 32, 256), 256, 0, st>>>(px, py, cat_off, ncat, nblk, work);
+    pairbin_boxes_kernel<<<(unsigned)tgp_cdiv(warps_needed * 32, 256), 256, 0, st>>>(px, py, pk, pw, cat_off, ncat, nblk,
+                                                                                       work);
     TGP_LAUNCH_CHECK();
     P.boxes = work;
   }
