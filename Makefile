@@ -1,7 +1,8 @@
 # Builds the C-ABI library (CUDA, sm_100a) and the CPU oracle.  No GPU needed to build.
 NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unknown-pragmas -Xptxas -v
+EXTRA     ?=
+NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unknown-pragmas -Xptxas -v $(EXTRA)
 CSRC      := treegp_b200/csrc
 OBJDIR    := build
 LIB       := treegp_b200/libtreegp_b200.so

@@ -287,7 +287,7 @@ def run_ours(args):
     # provably share a bin are summed in closed form and cost no per-pair FP64 work
     st_tot = max(1, sum(stats.values()))
     frac_paths = {k: v / st_tot for k, v in stats.items()}
-    evaluated = my_pairs * (1.0 - frac_paths["closed_form"])
+    evaluated = my_pairs * (1.0 - frac_paths["closed_form"] - frac_paths["one_axis_sorted"])
     ach_gops = ops_per_pair * evaluated / kern_s / 1e9
     ach_pp = ops_per_pair * my_pairs / pp_s / 1e9
     same_counts = bool(torch.equal(res_pp[0], res[0])) if world == 1 else None

@@ -207,7 +207,8 @@ int tgp_pairbin_tile(void);
 /* Diagnostics: how many pairs (32 x columns per processed block) of all tgp_pairbin launches since the last
  * reset went through each path: host8[0] closed form (whole block in one bin and its mirror image), [1] one
  * varying axis (one compare pair per pair of points), [2] pair by pair in a 2 x 2 bin window or through the
- * generic path (the diagonal blocks are not tallied).  Synchronous. */
+ * generic path (the diagonal blocks are not tallied), [3] one varying axis answered by a rank query on the
+ * chunk's sorted copy (6 probes per row point instead of 32 compares).  Synchronous. */
 int tgp_pairbin_stats(unsigned long long* host8 /*host*/, int reset);
 
 /* Tuning knobs for experiments (not needed for normal use).  "gemm_config": -1 automatic,

@@ -140,3 +140,49 @@ def test_pairbin_n20000_vs_oracle(gpu_ready):
     _check(res, ref)
     assert res[0].sum() == ref["npairs"].sum()
     _check(_gpu_pairbin(x, y, k, None, 0.0, mx, nb, "TwoD", hilbert=True), ref)
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("kind", ["uniform", "lattice"])
+def test_pairbin_block_forms_equal_pair_by_pair(gpu_ready, weighted, kind):
+    """The block forms (whole block booked from chunk sums; one-axis blocks answered by a rank query on the sorted
+    chunk) against the same kernel with them switched off (every pair evaluated individually), at a size where
+    most blocks take them.  Counts identical; sums to summation order.  The lattice puts thousands of
+    displacements exactly on bin edges (spacing 0.5, bin width 8), which is where the exact mirrored-bin check of
+    the rank query has to hand blocks back to the pair-by-pair path."""
+    from treegp_b200 import backend
+
+    rng = np.random.default_rng(11)
+    if kind == "uniform":
+        n = 150000
+        x, y = rng.uniform(0, 400, n), rng.uniform(0, 400, n)
+        mx, nb = 280.0, 21
+    else:
+        g = np.arange(0, 300, dtype=np.float64) * 0.5
+        X, Y = np.meshgrid(g, g)
+        x, y = X.ravel(), Y.ravel()
+        n = len(x)
+        mx, nb = 64.0, 16
+    k = rng.normal(size=n)
+    w = rng.uniform(0.5, 2.0, n) if weighted else None
+    backend.pairbin_stats(reset=True)
+    fast = _gpu_pairbin(x, y, k, w, 0.0, mx, nb, "TwoD", hilbert=True)
+    stats = backend.pairbin_stats(reset=True)
+    assert stats["closed_form"] > 0
+    if kind == "uniform":
+        assert stats["one_axis_sorted"] > 0
+    else:   # every chunk of a lattice has columns on a bin edge: the rank query hands its blocks back
+        assert stats["one_axis"] > 0
+    backend.set_option("pairbin_block_sums", 0)
+    try:
+        slow = _gpu_pairbin(x, y, k, w, 0.0, mx, nb, "TwoD", hilbert=True)
+        st0 = backend.pairbin_stats(reset=True)
+    finally:
+        backend.set_option("pairbin_block_sums", 1)
+    assert st0["closed_form"] == 0 and st0["one_axis_sorted"] == 0 and st0["one_axis"] == 0
+    np.testing.assert_array_equal(fast[0], slow[0])
+    np.testing.assert_allclose(fast[1], slow[1], rtol=1e-12, atol=1e-12 * np.abs(slow[1]).max())
+    np.testing.assert_allclose(fast[2], slow[2], rtol=0, atol=1e-11 * max(1.0, np.abs(slow[2]).max()))
+    if kind == "uniform":   # point symmetric (on the lattice displacements sit ON bin edges, where the formula is not)
+        c = fast[0][0].reshape(nb, nb)
+        np.testing.assert_array_equal(c, c[::-1, ::-1])

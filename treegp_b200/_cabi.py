@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtreegp_b200.so")
+# TREEGP_B200_LIB: alternative build of the same library (kernel-tuning experiments only)
+LIB_PATH = os.environ.get("TREEGP_B200_LIB") or os.path.join(_HERE, "libtreegp_b200.so")
 
 ABI_VERSION = 1
 

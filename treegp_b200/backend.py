@@ -217,7 +217,7 @@ def pairbin_stats(reset=True):
     """Pairs per kernel path since the last reset (see tgp_pairbin_stats); synchronises the device."""
     buf = (ctypes.c_ulonglong * 8)()
     check(_cabi.load().tgp_pairbin_stats(buf, int(bool(reset))), "tgp_pairbin_stats")
-    keys = ("closed_form", "one_axis", "pairwise")
+    keys = ("closed_form", "one_axis", "pairwise", "one_axis_sorted")
     return {k: int(buf[i]) for i, k in enumerate(keys)}
 
 

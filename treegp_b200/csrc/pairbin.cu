@@ -42,6 +42,9 @@
 constexpr int PB_CHUNK = 32;          // column points per block (= row points per warp)
 constexpr int PB_MAX_WARPS = 8;       // warps per CTA (each owns a private histogram)
 constexpr int PB_FLUSH_ITEMS = 2048;  // keeps the 32-bit private counters from overflowing
+constexpr int PB_SLOT = 8;            // doubles per chunk slot of the pre-pass: box + sums
+constexpr int PB_SORTED = 6 * PB_CHUNK;  // + {sorted x, suffix k w, suffix w, sorted y, suffix k w, suffix w}
+constexpr int PB_STRIDE = PB_SLOT + PB_SORTED;   // the two records of a chunk are stored back to back
 
 struct PBParams {
   const double *px, *py, *pk, *pw;
@@ -51,6 +54,7 @@ struct PBParams {
   double *sumw, *sumwkk, *sumwr;
   unsigned long long* counter;  // dynamic work counter (zeroed before the launch)
   const double* boxes;          // optional precomputed chunk boxes + sums (8 doubles per slot) or NULL
+  const double* sorted;         // optional per-chunk sorted coordinates + suffix sums (PB_SORTED doubles per slot)
   double lo2;       // pairs need r2 >= lo2 (= max(min_sep^2, DBL_TRUE_MIN) for TwoD; min_sep^2 for Log)
   double hi;        // TwoD: max_sep (|dx|,|dy| < hi);  Log: max_sep^2 (r2 < hi)
   double inv_bin;   // TwoD: nbins / (2 max_sep)
@@ -62,8 +66,8 @@ struct PBParams {
 };
 
 // Which path the pairs of all launches since the last reset took (in pairs): [0] closed form (block in one bin),
-// [1] one varying axis, [2] pair by pair (2 x 2 window with or without the per-pair range test, generic
-// sub-blocks).  Diagnostics for bench.py / DESIGN.md.
+// [1] one varying axis, pair by pair, [2] pair by pair (2 x 2 window with or without the per-pair range test,
+// generic sub-blocks), [3] one varying axis answered by a rank query on the sorted chunk.  Diagnostics.
 __device__ unsigned long long g_pb_stats[8];
 
 __device__ __forceinline__ int pb_bin_twod(double d, double hi, double inv_bin, int nbins,
@@ -164,7 +168,7 @@ __device__ __forceinline__ double pb_unkey(long long k) {
 // the ordered doubles inside a bracket of a few ulp(t) + ulp(t + xi) around t + xi.  `ok` is cleared if no
 // bracket was found (the caller then uses the generic path).  NaN xi -> NaN (dead lanes: every comparison
 // false); infinite t is returned unchanged (nbins == 1: the bit is constant).
-__device__ __forceinline__ double pb_coord_ge(double xi, double t, bool& ok) {
+__device__ __noinline__ double pb_coord_ge(double xi, double t, bool& ok) {
   if (isinf(t) || isnan(xi)) return isnan(xi) ? xi : t;
   const double c = t + xi;
   double e = (fabs(t) + fabs(c)) * 0x1p-50 + 0x1p-1060;
@@ -179,7 +183,7 @@ __device__ __forceinline__ double pb_coord_ge(double xi, double t, bool& ok) {
   return pb_unkey(khi);
 }
 // Largest X with fl(X - xi) <= t.
-__device__ __forceinline__ double pb_coord_le(double xi, double t, bool& ok) {
+__device__ __noinline__ double pb_coord_le(double xi, double t, bool& ok) {
   if (isinf(t) || isnan(xi)) return isnan(xi) ? xi : t;
   const double c = t + xi;
   double e = (fabs(t) + fabs(c)) * 0x1p-50 + 0x1p-1060;
@@ -338,7 +342,10 @@ __device__ __forceinline__ int pb_classify_twod(double iminx, double imaxx, doub
 }
 
 template <int BT, bool WEIGHTED>
-__global__ void __launch_bounds__(PB_MAX_WARPS * 32)
+#ifndef PB_MIN_CTAS
+#define PB_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(PB_MAX_WARPS * 32, PB_MIN_CTAS)
 pairbin_kernel(PBParams P) {
   extern __shared__ __align__(16) unsigned char pb_smem[];
   const int nb = P.nb, nbins = P.nbins, nwarps = P.warps;
@@ -518,7 +525,7 @@ pairbin_kernel(PBParams P) {
   };
   const double M = P.hi, lo2 = P.lo2;
   const int R = P.run;
-  unsigned st_closed = 0, st_1d = 0, st_pw = 0;   // column counts (x 32 rows = pairs): closed form / one axis / pairwise
+  unsigned st_closed = 0, st_1d = 0, st_pw = 0, st_sorted = 0;   // column counts (x 32 rows = pairs) per path
   int cur_cat = -1;
   int since_flush = 0;
   while (true) {
@@ -584,13 +591,14 @@ pairbin_kernel(PBParams P) {
       // ---- lane l classifies column chunk sc + l ----
       const int64_t mychunk = sc + lane;
       int cls = PB_OUT;
+      int kind = 0;   // 0: raw points; 1 / 2: one-axis block answered from the x- / y-sorted copy of the chunk
       int win[4] = {0, 0, 0, 0};
       if (mychunk < c_hi) {
         const int64_t j0g = mychunk * PB_CHUNK;
         const int cnt = (int)((n - j0g < PB_CHUNK) ? (n - j0g) : PB_CHUNK);
         double cminx = INFINITY, cmaxx = -INFINITY, cminy = INFINITY, cmaxy = -INFINITY;
         if (P.boxes) {
-          const double4 bb = *reinterpret_cast<const double4*>(P.boxes + 8 * ((off + j0g) / PB_CHUNK + cat));
+          const double4 bb = *reinterpret_cast<const double4*>(P.boxes + PB_STRIDE * ((off + j0g) / PB_CHUNK + cat));
           cminx = bb.x; cmaxx = bb.y; cminy = bb.z; cmaxy = bb.w;
         } else {
           const double* xs = P.px + off + j0g;
@@ -626,9 +634,12 @@ pairbin_kernel(PBParams P) {
           // columns' k w)); the points of the chunk are never loaded.  Consecutive chunks of a lane mostly hit
           // the same bin: the lane keeps one open bin in registers and spills to the warp histogram on a change.
           const int x0 = win[0] & 0xffff, y0 = win[1] & 0xffff, rx0 = win[2] & 0xffff, ry0 = win[3] & 0xffff;
-          if ((win[0] >> 16) == 0 && (win[1] >> 16) == 0 && (win[2] >> 16) == 0 && (win[3] >> 16) == 0 &&
-              rx0 == nbins - 1 - x0 && ry0 == nbins - 1 - y0) {
-            const double2 sums = *reinterpret_cast<const double2*>(P.boxes + 8 * ((off + j0g) / PB_CHUNK + cat) + 4);
+          const bool one_x = (win[0] >> 16) == 0 && (win[2] >> 16) == 0 && rx0 == nbins - 1 - x0;
+          const bool one_y = (win[1] >> 16) == 0 && (win[3] >> 16) == 0 && ry0 == nbins - 1 - y0;
+          // exactly one varying axis: the block is answered from the chunk's points sorted along that axis
+          if (P.sorted && cnt == PB_CHUNK) kind = (one_y && !one_x) ? 1 : ((one_x && !one_y) ? 2 : 0);
+          if (one_x && one_y) {
+            const double2 sums = *reinterpret_cast<const double2*>(P.boxes + PB_STRIDE * ((off + j0g) / PB_CHUNK + cat) + 4);
             const int o = y0 * nbins + x0;
             if (o != cf_bin) { cf_spill(); cf_bin = o; }
             cf_cnt += (unsigned)(nlive * cnt);
@@ -643,13 +654,29 @@ pairbin_kernel(PBParams P) {
       // ---- process the non-OUT chunks; the next chunk's points are prefetched into registers ----
       unsigned rest = todo;
       double nx_ = 0.0, ny_ = 0.0, nk_ = 0.0, nw_ = 1.0;
-      auto fetch = [&](int c) {
+      double2 nsum_ = make_double2(0.0, 0.0);
+      int nkind_ = 0;
+      auto fetch_raw = [&](int c) {
         const int64_t jg = (sc + c) * PB_CHUNK + lane;
         const bool ok = jg < n;
         nx_ = ok ? P.px[off + jg] : 0.0;
         ny_ = ok ? P.py[off + jg] : 0.0;
         if constexpr (WEIGHTED) nw_ = ok ? P.pw[off + jg] : 0.0;
         nk_ = ok ? P.pk[off + jg] * nw_ : 0.0;
+      };
+      auto fetch = [&](int c) {
+        nkind_ = __shfl_sync(0xffffffffu, kind, c);
+        const int64_t slot = (off + (sc + c) * PB_CHUNK) / PB_CHUNK + cat;
+        if (P.boxes) nsum_ = *reinterpret_cast<const double2*>(P.boxes + PB_STRIDE * slot + 4);
+        if (nkind_ == 0) {
+          fetch_raw(c);
+        } else {
+          // sorted copy: coordinate along the varying axis, suffix sums of k w (and w) in that order
+          const double* sp = P.sorted + PB_STRIDE * slot + (nkind_ == 1 ? 0 : 3 * PB_CHUNK) + lane;
+          nx_ = sp[0];
+          ny_ = sp[PB_CHUNK];
+          if constexpr (WEIGHTED) nw_ = sp[2 * PB_CHUNK];
+        }
       };
       if (rest) fetch(__ffs(rest) - 1);
       while (rest) {
@@ -659,8 +686,22 @@ pairbin_kernel(PBParams P) {
         cxy[lane] = make_double2(nx_, ny_);
         ck[lane] = nk_;
         if constexpr (WEIGHTED) cw[lane] = nw_;
+        int ckind = nkind_;
+        const double2 csum = nsum_;
         __syncwarp();
         if (rest) fetch(__ffs(rest) - 1);
+        // a block staged from the sorted copy that ends up on a pair-by-pair path needs the raw points after all
+        auto ensure_raw = [&]() {
+          if (ckind == 0) return;
+          __syncwarp();
+          fetch_raw(c);
+          cxy[lane] = make_double2(nx_, ny_);
+          ck[lane] = nk_;
+          if constexpr (WEIGHTED) cw[lane] = nw_;
+          __syncwarp();
+          if (rest) fetch(__ffs(rest) - 1);   // fetch_raw clobbered the prefetch registers
+          ckind = 0;
+        };
         const int64_t j0g = (sc + c) * PB_CHUNK;
         const int jcount = (int)((n - j0g < PB_CHUNK) ? (n - j0g) : PB_CHUNK);
         int ccls = __shfl_sync(0xffffffffu, cls, c);
@@ -720,7 +761,7 @@ pairbin_kernel(PBParams P) {
               if (covers(ax, fy0)) fx0 = ax;
               else if (covers(fx0, ay)) fy0 = ay;
               else if (covers(ax, ay)) { fx0 = ax; fy0 = ay; }
-              else { generic_block(j0, jn, 0, xi, yi, ki, wi, live); continue; }  // edge asymmetry: exact path
+              else { ensure_raw(); generic_block(j0, jn, 0, xi, yi, ki, wi, live); continue; }  // edge asymmetry: exact path
             }
             A.fx0 = fx0; A.fy0 = fy0;
             A.ownerI = owner;
@@ -738,6 +779,7 @@ pairbin_kernel(PBParams P) {
             if (!__all_sync(0xffffffffu, okl)) {
               // (never seen in practice) the per-lane thresholds did not settle: generic path for this block
               A.fx0 = -1;
+              ensure_raw();
               generic_block(j0, jn, 0, xi, yi, ki, wi, live);
               continue;
             }
@@ -753,26 +795,56 @@ pairbin_kernel(PBParams P) {
             const unsigned n_add = live ? (unsigned)jn : 0u;
             if (one_x || one_y) {
               // chunk sums of the column values (dead columns were staged as zero)
-              const double S = warp_sum(ck[lane]);
-              double Sw = 0.0;
-              if constexpr (WEIGHTED) Sw = warp_sum(cw[lane]);
+              double S, Sw = 0.0;
+              if (P.boxes) {
+                S = csum.x;
+                Sw = csum.y;
+              } else {
+                S = warp_sum(ck[lane]);
+                if constexpr (WEIGHTED) Sw = warp_sum(cw[lane]);
+              }
               const bool bx = (x0 - A.fx0) != 0, by = (y0 - A.fy0) != 0;   // window bits of the constant axes
               double bs = 0.0, bw_ = 0.0;     // block-local sums / count of the pairs in the upper bin of the varying axis
               unsigned bc = 0u;
-              if (one_x && one_y) {
+              bool done = false;
+              if (ckind != 0) {
+                // Staged: the chunk's coordinates along the varying axis in ascending order (cxy[].x) with the
+                // suffix sums of k w (cxy[].y) and w (cw[]).  The lane's bit "c_j >= T" is a rank query: lower
+                // bound by bisection (6 probes instead of 32 compares), count and sum read off the suffix arrays.
+                const double T = (ckind == 1) ? A.Tx : A.Ty, RT = (ckind == 1) ? A.RTx : A.RTy;
+                int pos = 0;
+#pragma unroll
+                for (int st = 16; st > 0; st >>= 1) pos += (cxy[pos + st - 1].x < T) ? st : 0;
+                pos += (cxy[pos].x < T) ? 1 : 0;           // number of columns with c_j < T, 0 .. 32
+                // exact mirrored bits: columns below pos need c_j <= RT, columns from pos on need c_j > RT; the
+                // order makes the two neighbours of the split the only ones to check
+                const bool okl = !live || ((pos == 0 || cxy[pos - 1].x <= RT) && (pos == PB_CHUNK || cxy[pos].x > RT));
+                if (__all_sync(0xffffffffu, okl)) {
+                  bc = live ? (unsigned)(PB_CHUNK - pos) : 0u;
+                  bs = (pos < PB_CHUNK) ? cxy[pos].y : 0.0;
+                  if constexpr (WEIGHTED) bw_ = (pos < PB_CHUNK) ? cw[pos] : 0.0;
+                  done = true;
+                } else {
+                  // (rare) a column within rounding of a bin edge: redo the block pair by pair from the raw points
+                  ensure_raw();
+                }
+              }
+              const bool vary_x = one_y;                 // (one_x && one_y): treated as "x varies" with a constant bit
+              if (done) {
+              } else if (one_x && one_y) {
                 // all 32 x jn pairs in one bin (and its mirror image): closed form, no per-pair work at all
                 bs = bx ? S : 0.0;
                 bw_ = bx ? Sw : 0.0;
                 bc = bx ? n_add : 0u;
               } else if (one_y) {
-#pragma unroll 8
+#pragma unroll 2
                 for (int jj = 0; jj < jn; ++jj) {
                   const double cj = cxy[jj].x, kj = ck[jj];
                   if constexpr (WEIGHTED) { const double wj = cw[jj]; PB_PAIR_1D_W(bs, bw_, bc, A.mmc, cj, kj, wj, A.Tx, A.RTx); }
                   else PB_PAIR_1D(bs, bc, A.mmc, cj, kj, A.Tx, A.RTx);
                 }
               } else {
-#pragma unroll 8
+#pragma unroll 2
                 for (int jj = 0; jj < jn; ++jj) {
                   const double cj = cxy[jj].y, kj = ck[jj];
                   if constexpr (WEIGHTED) { const double wj = cw[jj]; PB_PAIR_1D_W(bs, bw_, bc, A.mmc, cj, kj, wj, A.Ty, A.RTy); }
@@ -781,7 +853,6 @@ pairbin_kernel(PBParams P) {
               }
               // fold into the window registers.  v = the varying axis (x unless only x is constant):
               // sum[v bit] += bs; sum[other bit] += S if that bit is set; sum[both] += bs if the other bit is set.
-              const bool vary_x = one_y;                 // (one_x && one_y): treated as "x varies" with a constant bit
               const bool other = vary_x ? by : bx;
               A.tot += S;
               if constexpr (WEIGHTED) A.wtot += Sw;
@@ -797,8 +868,10 @@ pairbin_kernel(PBParams P) {
               }
               if (other) { A.fsxy += bs; A.fcxy += bc; if constexpr (WEIGHTED) A.fwxy += bw_; }
               if (!live) A.mmc = 0u;
-              if (!(one_x && one_y)) fix_mirror(j0, jn, false, xi, yi, ki, wi);
-              if (one_x && one_y) { if (lane == 0) st_closed += (unsigned)jn; } else st_1d += (unsigned)jn;
+              if (!(one_x && one_y) && !done) fix_mirror(j0, jn, false, xi, yi, ki, wi);
+              if (one_x && one_y) { if (lane == 0) st_closed += (unsigned)jn; }
+              else if (done) st_sorted += (unsigned)jn;
+              else st_1d += (unsigned)jn;
               continue;
             }
 #pragma unroll 4
@@ -853,17 +926,17 @@ pairbin_kernel(PBParams P) {
   if (lane == 0) {
     if (st_1d) atomicAdd(&g_pb_stats[1], 32ull * st_1d);
     if (st_pw) atomicAdd(&g_pb_stats[2], 32ull * st_pw);
+    if (st_sorted) atomicAdd(&g_pb_stats[3], 32ull * st_sorted);
   }
 }
 
 // Pre-pass: bounding box and sums of every 32-point chunk of every catalogue (one warp per chunk).
 // Slot of chunk c of catalogue `cat`: (cat_off[cat] + 32 c) / 32 + cat  (distinct and monotone); PB_SLOT doubles
 // per slot: {xmin, xmax, ymin, ymax, sum k w, sum w, -, -}.
-constexpr int PB_SLOT = 8;
 __global__ void __launch_bounds__(256)
 pairbin_boxes_kernel(const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ pk,
                      const double* __restrict__ pw, const int64_t* __restrict__ cat_off,
-                     int32_t ncat, int64_t chunks_per_cat, double* __restrict__ boxes) {
+                     int32_t ncat, int64_t chunks_per_cat, double* __restrict__ boxes, double* __restrict__ sorted) {
   const int lane = threadIdx.x & 31;
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t cat = w / chunks_per_cat, c = w % chunks_per_cat;
@@ -878,17 +951,47 @@ pairbin_boxes_kernel(const double* __restrict__ px, const double* __restrict__ p
   const double a = warp_min(ok ? x : INFINITY), b = warp_max(ok ? x : -INFINITY);
   const double cc = warp_min(ok ? y : INFINITY), d = warp_max(ok ? y : -INFINITY);
   const double sk = warp_sum(kj), sw = warp_sum(wj);
+  const int64_t slot = (off + c * PB_CHUNK) / PB_CHUNK + cat;
   if (lane == 0) {
-    double* o = boxes + PB_SLOT * ((off + c * PB_CHUNK) / PB_CHUNK + cat);
+    double* o = boxes + PB_STRIDE * slot;
     o[0] = a; o[1] = b; o[2] = cc; o[3] = d;
     o[4] = sk; o[5] = sw; o[6] = 0.0; o[7] = 0.0;
+  }
+  if (sorted) {
+    // the chunk sorted by x and by y (bitonic network over the 32 lanes; absent points sort last as +inf with
+    // zero payload), each with the suffix sums of k w and w in that order
+#pragma unroll
+    for (int axis = 0; axis < 2; ++axis) {
+      double key = ok ? (axis == 0 ? x : y) : INFINITY, vk = kj, vw = wj;
+#pragma unroll
+      for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+          const double okey = __shfl_xor_sync(0xffffffffu, key, j2);
+          const double ovk = __shfl_xor_sync(0xffffffffu, vk, j2);
+          const double ovw = __shfl_xor_sync(0xffffffffu, vw, j2);
+          const bool take_min = ((lane & j2) == 0) == ((lane & k2) == 0);
+          const bool swap = take_min ? (okey < key) : (okey > key);
+          if (swap) { key = okey; vk = ovk; vw = ovw; }
+        }
+      }
+#pragma unroll
+      for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        const double tk = __shfl_down_sync(0xffffffffu, vk, o2), tw = __shfl_down_sync(0xffffffffu, vw, o2);
+        if (lane + o2 < 32) { vk += tk; vw += tw; }
+      }
+      double* o = sorted + PB_STRIDE * slot + axis * 3 * PB_CHUNK + lane;
+      o[0] = key;
+      o[PB_CHUNK] = vk;
+      o[2 * PB_CHUNK] = vw;
+    }
   }
 }
 
 extern "C" int tgp_pairbin_tile(void) { return PB_CHUNK; }
 
 extern "C" int64_t tgp_pairbin_work_doubles(int64_t total_points, int32_t ncat) {
-  return 8 * (total_points / PB_CHUNK + (int64_t)ncat + 2);   // PB_SLOT doubles per chunk slot
+  return (int64_t)PB_STRIDE * (total_points / PB_CHUNK + (int64_t)ncat + 2);
 }
 
 static int g_pb_block_sums = 1;   // tgp_set_option("pairbin_block_sums", 0): every pair evaluated individually
@@ -981,13 +1084,15 @@ extern "C" int tgp_pairbin(const double* px, const double* py, const double* pk,
   if (grid > grid_target) grid = grid_target;
 
   P.boxes = nullptr;
+  P.sorted = nullptr;
   if (work) {
     TGP_CHECK_ARG(((uintptr_t)work % 32) == 0, "work must be 32-byte aligned");
     const int64_t warps_needed = nblk * ncat;
     pairbin_boxes_kernel<<<(unsigned)tgp_cdiv(warps_needed * 32, 256), 256, 0, st>>>(px, py, pk, pw, cat_off, ncat, nblk,
-                                                                                       work);
+                                                                                       work, work + PB_SLOT);
     TGP_LAUNCH_CHECK();
     P.boxes = work;
+    P.sorted = work + PB_SLOT;
   }
 
   static unsigned launch_seq = 0;
