@@ -581,6 +581,8 @@ pairbin_kernel(PBParams P) {
     const double iminx = warp_min(live ? xi : INFINITY), imaxx = warp_max(live ? xi : -INFINITY);
     const double iminy = warp_min(live ? yi : INFINITY), imaxy = warp_max(live ? yi : -INFINITY);
     const long long owner = (long long)(off + ib * PB_CHUNK);
+    // pre-pass record of chunk c of this catalogue: slot (off + 32 c) / 32 + cat = off / 32 + c + cat
+    const double* rec0 = P.boxes ? P.boxes + (size_t)PB_STRIDE * (size_t)(off / PB_CHUNK + cat) : nullptr;
     // row-block aggregates for the blocks that are booked whole
     const double rowK = warp_sum(ki);
     double rowW = 0.0;
@@ -598,7 +600,7 @@ pairbin_kernel(PBParams P) {
         const int cnt = (int)((n - j0g < PB_CHUNK) ? (n - j0g) : PB_CHUNK);
         double cminx = INFINITY, cmaxx = -INFINITY, cminy = INFINITY, cmaxy = -INFINITY;
         if (P.boxes) {
-          const double4 bb = *reinterpret_cast<const double4*>(P.boxes + PB_STRIDE * ((off + j0g) / PB_CHUNK + cat));
+          const double4 bb = *reinterpret_cast<const double4*>(rec0 + (size_t)PB_STRIDE * (size_t)mychunk);
           cminx = bb.x; cmaxx = bb.y; cminy = bb.z; cmaxy = bb.w;
         } else {
           const double* xs = P.px + off + j0g;
@@ -639,7 +641,7 @@ pairbin_kernel(PBParams P) {
           // exactly one varying axis: the block is answered from the chunk's points sorted along that axis
           if (P.sorted && cnt == PB_CHUNK) kind = (one_y && !one_x) ? 1 : ((one_x && !one_y) ? 2 : 0);
           if (one_x && one_y) {
-            const double2 sums = *reinterpret_cast<const double2*>(P.boxes + PB_STRIDE * ((off + j0g) / PB_CHUNK + cat) + 4);
+            const double2 sums = *reinterpret_cast<const double2*>(rec0 + (size_t)PB_STRIDE * (size_t)mychunk + 4);
             const int o = y0 * nbins + x0;
             if (o != cf_bin) { cf_spill(); cf_bin = o; }
             cf_cnt += (unsigned)(nlive * cnt);
@@ -666,13 +668,13 @@ pairbin_kernel(PBParams P) {
       };
       auto fetch = [&](int c) {
         nkind_ = __shfl_sync(0xffffffffu, kind, c);
-        const int64_t slot = (off + (sc + c) * PB_CHUNK) / PB_CHUNK + cat;
-        if (P.boxes) nsum_ = *reinterpret_cast<const double2*>(P.boxes + PB_STRIDE * slot + 4);
+        const double* rec = rec0 + (size_t)PB_STRIDE * (size_t)(sc + c);
+        if (P.boxes) nsum_ = *reinterpret_cast<const double2*>(rec + 4);
         if (nkind_ == 0) {
           fetch_raw(c);
         } else {
           // sorted copy: coordinate along the varying axis, suffix sums of k w (and w) in that order
-          const double* sp = P.sorted + PB_STRIDE * slot + (nkind_ == 1 ? 0 : 3 * PB_CHUNK) + lane;
+          const double* sp = rec + PB_SLOT + (nkind_ == 1 ? 0 : 3 * PB_CHUNK) + lane;
           nx_ = sp[0];
           ny_ = sp[PB_CHUNK];
           if constexpr (WEIGHTED) nw_ = sp[2 * PB_CHUNK];
