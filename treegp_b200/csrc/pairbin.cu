@@ -707,15 +707,15 @@ pairbin_kernel(PBParams P) {
         const int64_t j0g = (sc + c) * PB_CHUNK;
         const int jcount = (int)((n - j0g < PB_CHUNK) ? (n - j0g) : PB_CHUNK);
         int ccls = __shfl_sync(0xffffffffu, cls, c);
-        if (BT != TGP_BIN_TWOD || (sc + c) == ib) {
-          generic_block(0, jcount, ((sc + c) == ib) ? lane + 1 : 0, xi, yi, ki, wi, live);
-          continue;
-        }
+        // Log bins and the diagonal block (needs j > i) go pair by pair through the generic path -- which has ONE
+        // call site, at the top of the sub-block loop below, so that its code exists once in the kernel
+        const bool whole_generic = (BT != TGP_BIN_TWOD) || (sc + c) == ib;
+        const int gfirst = ((sc + c) == ib) ? lane + 1 : 0;
         int cw4[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) cw4[k] = __shfl_sync(0xffffffffu, win[k], c);
         // a block whose window is too wide is retried as four 8-column sub-blocks
-        const int nsub = (ccls == PB_GENERIC) ? 4 : 1;
+        const int nsub = (ccls == PB_GENERIC && !whole_generic) ? 4 : 1;
         int scls = ccls;
         int sw[4] = {cw4[0], cw4[1], cw4[2], cw4[3]};
         if (nsub == 4) {
@@ -742,7 +742,7 @@ pairbin_kernel(PBParams P) {
             if (jn <= 0) bcls = PB_OUT;
           }
           if (bcls == PB_OUT) continue;
-          if (bcls == PB_GENERIC) { generic_block(j0, jn, 0, xi, yi, ki, wi, live); st_pw += (unsigned)jn; continue; }
+          bool gen = (bcls == PB_GENERIC);
           // ---- register path: make sure the open window covers this block ----
           const int x0 = bw[0] & 0xffff, x1 = x0 + (bw[0] >> 16), y0 = bw[1] & 0xffff, y1 = y0 + (bw[1] >> 16);
           const int rx0 = bw[2] & 0xffff, rx1 = rx0 + (bw[2] >> 16), ry0 = bw[3] & 0xffff, ry1 = ry0 + (bw[3] >> 16);
@@ -752,7 +752,7 @@ pairbin_kernel(PBParams P) {
                    rx0 >= nbins - 2 - fx0 && rx1 <= nbins - 1 - fx0 && ry0 >= nbins - 2 - fy0 && ry1 <= nbins - 1 - fy0;
           };
           const bool fits = A.fx0 >= 0 && A.ownerI == owner && covers(A.fx0, A.fy0);
-          if (!fits) {
+          if (!fits && !gen) {
             flush_regs();
             // candidate origins: the block's lowest bin, or one below it (a window must stay inside the grid
             // unless nbins == 1)
@@ -763,8 +763,9 @@ pairbin_kernel(PBParams P) {
               if (covers(ax, fy0)) fx0 = ax;
               else if (covers(fx0, ay)) fy0 = ay;
               else if (covers(ax, ay)) { fx0 = ax; fy0 = ay; }
-              else { ensure_raw(); generic_block(j0, jn, 0, xi, yi, ki, wi, live); continue; }  // edge asymmetry: exact path
+              else gen = true;   // edge asymmetry: exact path
             }
+            if (!gen) {
             A.fx0 = fx0; A.fy0 = fy0;
             A.ownerI = owner;
             A.rki = ki;
@@ -781,10 +782,15 @@ pairbin_kernel(PBParams P) {
             if (!__all_sync(0xffffffffu, okl)) {
               // (never seen in practice) the per-lane thresholds did not settle: generic path for this block
               A.fx0 = -1;
-              ensure_raw();
-              generic_block(j0, jn, 0, xi, yi, ki, wi, live);
-              continue;
+              gen = true;
             }
+            }
+          }
+          if (gen) {
+            ensure_raw();
+            generic_block(j0, jn, gfirst, xi, yi, ki, wi, live);
+            if (!whole_generic) st_pw += (unsigned)jn;
+            continue;
           }
           if (bcls == PB_REG_FULL) {
             // Every pair of the block is in range.  How many bins do its displacements span?  one_x: all dx in ONE
