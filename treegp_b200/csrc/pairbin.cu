@@ -451,8 +451,7 @@ pairbin_kernel(PBParams P) {
     __syncwarp();
   };
   // Warp-private shared histogram -> global (red.global), then clear.
-  auto flush_hist = [&](int cat) {
-    flush_regs();
+  auto flush_hist = [&](int cat) {   // the window registers were flushed at the end of the last item
     __syncwarp();
     if (cat >= 0) {
       for (int b = lane; b < nb; b += 32) {
@@ -876,12 +875,11 @@ pairbin_kernel(PBParams P) {
               }
               if (other) { A.fsxy += bs; A.fcxy += bc; if constexpr (WEIGHTED) A.fwxy += bw_; }
               if (!live) A.mmc = 0u;
-              if (!(one_x && one_y) && !done) fix_mirror(j0, jn, false, xi, yi, ki, wi);
               if (one_x && one_y) { if (lane == 0) st_closed += (unsigned)jn; }
               else if (done) st_sorted += (unsigned)jn;
               else st_1d += (unsigned)jn;
-              continue;
-            }
+              if ((one_x && one_y) || done) continue;   // nothing can be inconsistent
+            } else {
 #pragma unroll 4
             for (int jj = j0; jj < j0 + jn; ++jj) {
               const double2 pj = cxy[jj];
@@ -895,8 +893,8 @@ pairbin_kernel(PBParams P) {
             }
             A.nin += n_add;
             if (!live) A.mmc = 0u;  // dead lanes (NaN coordinates) compare false everywhere: not a mismatch
-            fix_mirror(j0, jn, false, xi, yi, ki, wi);
             st_pw += (unsigned)jn;
+            }
           } else {
             st_pw += (unsigned)jn;
 #pragma unroll 2
@@ -916,8 +914,8 @@ pairbin_kernel(PBParams P) {
                 A.nin += 1u;
               }
             }
-            fix_mirror(j0, jn, true, xi, yi, ki, wi);
           }
+          fix_mirror(j0, jn, bcls != PB_REG_FULL, xi, yi, ki, wi);
         }
       }
     }
