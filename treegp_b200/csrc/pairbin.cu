@@ -341,10 +341,13 @@ __device__ __forceinline__ int pb_classify_twod(double iminx, double imaxx, doub
   return (ax < M && ay < M && r2min >= lo2) ? PB_REG_FULL : PB_REG_CHECK;
 }
 
-template <int BT, bool WEIGHTED>
 #ifndef PB_MIN_CTAS
 #define PB_MIN_CTAS 2
 #endif
+// BS: block forms on (closed-form / one-axis blocks).  BS = false is the pair-by-pair kernel: every pair of every
+// in-range block goes through the compare / masked-FMA loop (TwoD) -- the kernel the 10-FP64-ops-per-pair
+// roofline is stated for; it is compiled without any of the block-form code.
+template <int BT, bool WEIGHTED, bool BS>
 __global__ void __launch_bounds__(PB_MAX_WARPS * 32, PB_MIN_CTAS)
 pairbin_kernel(PBParams P) {
   extern __shared__ __align__(16) unsigned char pb_smem[];
@@ -629,7 +632,7 @@ pairbin_kernel(PBParams P) {
           if (mychunk == ib) cls = PB_GENERIC;
         }
         if (!(iminx <= imaxx)) cls = PB_OUT;  // no live row in this warp
-        if (BT == TGP_BIN_TWOD && cls == PB_REG_FULL && P.boxes && P.block_sums) {
+        if (BS && BT == TGP_BIN_TWOD && cls == PB_REG_FULL && P.boxes) {
           // Whole block in ONE forward bin and in its mirror image: the classifying lane books the block itself
           // from the chunk sums of the pre-pass (count = rows x columns, sum = (sum of the rows' k w) x (sum of the
           // columns' k w)); the points of the chunk are never loaded.  Consecutive chunks of a lane mostly hit
@@ -666,6 +669,10 @@ pairbin_kernel(PBParams P) {
         nk_ = ok ? P.pk[off + jg] * nw_ : 0.0;
       };
       auto fetch = [&](int c) {
+        if constexpr (!BS) {
+          fetch_raw(c);
+          return;
+        }
         nkind_ = __shfl_sync(0xffffffffu, kind, c);
         const double* rec = rec0 + (size_t)PB_STRIDE * (size_t)(sc + c);
         if (P.boxes) nsum_ = *reinterpret_cast<const double2*>(rec + 4);
@@ -796,7 +803,7 @@ pairbin_kernel(PBParams P) {
             // forward bin, all -dx in ONE mirrored bin, and that bin is the mirror image (the usual case: bins are
             // much wider than a 32-point chunk of a sorted catalogue).  Such an axis needs no per-pair decision:
             // the window bit is the same for the whole block.
-            const bool whole = (nsub == 1) && P.block_sums;
+            const bool whole = BS && (nsub == 1);
             const bool one_x = whole && x1 == x0 && rx1 == rx0 && rx0 == nbins - 1 - x0;
             const bool one_y = whole && y1 == y0 && ry1 == ry0 && ry0 == nbins - 1 - y0;
             const unsigned n_add = live ? (unsigned)jn : 0u;
@@ -1107,16 +1114,18 @@ extern "C" int tgp_pairbin(const double* px, const double* py, const double* pk,
   P.counter = reinterpret_cast<unsigned long long*>(cbase) + (launch_seq++ % PB_COUNTER_SLOTS);
   TGP_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), st));
 
-#define TGP_PB_LAUNCH(BT, W)                                                                          \
-  do {                                                                                                \
-    TGP_CUDA(cudaFuncSetAttribute(pairbin_kernel<BT, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  (int)budget));                                                      \
-    pairbin_kernel<BT, W><<<(unsigned)grid, warps * 32, smem, st>>>(P);                               \
+#define TGP_PB_LAUNCH(BT, W, BS)                                                                          \
+  do {                                                                                                    \
+    TGP_CUDA(cudaFuncSetAttribute(pairbin_kernel<BT, W, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  (int)budget));                                                          \
+    pairbin_kernel<BT, W, BS><<<(unsigned)grid, warps * 32, smem, st>>>(P);                               \
   } while (0)
-  if (twod) {
-    if (weighted) TGP_PB_LAUNCH(TGP_BIN_TWOD, true); else TGP_PB_LAUNCH(TGP_BIN_TWOD, false);
+  if (twod && P.block_sums) {
+    if (weighted) TGP_PB_LAUNCH(TGP_BIN_TWOD, true, true); else TGP_PB_LAUNCH(TGP_BIN_TWOD, false, true);
+  } else if (twod) {
+    if (weighted) TGP_PB_LAUNCH(TGP_BIN_TWOD, true, false); else TGP_PB_LAUNCH(TGP_BIN_TWOD, false, false);
   } else {
-    if (weighted) TGP_PB_LAUNCH(TGP_BIN_LOG, true); else TGP_PB_LAUNCH(TGP_BIN_LOG, false);
+    if (weighted) TGP_PB_LAUNCH(TGP_BIN_LOG, true, false); else TGP_PB_LAUNCH(TGP_BIN_LOG, false, false);
   }
 #undef TGP_PB_LAUNCH
   TGP_LAUNCH_CHECK();
