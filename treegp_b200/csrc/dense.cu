@@ -237,28 +237,45 @@ __device__ __forceinline__ void potf2_smem(double* __restrict__ S, double* __res
   if (tid == 0) g_pf_cycles[0] = g_pf_cycles[1] = g_pf_cycles[2] = 0;
 #endif
   for (int k0 = 0; k0 < NB; k0 += PF_B) {
-    // (i) 16 x 16 diagonal sub-block, lanes 0..15 hold one row each
+    // (i) 16 x 16 diagonal sub-block, lanes 0..15 hold one row each.  Pivots in groups of four: inside a group
+    // every pivot updates only the group's own columns (<= 3 shuffle + DFMA pairs on the critical path); the
+    // columns to the right take the group's rank-4 update afterwards, as independent shuffle / DFMA pairs.
     if (warp == 0) {
       double a[PF_B];
-      const int r = k0 + (lane & 15);
+      const int l15 = lane & 15;
+      const int r = k0 + l15;
+      unsigned badmask = 0u;       // the same in every lane (d is a broadcast)
 #pragma unroll
       for (int c = 0; c < PF_B; ++c) a[c] = S[r * NB_PITCH + k0 + c];
 #pragma unroll
-      for (int j = 0; j < PF_B; ++j) {
-        const double d = __shfl_sync(0xffffffffu, a[j], j);           // pivot a_jj from lane j
-        if (lane == j && k0 + j < n && (!(d > 0.0) || !isfinite(d)))
-          atomicCAS(info, 0, (int32_t)(global_off + k0 + j + 1));     // keep the first failure
-        // one reciprocal square root per pivot: l_jj = d * rsqrt(d), l_ij = a_ij * rsqrt(d) (no FP64 divide or
-        // square-root call on the critical path; results agree with sqrt/divide to ~1 ulp)
-        const double rinv = rsqrt(d);                                 // CUDA's rsqrt is accurate to 1 ulp
-        const int l15 = lane & 15;
-        a[j] = (l15 == j) ? d * rinv : ((l15 > j) ? a[j] * rinv : a[j]);
-        if (lane == j) rdiag[k0 + j] = rinv;
+      for (int grp = 0; grp < PF_B / 4; ++grp) {
 #pragma unroll
-        for (int c = 0; c < PF_B; ++c) {   // constant bounds + static predicate: keeps a[] in registers
-          if (c > j) {
-            const double lcj = __shfl_sync(0xffffffffu, a[j], c);     // l_cj from lane c
-            a[c] = (l15 >= c) ? fma(-a[j], lcj, a[c]) : a[c];
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = 4 * grp + jj;
+          const double d = __shfl_sync(0xffffffffu, a[j], j);           // pivot a_jj from lane j
+          // not positive definite / not finite: remembered branch-free (bit j), reported once after the block
+          badmask |= (k0 + j < n && (!(d > 0.0) || !isfinite(d))) ? (1u << j) : 0u;
+          // one reciprocal square root per pivot: l_jj = d * rsqrt(d), l_ij = a_ij * rsqrt(d) (no FP64 divide or
+          // square-root call on the critical path; results agree with sqrt/divide to ~1 ulp)
+          const double rinv = rsqrt(d);
+          a[j] = (l15 == j) ? d * rinv : ((l15 > j) ? a[j] * rinv : a[j]);
+          if (lane == j) rdiag[k0 + j] = rinv;
+#pragma unroll
+          for (int c = 0; c < PF_B; ++c) {   // constant bounds + static predicate: keeps a[] in registers
+            if (c > j && c < 4 * grp + 4) {
+              const double lcj = __shfl_sync(0xffffffffu, a[j], c);     // l_cj from lane c
+              a[c] = (l15 >= c) ? fma(-a[j], lcj, a[c]) : a[c];
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < PF_B; ++c) {
+          if (c >= 4 * grp + 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const double lck = __shfl_sync(0xffffffffu, a[4 * grp + k], c);
+              a[c] = (l15 >= c) ? fma(-a[4 * grp + k], lck, a[c]) : a[c];
+            }
           }
         }
       }
@@ -266,6 +283,8 @@ __device__ __forceinline__ void potf2_smem(double* __restrict__ S, double* __res
 #pragma unroll
         for (int c = 0; c < PF_B; ++c) S[r * NB_PITCH + k0 + c] = a[c];
       }
+      if (badmask && lane == 0)   // keep the first failure (LAPACK's info)
+        atomicCAS(info, 0, (int32_t)(global_off + k0 + __ffs(badmask)));
     }
     __syncthreads();
     PF_T(0);
@@ -287,16 +306,21 @@ __device__ __forceinline__ void potf2_smem(double* __restrict__ S, double* __res
     }
     __syncthreads();
     PF_T(1);
-    // (iii) trailing update: S[i][c] -= sum_k S[i][k0+k] S[c][k0+k], k0+16 <= c <= i < 64; 16 x 16 thread grid
+    // (iii) trailing update S[i][c] -= sum_k S[i][k0+k] S[c][k0+k], k0+16 <= c <= i < 64, on the DMMA pipe:
+    // the lower 8 x 8 blocks of the trailing square are dealt to the warps, K = 16 = four m8n8k4 steps each
     if (below > 0) {
-      const int ty = tid >> 4, tx = tid & 15;
-      for (int i = k0 + PF_B + ty; i < NB; i += 16) {
-        for (int c = k0 + PF_B + tx; c <= i; c += 16) {
-          double acc = S[i * NB_PITCH + c];
+      const int m0 = k0 + PF_B, nblk = below / 8, g8 = lane >> 2, t4 = lane & 3;
+      for (int p = warp; p < nblk * (nblk + 1) / 2; p += 8) {
+        int bi = 0, bj = p;
+        while (bj > bi) { bj -= bi + 1; ++bi; }
+        const double* Ar = S + (m0 + 8 * bi + g8) * NB_PITCH + k0 + t4;
+        const double* Br = S + (m0 + 8 * bj + g8) * NB_PITCH + k0 + t4;
+        double c0 = 0.0, c1 = 0.0;
 #pragma unroll
-          for (int k = 0; k < PF_B; ++k) acc = fma(-S[i * NB_PITCH + k0 + k], S[c * NB_PITCH + k0 + k], acc);
-          S[i * NB_PITCH + c] = acc;
-        }
+        for (int ks = 0; ks < PF_B / 4; ++ks) dmma884(c0, c1, Ar[4 * ks], Br[4 * ks]);
+        double* Cr = S + (m0 + 8 * bi + g8) * NB_PITCH + m0 + 8 * bj + 2 * t4;
+        Cr[0] -= c0;
+        Cr[1] -= c1;
       }
     }
     __syncthreads();
@@ -466,7 +490,8 @@ static int trsm_panel_launch(const double* L, int nb, int64_t ldl, double* B, in
 constexpr int PL_THREADS = 256;
 constexpr int PL_P = NB + 2;                                 // pitch of the T / L tiles (even: 16-byte LDS)
 constexpr int PL_RING_D = STAGES * (NB + NB) * BK;            // operand ring, doubles
-constexpr int PL_TAIL_D = 2 * NB * PL_P + NB;                 // T tile + L tile + 1/diag (aliases the ring)
+constexpr int PL_MP = 9;                                      // pitch of the 8 x 8 inverse blocks
+constexpr int PL_TAIL_D = 2 * NB * PL_P + NB + 8 * 8 * PL_MP;  // T tile + L tile + 1/diag + 8 inverses (aliases the ring)
 constexpr int PL_SMEM = (PL_RING_D > PL_TAIL_D ? PL_RING_D : PL_TAIL_D) * 8;
 constexpr int PL_NFLAGS = 4096;
 __device__ unsigned g_panel_flags[PL_NFLAGS];
@@ -630,6 +655,7 @@ panel_left_kernel(double* __restrict__ Akk, int64_t ld, int w, int64_t below, in
   double* Ts = psm;                        // NB x PL_P
   double* Ls = psm + NB * PL_P;            // NB x PL_P, Ls[i][c] = L_jj[i][c]
   double* dinv = Ls + NB * PL_P;           // 1 / L_jj[c][c]
+  double* Minv = dinv + NB;                // inverses of the 8 x 8 diagonal blocks of L_jj, pitch PL_MP
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -655,52 +681,71 @@ panel_left_kernel(double* __restrict__ Akk, int64_t ld, int w, int64_t below, in
   PL_T(10);
   const double* Lg = Akk + (int64_t)c0 * ld + c0;
   {
-    // Ls[i][c] = L[i][c] / L[c][c]: with the columns pre-scaled the substitution below runs on the UNSCALED
-    // unknowns u_c = x_c L_cc, so its critical path is one shuffle + one DFMA per pivot (no multiply, no
-    // shared-memory load); x = u / diag at the end.  Every thread only ever touches column c = tid % 64.
+    // Ls[i][c] = L[i][c] (strictly lower part), dinv[c] = 1 / L[c][c].  Every thread touches column tid % 64.
     const int c = tid & (NB - 1);
-    const double dc = (c < nbj) ? 1.0 / __ldcg(Lg + (int64_t)c * ld + c) : 1.0;
 #pragma unroll 4
     for (int idx = tid; idx < NB * NB; idx += PL_THREADS) {
       const int i = idx / NB;
-      Ls[i * PL_P + c] = (i < nbj && c < i) ? __ldcg(Lg + (int64_t)i * ld + c) * dc : 0.0;
+      Ls[i * PL_P + c] = (i < nbj && c < i) ? __ldcg(Lg + (int64_t)i * ld + c) : 0.0;
     }
-    if (tid < NB) dinv[tid] = dc;
+    if (tid < NB) dinv[tid] = (tid < nbj) ? 1.0 / __ldcg(Lg + (int64_t)tid * ld + tid) : 1.0;
+  }
+  __syncthreads();
+  // inverses of the eight 8 x 8 diagonal blocks of L (warp b, lane c < 8: column c of block b by forward
+  // substitution); everything else of the solve is then DMMA work without a scalar dependency chain
+  if (lane < 8) {
+    const int o = warp * 8, c = lane;
+    double z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double sacc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < i) sacc = fma(-Ls[(o + i) * PL_P + o + k], (k >= c) ? z[k] : 0.0, sacc);
+      z[i] = (i >= c) ? sacc * dinv[o + i] : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Minv[warp * PL_MP * 8 + i * PL_MP + c] = z[i];
   }
   __syncthreads();
   PL_T(11);
 
-  // ---- X = T L^-T: 4 threads per row, thread q owns columns q, q+4, ..., two pivots per step -----------
+  // ---- X = T L^-T by 8-column blocks: X_b = (T_b - sum_{b' < b} X_b' L_bb'^T) L_bb^-T.  Warp w owns rows
+  // 8 w .. 8 w + 7 of the tile, so every dependency stays inside the warp (syncwarp only); right-looking: as
+  // soon as X_b exists it is subtracted from all later column blocks (independent accumulators) -------------
   {
-    const int row = warp * 8 + g, q = t;
-    const int lbase = lane & ~3;
-    double x[16];
+    double* Tw = Ts + (warp * 8 + g) * PL_P;      // this lane's row of the tile
+    double acc[8][2];
 #pragma unroll
-    for (int m = 0; m < 16; ++m) x[m] = Ts[row * PL_P + q + 4 * m];
+    for (int bb = 0; bb < 8; ++bb) {
+      const double2 v = *reinterpret_cast<const double2*>(Tw + 8 * bb + 2 * t);
+      acc[bb][0] = v.x;
+      acc[bb][1] = v.y;
+    }
 #pragma unroll
-    for (int mj = 0; mj < 16; ++mj) {
+    for (int bb = 0; bb < 8; ++bb) {
+      // R_b from the accumulator layout (row g, columns 2t, 2t+1) to the A-operand layout (row g, k = t)
+      __syncwarp();
+      *reinterpret_cast<double2*>(Tw + 8 * bb + 2 * t) = make_double2(acc[bb][0], acc[bb][1]);
+      __syncwarp();
+      const double a0 = Tw[8 * bb + t], a1 = Tw[8 * bb + 4 + t];
+      const double* Mi = Minv + bb * PL_MP * 8 + g * PL_MP;
+      double x0 = 0.0, x1 = 0.0;
+      dmma884(x0, x1, a0, Mi[t]);
+      dmma884(x0, x1, a1, Mi[4 + t]);
+      __syncwarp();
+      *reinterpret_cast<double2*>(Tw + 8 * bb + 2 * t) = make_double2(x0, x1);     // X_b, final
+      if (bb < 7) {
+        __syncwarp();
+        const double na0 = -Tw[8 * bb + t], na1 = -Tw[8 * bb + 4 + t];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int ja = 4 * mj + 2 * h, qa = 2 * h;          // pivots ja (thread qa) and ja + 1 (thread qa + 1)
-        const double ua = __shfl_sync(0xffffffffu, x[mj], lbase | qa);
-        double ub = fma(-ua, Ls[(ja + 1) * PL_P + ja], x[mj]);
-        ub = __shfl_sync(0xffffffffu, ub, lbase | (qa + 1));
-        if (q == qa + 1) x[mj] = ub;
-        {
-          const double2 l = *reinterpret_cast<const double2*>(Ls + (q + 4 * mj) * PL_P + ja);
-          if (q > qa + 1) x[mj] = fma(-ub, l.y, fma(-ua, l.x, x[mj]));
-        }
-#pragma unroll
-        for (int m = mj + 1; m < 16; ++m) {
-          const double2 l = *reinterpret_cast<const double2*>(Ls + (q + 4 * m) * PL_P + ja);
-          x[m] = fma(-ub, l.y, fma(-ua, l.x, x[m]));
+        for (int b2 = bb + 1; b2 < 8; ++b2) {
+          const double* Lr = Ls + (8 * b2 + g) * PL_P + 8 * bb;
+          dmma884(acc[b2][0], acc[b2][1], na0, Lr[t]);
+          dmma884(acc[b2][0], acc[b2][1], na1, Lr[4 + t]);
         }
       }
     }
-#pragma unroll
-    for (int m = 0; m < 16; ++m) x[m] *= dinv[q + 4 * m];
-#pragma unroll
-    for (int m = 0; m < 16; ++m) Ts[row * PL_P + q + 4 * m] = x[m];
   }
   __syncthreads();
   PL_T(12);
