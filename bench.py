@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--npoints", type=int, default=1_000_000, help="2PCF points (configs[3]: 1e6)")
@@ -79,19 +79,29 @@ class ClockSampler(threading.Thread):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                parts = [p.strip() for p in out.stdout.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+        # one nvidia-smi process sampling every 50 ms (a fresh process per sample takes ~0.2 s to start, which is
+        # as long as a whole timed step by now)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.strip().split(",")]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+            if self._stop_evt.is_set():
+                break
 
     def stop(self):
         self._stop_evt.set()
+        if getattr(self, "proc", None) is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
         self.join(timeout=3)
         sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]

@@ -138,6 +138,13 @@ int tgp_predict_var(const double* Xs, int64_t M, const double* X, int64_t N,
                     const tgp_kernel* k /*host*/, const double* L, int64_t ld, double* work,
                     int64_t chunk, double* var, void* stream);
 
+/* out[m] = uniform mean of y0 over the k grid points nearest to Xq_m (squared Euclidean distance, exact ties
+ * towards the lower grid index, values summed in order of increasing distance).  Replaces
+ * KNeighborsRegressor(n_neighbors=k).fit(X0, y0).predict(Xq), the mean-function lookup of
+ * gp_interp.py:236-238.  Xq: (M, ndim), X0: (n0, ndim), y0: n0.  1 <= k <= min(n0, 16). */
+int tgp_knn_mean(const double* Xq, int64_t M, const double* X0, const double* y0, int64_t n0,
+                 int32_t ndim, int32_t k, double* out, void* stream);
+
 /* ---- (3) two-point correlation function ------------------------------------------------------ */
 
 typedef enum {

@@ -136,6 +136,12 @@ def install():
         st = lambda key: torch.as_tensor(np.stack([r[key] for r in rows]))
         return st("npairs"), st("weight"), st("sumwkk"), (st("sumwr") if bt == "Log" else None)
 
+    def knn_mean(X0, y0, Xq, k):
+        from sklearn.neighbors import KNeighborsRegressor   # what the reference itself calls (gp_interp.py:236-238)
+
+        return torch.as_tensor(KNeighborsRegressor(n_neighbors=k).fit(_np(X0), _np(y0)).predict(_np(Xq)))
+
+    backend.knn_mean = knn_mean
     backend.kmat_sym, backend.kmat_cross, backend.potrf, backend.potrs_vec = kmat_sym, kmat_cross, potrf, potrs_vec
     backend.trsm_rows, backend.gemm_nt_sub, backend.loglike = trsm_rows, gemm_nt_sub, loglike
     backend.predict_mean, backend.predict_var, backend.pairbin = predict_mean, predict_var, pairbin

@@ -109,3 +109,40 @@ def test_predict_mean_truncated_support(gpu_ready, fam, ndim):
                                            ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(work.data_ptr()),
                                            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
     np.testing.assert_allclose(out.cpu().numpy(), full, rtol=0, atol=tol)
+
+
+@pytest.mark.parametrize("ndim", [1, 2])
+@pytest.mark.parametrize("k", [1, 4, 7, 16])
+def test_knn_mean_matches_sklearn(gpu_ready, ndim, k):
+    """tgp_knn_mean against what the reference calls (gp_interp.py:236-238): KNeighborsRegressor(k).fit(X0, y0)
+    .predict(X).  Random queries have no distance ties, so the neighbour sets are identical and the means agree
+    to rounding; also a two-column y0 (the reference then picks a column with indice_meanify) and a grid that
+    spans several shared-memory tiles."""
+    from sklearn.neighbors import KNeighborsRegressor
+    from treegp_b200 import backend
+
+    rng = np.random.default_rng(3 + k)
+    for n0, m in ((2500, 20000), (20, 300), (1025, 5)):
+        X0 = rng.uniform(-1, 1, size=(n0, ndim))
+        Xq = rng.uniform(-1.2, 1.2, size=(m, ndim))
+        y0 = rng.normal(size=(n0, 2))
+        ref = KNeighborsRegressor(n_neighbors=k).fit(X0, y0).predict(Xq)
+        got = backend.knn_mean(X0, y0, Xq, k).cpu().numpy()
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-14 * k)
+        got1 = backend.knn_mean(X0, y0[:, 1], Xq, k).cpu().numpy()
+        np.testing.assert_allclose(got1, ref[:, 1], rtol=0, atol=1e-14 * k)
+    with pytest.raises(ValueError):
+        backend.knn_mean(X0[:3], y0[:3], Xq, 4)
+
+
+def test_knn_mean_ties_take_the_lower_index(gpu_ready):
+    """On a regular grid a query at a node has four neighbours at the same distance: the documented rule (lower
+    grid index first) makes the result deterministic where sklearn's KD-tree leaves it open."""
+    from treegp_b200 import backend
+
+    g = np.arange(5.0)
+    X0 = np.array([[a, b] for a in g for b in g])
+    y0 = np.arange(25.0)
+    got = backend.knn_mean(X0, y0, np.array([[2.0, 2.0]]), 4).cpu().numpy()
+    # nearest: index 12 (d = 0), then 7, 11, 13, 17 at d = 1 -> 7, 11, 13 by index
+    np.testing.assert_allclose(got, [(12 + 7 + 11 + 13) / 4.0])

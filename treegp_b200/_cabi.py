@@ -47,6 +47,7 @@ SIGNATURES = {
     "tgp_predict_mean_trunc": [_vp, _i64, _vp, _i64, _kp, _vp, _vp, _vp, _vp],
     "tgp_predict_work_doubles": [_i64],
     "tgp_profile_qcut": [_i32],
+    "tgp_knn_mean": [_vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp, _vp],
     "tgp_predict_var": [_vp, _i64, _vp, _i64, _kp, _vp, _i64, _vp, _i64, _vp, _vp],
     "tgp_pairbin": [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _i32, _f64, _f64, _i32, _i32,
                     _vp, _vp, _vp, _vp, _vp, _vp],

@@ -160,6 +160,27 @@ def predict_mean(Xs, X, kdesc, alpha, out=None, truncate=None):
     return out
 
 
+def knn_mean(X0, y0, Xq, k):
+    """Uniform mean of the k nearest grid values for every query point (gp_interp.py:236-238); y0 (n0,) or
+    (n0, ncols).  Returns a device tensor (M,) or (M, ncols)."""
+    X0, Xq = as_points(X0), as_points(Xq)
+    n0, M = X0.shape[0], Xq.shape[0]
+    if X0.shape[1] != Xq.shape[1]:
+        raise ValueError("query and grid dimensions differ")
+    if k > n0:
+        # what sklearn's KNeighborsRegressor raises
+        raise ValueError("Expected n_neighbors <= n_samples_fit, but n_neighbors = %d, n_samples_fit = %d" % (k, n0))
+    y0 = to_device(y0)
+    cols = [y0] if y0.dim() == 1 else [y0[:, j].contiguous() for j in range(y0.shape[1])]
+    outs = []
+    for col in cols:
+        out = torch.empty(M, dtype=F64, device=X0.device)
+        check(_cabi.load().tgp_knn_mean(_p(Xq), M, _p(X0), _p(col), n0, int(X0.shape[1]), int(k), _p(out), _stream()),
+              "tgp_knn_mean")
+        outs.append(out)
+    return outs[0] if y0.dim() == 1 else torch.stack(outs, dim=1)
+
+
 def predict_var(Xs, X, kdesc, L, chunk=None, out=None, work=None):
     Xs, X = as_points(Xs), as_points(X)
     M, N = Xs.shape[0], X.shape[0]
@@ -202,8 +223,9 @@ def hilbert_order(px, py):
     n = int(px.numel())
     if n == 0:
         return torch.zeros(0, dtype=torch.int64, device=px.device)
-    xmin, xmax = float(px.min().item()), float(px.max().item())
-    ymin, ymax = float(py.min().item()), float(py.max().item())
+    # one device->host transfer for the four extrema
+    ext = torch.stack([px.min(), px.max(), py.min(), py.max()]).cpu().numpy()
+    xmin, xmax, ymin, ymax = (float(v) for v in ext)
     extent = max(xmax - xmin, ymax - ymin)
     extent = extent * (1.0 + 1e-9) if extent > 0 else 1.0
     order = int(min(16, max(1, np.ceil(np.log2(max(np.sqrt(n), 2.0))) + 1)))

@@ -295,3 +295,84 @@ extern "C" int tgp_predict_var(const double* Xs, int64_t M, const double* X, int
   }
   return TGP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Mean-function lookup: uniform mean of the k nearest points of the meanify grid.
+// Replaces sklearn's KNeighborsRegressor(n_neighbors).fit(X0, y0).predict(X) at
+// /root/reference/treegp/gp_interp.py:236-238 (with the GP algebra on the device this
+// KD-tree query of every training / test point is the host-side tail of predict()).  The grid is small
+// (a few thousand points), so every query scans all of it: thread per query, grid tiles broadcast from
+// shared memory, the K best kept sorted in registers.  Distances are squared Euclidean in FP64; exact ties
+// are resolved towards the lower grid index (sklearn's KD-tree leaves them unspecified); the values are
+// summed in order of increasing distance, as numpy.mean does over sklearn's sorted neighbour list.
+// ---------------------------------------------------------------------------------------------
+constexpr int KNN_TILE = 1024;
+template <int K>
+__global__ void __launch_bounds__(256)
+knn_mean_kernel(const double* __restrict__ Xq, int64_t M, const double* __restrict__ X0,
+                const double* __restrict__ y0, int64_t n0, int ndim, int k, double* __restrict__ out) {
+  __shared__ double2 gxy[KNN_TILE];
+  __shared__ double gv[KNN_TILE];
+  const int tid = threadIdx.x;
+  const int64_t m = (int64_t)blockIdx.x * 256 + tid;
+  const bool live = m < M;
+  const double qx = live ? Xq[m * ndim] : 0.0;
+  const double qy = (live && ndim == 2) ? Xq[m * 2 + 1] : 0.0;
+  double bd[K], bv[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) { bd[j] = INFINITY; bv[j] = 0.0; }
+  for (int64_t n00 = 0; n00 < n0; n00 += KNN_TILE) {
+    __syncthreads();
+    for (int i = tid; i < KNN_TILE; i += 256) {
+      const int64_t n = n00 + i;
+      const bool ok = n < n0;
+      gxy[i] = make_double2(ok ? X0[n * ndim] : INFINITY, (ok && ndim == 2) ? X0[n * 2 + 1] : 0.0);
+      gv[i] = ok ? y0[n] : 0.0;
+    }
+    __syncthreads();
+    const int cnt = (int)((n0 - n00 < KNN_TILE) ? (n0 - n00) : KNN_TILE);
+    for (int i = 0; i < cnt; ++i) {
+      const double2 p = gxy[i];
+      const double dx = p.x - qx, dy = p.y - qy;
+      double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+      if (d < bd[K - 1]) {       // strict: an equal distance later in index order does not displace an earlier one
+        double v = gv[i];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {   // insertion into the ascending list, stable for ties
+          if (d < bd[j]) {
+            const double td = bd[j], tv = bv[j];
+            bd[j] = d; bv[j] = v;
+            d = td; v = tv;
+          }
+        }
+      }
+    }
+  }
+  if (live) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+      if (j < k) s += bv[j];
+    out[m] = s / (double)k;
+  }
+}
+
+extern "C" int tgp_knn_mean(const double* Xq, int64_t M, const double* X0, const double* y0, int64_t n0,
+                            int32_t ndim, int32_t k, double* out, void* stream) {
+  TGP_CHECK_ARG(M >= 0 && n0 >= 1 && (ndim == 1 || ndim == 2), "M/n0/ndim");
+  TGP_CHECK_ARG(k >= 1 && k <= n0, "need 1 <= n_neighbors <= number of grid points");
+  if (k > 16) {
+    tgp_set_error("tgp_knn_mean: n_neighbors > 16 is not supported");
+    return TGP_ERR_UNSUPPORTED;
+  }
+  if (M == 0) return TGP_OK;
+  TGP_CHECK_ARG(Xq && X0 && y0 && out, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)tgp_cdiv(M, 256);
+  // K = list length compiled in (entries beyond k stay +inf and are never summed... they are: cap by j < k)
+  if (k <= 4) knn_mean_kernel<4><<<grid, 256, 0, st>>>(Xq, M, X0, y0, n0, ndim, k, out);
+  else if (k <= 8) knn_mean_kernel<8><<<grid, 256, 0, st>>>(Xq, M, X0, y0, n0, ndim, k, out);
+  else knn_mean_kernel<16><<<grid, 256, 0, st>>>(Xq, M, X0, y0, n0, ndim, k, out);
+  TGP_LAUNCH_CHECK();
+  return TGP_OK;
+}

@@ -3,7 +3,7 @@
 SURVEY.md section 8f-1 ranks this path NEXT after the GP hot path.  Provided here on the host (it is O(N)
 binning that runs once, offline, in the reference as well):
 * the consumer side GPInterpolation needs (gp_interp.py:97-107, :229-243): reading the spatial-average
-  table and the k-nearest-neighbour lookup (sklearn's KD-tree, exactly as in the reference);
+  table and the k-nearest-neighbour lookup (`tgp_knn_mean` on the device; sklearn's KD-tree in the reference);
 * the producer, class ``meanify`` (mirror of /root/reference/treegp/meanify.py:12-165): 2-D binned mean /
   median / weighted mean over many fields and a FITS table writer -- written with numpy bin counts
   instead of scipy.stats.binned_statistic_2d, and with the in-repo FITS writer instead of fitsio.
@@ -22,12 +22,12 @@ def read_average(path):
 
 
 def knn_average(X0, y0, X, n_neighbors):
-    """Uniform mean of the `n_neighbors` nearest mean-grid values (gp_interp.py:236-238)."""
-    from sklearn.neighbors import KNeighborsRegressor
+    """Uniform mean of the `n_neighbors` nearest mean-grid values (gp_interp.py:236-238: sklearn's
+    KNeighborsRegressor in the reference; here every query scans the small grid on the device)."""
+    from . import backend
 
-    neigh = KNeighborsRegressor(n_neighbors=n_neighbors)
-    neigh.fit(X0, y0)
-    return neigh.predict(X)
+    return backend.knn_mean(np.asarray(X0, dtype=np.float64), np.asarray(y0, dtype=np.float64),
+                            np.asarray(X, dtype=np.float64), int(n_neighbors)).cpu().numpy()
 
 
 def _bin_index(v, edges):

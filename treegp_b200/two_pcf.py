@@ -254,7 +254,8 @@ class two_pcf(object):
         y_err = np.asarray(y_err, dtype=np.float64)
         pw = None if np.sum(y_err) == 0 else backend.to_device(1.0 / y_err ** 2)
         n = len(y)
-        px, py = backend.to_device(X[:, 0]), backend.to_device(X[:, 1])
+        Xd = backend.to_device(X)            # one upload of the (n, 2) array; the columns are split on the device
+        px, py = Xd[:, 0].contiguous(), Xd[:, 1].contiguous()
         pk = backend.to_device(y - np.mean(y))
         if self.anisotropic:
             # spatially sorted input lets the kernel keep 32 x 32 pair blocks inside a 2 x 2 bin window
