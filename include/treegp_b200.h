@@ -208,6 +208,18 @@ int tgp_hilbert_keys(const double* x, const double* y, int64_t n, double xmin, d
  *  mult  : host uint8[b * n], overwritten.  More than 255 draws of one point -> TGP_ERR_UNSUPPORTED. */
 int tgp_bootstrap_multiplicities(uint64_t* state, int64_t n, int64_t b, const int64_t* pos, uint8_t* mult);
 
+/* Pair sums of a VECTOR field's 2-point functions in log-radius bins (E/B diagnostics; replaces the all-pairs numpy
+ * loop of utils.py:5-74 and TreeCorr's VVCorrelation of utils.py:110-155 in the bin_slop -> 0 limit).
+ *  x, y, vx, vy : n points and the vector field there.
+ *  edges        : device double[nbins+1] thresholds on r^2 (treegp_b200.binning.logr_thresholds): a pair with
+ *                 d = z_j - z_i, r2 = |d|^2 != 0 goes to bin k = #{1 <= m <= nbins-1 : r2 >= edges[m]} iff
+ *                 edges[0] <= r2 < edges[nbins].
+ *  counts       : device int64[nbins], ACCUMULATED.
+ *  sums         : device double[6 * nbins], ACCUMULATED: {ln r, Re(v_i conj v_j), Re(v_i v_j), Im(v_i v_j),
+ *                 Re(v_i v_j conj(d)^2 / r2), Im(same)} each over nbins. */
+int tgp_vcorr(const double* x, const double* y, const double* vx, const double* vy, int64_t n,
+              const double* edges, int32_t nbins, int64_t* counts, double* sums, void* stream);
+
 /* Points per pair block: 32 (informational). */
 int tgp_pairbin_tile(void);
 

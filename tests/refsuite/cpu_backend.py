@@ -142,6 +142,13 @@ def install():
         return torch.as_tensor(KNeighborsRegressor(n_neighbors=k).fit(_np(X0), _np(y0)).predict(_np(Xq)))
 
     backend.knn_mean = knn_mean
+
+    def vcorr_sums(x, y, dx, dy, logrmin, dlogr, bins):
+        from oracle import eb_oracle
+
+        return eb_oracle.pair_sums(*(np.asarray(a, dtype=float) for a in (x, y, dx, dy)), logrmin, dlogr, bins)
+
+    backend.vcorr_sums = vcorr_sums
     backend.kmat_sym, backend.kmat_cross, backend.potrf, backend.potrs_vec = kmat_sym, kmat_cross, potrf, potrs_vec
     backend.trsm_rows, backend.gemm_nt_sub, backend.loglike = trsm_rows, gemm_nt_sub, loglike
     backend.predict_mean, backend.predict_var, backend.pairbin = predict_mean, predict_var, pairbin

@@ -269,30 +269,39 @@ def test_meanify_matches_binned_statistic(stat, tmp_path):
         treegp.meanify().add_field(np.zeros((3, 1)), np.zeros(3))
 
 
-def test_eb_decomposition_matches_all_pairs_formula():
-    """utils.vcorr (utils.py:5-74) restated without materialising all index pairs."""
-    import treegp_b200 as treegp
-    from treegp_b200.utils import vcorr
+def test_eb_oracle_matches_all_pairs_formula():
+    """oracle/eb_oracle.py (the checker of csrc/vcorr.cu) against the reference's own all-pairs formulas
+    (utils.py:38-74), and the threshold form of the log-radius binning against the floor formula."""
+    from oracle import eb_oracle
+    from treegp_b200 import binning
 
     rng = np.random.default_rng(2)
     n = 500
     x, y, dx, dy = rng.uniform(0, 1, n), rng.uniform(0, 1, n), rng.normal(size=n), rng.normal(size=n)
-    lr, xp, xm, xc, xz = vcorr(x, y, dx, dy, rmin=0.01, rmax=1.0, dlogr=0.2)
+    rmin, dlogr = 0.01, 0.2
+    bins = int(np.ceil(np.log(1 / rmin) / dlogr))
+    cnt_o, slr, sp, sz2, sm = eb_oracle.pair_sums(x, y, dx, dy, np.log(rmin), dlogr, bins)
     i1, i2 = np.triu_indices(n, 1)
     dr = (x[i2] - x[i1]) + 1j * (y[i2] - y[i1])
     ld = np.log(np.abs(dr))
-    bins = int(np.ceil(np.log(1 / 0.01) / 0.2))
-    hr = (np.log(0.01), np.log(0.01) + bins * 0.2)
+    hr = (np.log(rmin), np.log(rmin) + bins * dlogr)
     cnt = np.histogram(ld, bins=bins, range=hr)[0]
+    np.testing.assert_array_equal(cnt_o, cnt)
     v = dx + 1j * dy
-    np.testing.assert_allclose(xp, np.histogram(ld, bins=bins, range=hr, weights=dx[i1] * dx[i2] + dy[i1] * dy[i2])[0] / cnt, atol=1e-13)
+    np.testing.assert_allclose(sp, np.histogram(ld, bins=bins, range=hr, weights=dx[i1] * dx[i2] + dy[i1] * dy[i2])[0], atol=1e-11)
     vv = v[i1] * v[i2] * np.conj(dr) ** 2 / np.abs(dr) ** 2
-    np.testing.assert_allclose(xm, np.histogram(ld, bins=bins, range=hr, weights=vv.real)[0] / cnt, atol=1e-13)
-    np.testing.assert_allclose(xc, np.histogram(ld, bins=bins, range=hr, weights=vv.imag)[0] / cnt, atol=1e-13)
-    xie, xib, logr = treegp.comp_eb(x, y, dx, dy, rmin=0.01, rmax=1.0, dlogr=0.2)
-    xie2, xib2, logr2 = treegp.comp_eb_treecorr(x, y, dx, dy, rmin=0.01, rmax=1.0, dlogr=0.2)
-    assert xie.shape == xib.shape == logr.shape == xie2.shape == (bins,)
-    np.testing.assert_allclose(xie + xib, xp, atol=1e-13)
+    np.testing.assert_allclose(sm.real, np.histogram(ld, bins=bins, range=hr, weights=vv.real)[0], atol=1e-11)
+    np.testing.assert_allclose(sm.imag, np.histogram(ld, bins=bins, range=hr, weights=vv.imag)[0], atol=1e-11)
+    # thresholds on r^2 reproduce the floor formula
+    ed = binning.logr_thresholds(np.log(rmin), dlogr, bins)
+    r2 = np.abs(dr) ** 2
+    k_formula = np.floor((0.5 * np.log(r2) - np.log(rmin)) / dlogr).astype(int)
+    k_thr = np.searchsorted(ed, r2, side="right") - 1
+    inside = (k_formula >= 0) & (k_formula < bins)
+    assert np.mean(k_thr[inside] == k_formula[inside]) > 0.9999     # numpy's vector log may differ from libm by 1 ulp
+    for k in range(bins + 1):
+        assert np.floor((0.5 * np.log(ed[k]) - np.log(rmin)) / dlogr) >= k > np.floor(
+            (0.5 * np.log(np.nextafter(ed[k], 0)) - np.log(rmin)) / dlogr)
 
 
 def test_truncation_thresholds_are_below_1e_minus_40():

@@ -248,3 +248,36 @@ def test_sample_grf_has_the_kernel_covariance(gpu_ready):
     assert np.abs(emp - K).max() < 0.2 * K.max()      # 3000 draws: ~4 sigma of the sampling noise
     y, y_err = treegp.sample_grf(kernel, X, noise=0.1, seed=1)
     assert y.shape == (60,) and np.all(y_err == 0.1)
+
+
+def test_eb_pair_sums_and_api_on_the_device(gpu_ready):
+    """csrc/vcorr.cu through treegp.comp_eb / comp_eb_treecorr / utils.vcorr (utils.py:5-155) against the oracle
+    restatement of the reference's all-pairs loop.  Bins come from thresholds on r^2, so the counts equal the
+    floor((ln r - ln rmin)/dlogr) formula up to numpy's vector-log rounding at bin boundaries (allowed: a
+    handful of pairs); sums to 1e-10 of the bin's absolute sum."""
+    import treegp_b200 as treegp
+    from oracle import eb_oracle
+    from treegp_b200 import backend
+    from treegp_b200.utils import vcorr
+
+    rng = np.random.default_rng(4)
+    n = 3000
+    x, y = rng.uniform(0, 1, n), rng.uniform(0, 1, n)
+    dx, dy = rng.normal(size=n), rng.normal(size=n)
+    x[10], y[10] = x[11], y[11]                      # a coincident pair (r = 0) is skipped
+    rmin, rmax, dlogr = 0.002, 1.0, 0.05
+    bins = int(np.ceil(np.log(rmax / rmin) / dlogr))
+    ref = eb_oracle.pair_sums(x, y, dx, dy, np.log(rmin), dlogr, bins)
+    got = backend.vcorr_sums(x, y, dx, dy, np.log(rmin), dlogr, bins)
+    assert np.abs(got[0] - ref[0]).sum() <= 4 and got[0].sum() > 0.9 * n * (n - 1) / 2 * 0.5
+    scale = np.sqrt(np.maximum(ref[0], 1.0)) * 5 + 1.0       # a boundary pair moved between bins
+    for a, b in zip(got[1:], ref[1:]):
+        assert np.all(np.abs(a - b) <= 1e-10 * np.abs(b) + 1e-9 + (np.abs(got[0] - ref[0]) > 0) * scale)
+    lr, xp, xm, xc, xz = vcorr(x, y, dx, dy, rmin=rmin, rmax=rmax, dlogr=dlogr)
+    ok = ref[0] > 0
+    np.testing.assert_allclose(xp[ok], (ref[2] / ref[0])[ok], atol=1e-6)
+    np.testing.assert_allclose(lr[ok], (ref[1] / ref[0])[ok], atol=1e-6)
+    xie, xib, logr = treegp.comp_eb(x, y, dx, dy, rmin=rmin, rmax=rmax, dlogr=dlogr)
+    xie2, xib2, logr2 = treegp.comp_eb_treecorr(x, y, dx, dy, rmin=rmin, rmax=rmax, dlogr=dlogr)
+    assert xie.shape == xib.shape == logr.shape == xie2.shape == (bins,)
+    np.testing.assert_allclose((xie + xib)[ok], xp[ok], atol=1e-12)

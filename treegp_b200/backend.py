@@ -217,6 +217,22 @@ def pairbin(px, py, pk, pw, cat_off, max_cat_len, bin_type, edges, nbins, min_se
     return npairs, sumw, sumwkk, sumwr
 
 
+def vcorr_sums(x, y, dx, dy, logrmin, dlogr, bins):
+    """Pair sums of the vector-field correlation functions (utils.py:5-74) as numpy arrays:
+    counts, sum ln r, sum Re(v1 conj v2), sum v1 v2 (complex), sum v1 v2 conj(d)^2/|d|^2 (complex)."""
+    from . import binning
+
+    xd, yd, vxd, vyd = (to_device(np.asarray(a, dtype=np.float64)) for a in (x, y, dx, dy))
+    n = int(xd.numel())
+    edges = to_device(binning.logr_thresholds(logrmin, dlogr, bins))
+    counts = torch.zeros(bins, dtype=torch.int64, device=xd.device)
+    sums = torch.zeros((6, bins), dtype=F64, device=xd.device)
+    check(_cabi.load().tgp_vcorr(_p(xd), _p(yd), _p(vxd), _p(vyd), n, _p(edges), int(bins), _p(counts), _p(sums),
+                                 _stream()), "tgp_vcorr")
+    s = sums.cpu().numpy()
+    return (counts.cpu().numpy().astype(np.float64), s[0], s[1], s[2] + 1j * s[3], s[4] + 1j * s[5])
+
+
 def hilbert_order(px, py):
     """Permutation (device int64) that sorts the points along a Hilbert curve; makes tgp_pairbin's
     register path applicable.  The argsort is torch plumbing; the keys come from the C ABI."""

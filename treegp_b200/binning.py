@@ -69,6 +69,18 @@ def log_thresholds(min_sep, max_sep, nbins):
     return edges
 
 
+def logr_thresholds(logrmin, dlogr, bins):
+    """edges[k], k = 0..bins: smallest r^2 with floor((0.5 ln(r^2) - logrmin) / dlogr) >= k -- the log-radius
+    binning of utils.py:50-53 (`vcorr`); a pair is kept iff edges[0] <= r^2 < edges[bins]."""
+    logrmin, dlogr = float(logrmin), float(dlogr)
+    edges = np.empty(bins + 1)
+    for k in range(bins + 1):
+        lo = math.exp(2.0 * (logrmin + (k - 1.0) * dlogr))
+        hi = math.exp(2.0 * (logrmin + (k + 1.0) * dlogr))
+        edges[k] = _smallest_true(lambda v: math.floor((0.5 * math.log(v) - logrmin) / dlogr) >= k, lo, hi)
+    return edges
+
+
 def twod_mask(nbins):
     """Boolean mask keeping one half-plane of the point-symmetric nbins x nbins grid (flattened,
     rows = dy).  Same selection as two_pcf.py:309-321: all rows below the centre, plus -- for odd

@@ -2,44 +2,20 @@
 
 Mirror of /root/reference/treegp/utils.py (``vcorr``, ``xiB``, ``comp_eb``, ``comp_eb_treecorr``).  These are
 diagnostics that GPInterpolation never calls (ranked NEXT, same pair-tile shape as the
-pair-binning kernel); this round keeps them on the host, written as a row-blocked accumulation so that the
-N(N-1)/2 index pairs the reference materialises (utils.py:38-47) never exist at once.
+pair-binning kernel); the O(N^2) pair sums run on the device (`tgp_vcorr`), so the N(N-1)/2 index pairs the
+reference materialises (utils.py:38-47) never exist; everything else (E/B combination, xiB integral) is O(bins)
+host arithmetic.
 """
 import numpy as np
 
 
-def _pair_sums(x, y, dx, dy, logrmin, dlogr, bins, block=512):
-    """Per log-r bin: counts, sum log r, sum v1.v2*, sum v1 v2, sum v1 v2 exp(-2 i phi)."""
-    z = x + 1j * y
-    v = dx + 1j * dy
-    counts = np.zeros(bins)
-    s_logr = np.zeros(bins)
-    s_plus = np.zeros(bins)
-    s_z2 = np.zeros(bins, dtype=complex)
-    s_minus = np.zeros(bins, dtype=complex)
-    n = len(z)
-    for a in range(0, n, block):
-        b = min(n, a + block)
-        dr = z[None, :] - z[a:b, None]                    # z_j - z_i
-        jj = np.arange(n)[None, :] > np.arange(a, b)[:, None]
-        dr = dr[jj]
-        r2 = dr.real ** 2 + dr.imag ** 2
-        ok = r2 > 0
-        logdr = 0.5 * np.log(r2[ok])
-        k = np.floor((logdr - logrmin) / dlogr).astype(np.int64)
-        inb = (k >= 0) & (k < bins)
-        k = k[inb]
-        vi = np.broadcast_to(v[a:b, None], (b - a, n))[jj][ok][inb]
-        vj = np.broadcast_to(v[None, :], (b - a, n))[jj][ok][inb]
-        d = dr[ok][inb]
-        counts += np.bincount(k, minlength=bins)
-        s_logr += np.bincount(k, weights=logdr[inb], minlength=bins)
-        s_plus += np.bincount(k, weights=(vi * np.conj(vj)).real, minlength=bins)
-        vv = vi * vj
-        s_z2 += np.bincount(k, weights=vv.real, minlength=bins) + 1j * np.bincount(k, weights=vv.imag, minlength=bins)
-        rot = vv * np.conj(d) ** 2 / r2[ok][inb]
-        s_minus += np.bincount(k, weights=rot.real, minlength=bins) + 1j * np.bincount(k, weights=rot.imag, minlength=bins)
-    return counts, s_logr, s_plus, s_z2, s_minus
+def _pair_sums(x, y, dx, dy, logrmin, dlogr, bins):
+    """Per log-r bin: counts, sum log r, sum v1.v2*, sum v1 v2, sum v1 v2 exp(-2 i phi) over all pairs -- on the
+    device (csrc/vcorr.cu); the bins are decided by thresholds on r^2 that reproduce
+    floor((ln r - ln rmin) / dlogr) (binning.logr_thresholds)."""
+    from . import backend
+
+    return backend.vcorr_sums(x, y, dx, dy, logrmin, dlogr, bins)
 
 
 def vcorr(x, y, dx, dy, rmin=5.0 / 3600.0, rmax=1.5, dlogr=0.05, maxpts=30000):
