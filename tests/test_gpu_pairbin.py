@@ -186,3 +186,27 @@ def test_pairbin_block_forms_equal_pair_by_pair(gpu_ready, weighted, kind):
     if kind == "uniform":   # point symmetric (on the lattice displacements sit ON bin edges, where the formula is not)
         c = fast[0][0].reshape(nb, nb)
         np.testing.assert_array_equal(c, c[::-1, ::-1])
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_pairbin_log_one_bin_blocks_match_oracle(gpu_ready, weighted):
+    """Log (isotropic) bins on Hilbert-sorted input: blocks whose smallest and largest r^2 share a radial bin are
+    booked from the row / chunk sums, with only sum w r evaluated pair by pair (two_pcf.py:330-338: npairs, xi and
+    meanr of the TreeCorr Log binning).  Counts bit-exact, sums incl. sum w r to summation order."""
+    from treegp_b200 import backend
+
+    rng = np.random.default_rng(21)
+    n = 30000
+    x, y = rng.uniform(0, 100, n), rng.uniform(0, 100, n)
+    k = rng.normal(size=n)
+    w = rng.uniform(0.5, 2.0, n) if weighted else None
+    for mn, mx, nb in ((0.5, 70.0, 12), (2.0, 40.0, 5)):
+        ref = po.pairbin(x, y, k, w, mn, mx, nb, "Log")
+        backend.pairbin_stats(reset=True)
+        _check(_gpu_pairbin(x, y, k, w, mn, mx, nb, "Log", hilbert=True), ref)
+        assert backend.pairbin_stats(reset=True)["closed_form"] > 0
+        backend.set_option("pairbin_block_sums", 0)
+        try:
+            _check(_gpu_pairbin(x, y, k, w, mn, mx, nb, "Log", hilbert=True), ref)
+        finally:
+            backend.set_option("pairbin_block_sums", 1)

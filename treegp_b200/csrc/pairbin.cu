@@ -629,6 +629,12 @@ pairbin_kernel(PBParams P) {
           const double r2max = __dadd_rn(__dmul_rn(ax, ax), __dmul_rn(ay, ay));
           const double r2min = __dadd_rn(__dmul_rn(nx, nx), __dmul_rn(ny, ny));
           cls = (r2max < lo2 || r2min >= M) ? PB_OUT : PB_GENERIC;  // M = max_sep^2 for Log
+          if (BS && cls == PB_GENERIC && mychunk != ib && r2min >= lo2 && r2max < M) {
+            // every pair in range; if the smallest and the largest r^2 of the block share a bin, all pairs do
+            const int k0 = pb_bin_log(r2min, nbins, ed), k1 = pb_bin_log(r2max, nbins, ed);
+            if (k0 == k1) { cls = PB_REG_FULL; win[0] = k0; }
+            else if (k1 == k0 + 1) { cls = PB_REG_CHECK; win[0] = k0; }     // two adjacent bins: one compare per pair
+          }
           if (mychunk == ib) cls = PB_GENERIC;
         }
         if (!(iminx <= imaxx)) cls = PB_OUT;  // no live row in this warp
@@ -715,11 +721,81 @@ pairbin_kernel(PBParams P) {
         int ccls = __shfl_sync(0xffffffffu, cls, c);
         // Log bins and the diagonal block (needs j > i) go pair by pair through the generic path -- which has ONE
         // call site, at the top of the sub-block loop below, so that its code exists once in the kernel
-        const bool whole_generic = (BT != TGP_BIN_TWOD) || (sc + c) == ib;
+        const bool whole_generic = (BT != TGP_BIN_TWOD && ccls == PB_GENERIC) || (sc + c) == ib;
         const int gfirst = ((sc + c) == ib) ? lane + 1 : 0;
         int cw4[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) cw4[k] = __shfl_sync(0xffffffffu, win[k], c);
+        if (BT == TGP_BIN_LOG && !whole_generic) {
+          // Log bins, every pair of the block in range and in ONE radial bin (or in two adjacent ones): counts and
+          // the k-weighted sums of the block are products of the row and chunk sums; sum w_i w_j r needs the pairs
+          // (one square root each); with two bins one compare per pair splits off the upper bin's share.  No
+          // per-pair bin search, no atomics.
+          const int kb = cw4[0];
+          const bool two = (ccls == PB_REG_CHECK);
+          double accr = 0.0, hr = 0.0, hk = 0.0, hw = 0.0;
+          unsigned hcn = 0u;
+          if (!two) {
+#pragma unroll 4
+            for (int jj = 0; jj < jcount; ++jj) {
+              const double2 pj = cxy[jj];
+              const double dx = pj.x - xi, dy = pj.y - yi;
+              const double r = sqrt(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+              if constexpr (WEIGHTED) accr = fma(cw[jj], r, accr);
+              else accr += r;
+            }
+          } else {
+            const double tsplit = ed[kb + 1];          // r2 >= tsplit <=> bin kb + 1
+#pragma unroll 2
+            for (int jj = 0; jj < jcount; ++jj) {
+              const double2 pj = cxy[jj];
+              const double dx = pj.x - xi, dy = pj.y - yi;
+              const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+              double wr = sqrt(r2);
+              if constexpr (WEIGHTED) wr *= cw[jj];
+              accr += wr;
+              const double m = (r2 >= tsplit) ? 1.0 : 0.0;
+              hr = fma(wr, m, hr);
+              hk = fma(ck[jj], m, hk);
+              if constexpr (WEIGHTED) hw = fma(cw[jj], m, hw);
+              hcn += (r2 >= tsplit) ? 1u : 0u;
+            }
+          }
+          const double tot_r = warp_sum(live ? accr * wi : 0.0);
+          double S, Sw = 0.0;
+          if (P.boxes) {
+            S = csum.x;
+            Sw = csum.y;
+          } else {
+            S = warp_sum(ck[lane]);
+            if constexpr (WEIGHTED) Sw = warp_sum(cw[lane]);
+          }
+          double up_r = 0.0, up_k = 0.0, up_w = 0.0;
+          unsigned up_c = 0u;
+          if (two) {
+            up_r = warp_sum(live ? hr * wi : 0.0);
+            up_k = warp_sum(live ? hk * ki : 0.0);
+            if constexpr (WEIGHTED) up_w = warp_sum(live ? hw * wi : 0.0);
+            up_c = warp_sum_u(live ? hcn : 0u);
+          }
+          if (lane == 0) {       // the histogram is private to this warp
+            my_c[kb] += (unsigned)(nlive * jcount) - up_c;
+            my_s[kb] += rowK * S - up_k;
+            if constexpr (WEIGHTED) my_w[kb] += rowW * Sw - up_w;
+            my_r[kb] += tot_r - up_r;
+            if (two) {
+              my_c[kb + 1] += up_c;
+              my_s[kb + 1] += up_k;
+              if constexpr (WEIGHTED) my_w[kb + 1] += up_w;
+              my_r[kb + 1] += up_r;
+              st_1d += (unsigned)jcount;
+            } else {
+              st_closed += (unsigned)jcount;
+            }
+          }
+          __syncwarp();
+          continue;
+        }
         // a block whose window is too wide is retried as four 8-column sub-blocks
         const int nsub = (ccls == PB_GENERIC && !whole_generic) ? 4 : 1;
         int scls = ccls;
@@ -1125,7 +1201,11 @@ extern "C" int tgp_pairbin(const double* px, const double* py, const double* pk,
   } else if (twod) {
     if (weighted) TGP_PB_LAUNCH(TGP_BIN_TWOD, true, false); else TGP_PB_LAUNCH(TGP_BIN_TWOD, false, false);
   } else {
-    if (weighted) TGP_PB_LAUNCH(TGP_BIN_LOG, true, false); else TGP_PB_LAUNCH(TGP_BIN_LOG, false, false);
+    if (P.block_sums) {
+      if (weighted) TGP_PB_LAUNCH(TGP_BIN_LOG, true, true); else TGP_PB_LAUNCH(TGP_BIN_LOG, false, true);
+    } else {
+      if (weighted) TGP_PB_LAUNCH(TGP_BIN_LOG, true, false); else TGP_PB_LAUNCH(TGP_BIN_LOG, false, false);
+    }
   }
 #undef TGP_PB_LAUNCH
   TGP_LAUNCH_CHECK();

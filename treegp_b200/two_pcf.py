@@ -257,8 +257,9 @@ class two_pcf(object):
         Xd = backend.to_device(X)            # one upload of the (n, 2) array; the columns are split on the device
         px, py = Xd[:, 0].contiguous(), Xd[:, 1].contiguous()
         pk = backend.to_device(y - np.mean(y))
-        if self.anisotropic:
-            # spatially sorted input lets the kernel keep 32 x 32 pair blocks inside a 2 x 2 bin window
+        if True:
+            # spatially sorted input lets the kernel keep 32 x 32 pair blocks inside a 2 x 2 bin window (TwoD) or
+            # inside one radial bin (Log)
             order = backend.hilbert_order(px, py)
             px, py, pk = px[order].contiguous(), py[order].contiguous(), pk[order].contiguous()
             pw = None if pw is None else pw[order].contiguous()
