@@ -944,8 +944,8 @@ static LookaheadCtx& lookahead_ctx() {
 static int potrf_lookahead(double* A, int64_t n, int64_t ld, int32_t* info, cudaStream_t U, int64_t extra = 0) {
   LookaheadCtx& L = lookahead_ctx();
   cudaStream_t P = L.panel;
-  // K = 1024 trailing updates amortise the C read-modify-write better once the updates dominate (N >= 32k)
-  const int64_t OBL = (g_ob_large > 0) ? g_ob_large : (n >= 32768 ? 1024 : 512);
+  // K = 1024 trailing updates amortise the C read-modify-write better once the updates dominate (measured: K = 1024 from N ~ 14k, 2048 from ~ 28k)
+  const int64_t OBL = (g_ob_large > 0) ? g_ob_large : (n >= 28000 ? 2048 : (n >= 14000 ? 1024 : 512));
   const int64_t nblk = tgp_cdiv(n, OBL);
   cudaEvent_t e_start = L.get(0);
   TGP_CUDA(cudaEventRecord(e_start, U));
