@@ -20,7 +20,19 @@
 // chunks; warps of persistent CTAs pull items from a global counter (dynamic load balance: blocks
 // that are provably out of range are skipped, so items differ in cost).  A lane owns one row point in
 // registers; the warp stages one column chunk at a time in its private slice of shared memory and
-// reads it back as broadcasts.  Every pair of a processed block is evaluated individually.
+// reads it back as broadcasts.
+//
+// Two instantiations per bin type (template parameter BS):
+//   BS = false  the pair-by-pair kernel: every pair of every in-range block is evaluated individually
+//               (tgp_set_option("pairbin_block_sums", 0)); the 10-FP64-ops-per-pair roofline is stated for it.
+//   BS = true   (default) block forms on top of the same classification, all exact:
+//               * TwoD, block in ONE forward bin whose mirrored window is its mirror image: booked whole by the
+//                 classifying lane from the chunk sums of the pre-pass (points never loaded);
+//               * TwoD, one varying axis: rank query (bisection, 6 probes per row point) on the chunk's copy
+//                 sorted along that axis with suffix sums (pre-pass); the exact mirrored bits need only the two
+//                 neighbours of the split, a failed check hands the block back to the pair-by-pair loop;
+//               * Log, block in one radial bin or two adjacent ones: counts / k-sums from row and chunk sums,
+//                 one square root per pair for sum w r, no atomics.
 //
 // For 32 chunks at a time each lane derives the bounding box of "its" chunk and classifies the
 // block against the warp's row bounding box (FP subtraction is monotone, so the box gives exact bounds
