@@ -687,13 +687,13 @@ pairbin_kernel(PBParams P) {
         nk_ = ok ? P.pk[off + jg] * nw_ : 0.0;
       };
       auto fetch = [&](int c) {
+        const double* rec = rec0 + (size_t)PB_STRIDE * (size_t)(sc + c);
+        if (P.boxes) nsum_ = *reinterpret_cast<const double2*>(rec + 4);   // chunk sums of k w and w (pre-pass)
         if constexpr (!BS) {
           fetch_raw(c);
           return;
         }
         nkind_ = __shfl_sync(0xffffffffu, kind, c);
-        const double* rec = rec0 + (size_t)PB_STRIDE * (size_t)(sc + c);
-        if (P.boxes) nsum_ = *reinterpret_cast<const double2*>(rec + 4);
         if (nkind_ == 0) {
           fetch_raw(c);
         } else {
@@ -975,15 +975,34 @@ pairbin_kernel(PBParams P) {
               else st_1d += (unsigned)jn;
               if ((one_x && one_y) || done) continue;   // nothing can be inconsistent
             } else {
+            // all pairs of the block are in range: the unmasked sums (sum of k w, of w) are the chunk sums of the
+            // pre-pass when the whole chunk is processed, so only the masked sums are accumulated per pair
+            const bool tot_from_sums = P.boxes && nsub == 1;
+            if (tot_from_sums) {
 #pragma unroll 4
-            for (int jj = j0; jj < j0 + jn; ++jj) {
-              const double2 pj = cxy[jj];
-              const double kj = ck[jj];
-              if constexpr (WEIGHTED) {
-                const double wj = cw[jj];
-                PB_PAIR_W(A, pj.x, pj.y, kj, wj);
-              } else {
-                PB_PAIR(A, pj.x, pj.y, kj);
+              for (int jj = j0; jj < j0 + jn; ++jj) {
+                const double2 pj = cxy[jj];
+                const double kj = ck[jj];
+                if constexpr (WEIGHTED) {
+                  const double wj = cw[jj];
+                  PB_PAIR_W_NT(A, pj.x, pj.y, kj, wj);
+                } else {
+                  PB_PAIR_NT(A, pj.x, pj.y, kj);
+                }
+              }
+              A.tot += csum.x;
+              if constexpr (WEIGHTED) A.wtot += csum.y;
+            } else {
+#pragma unroll 4
+              for (int jj = j0; jj < j0 + jn; ++jj) {
+                const double2 pj = cxy[jj];
+                const double kj = ck[jj];
+                if constexpr (WEIGHTED) {
+                  const double wj = cw[jj];
+                  PB_PAIR_W(A, pj.x, pj.y, kj, wj);
+                } else {
+                  PB_PAIR(A, pj.x, pj.y, kj);
+                }
               }
             }
             A.nin += n_add;
