@@ -227,12 +227,16 @@ int tgp_pairbin_tile(void);
  * reset went through each path: host8[0] closed form (whole block in one bin and its mirror image), [1] one
  * varying axis (one compare pair per pair of points), [2] pair by pair in a 2 x 2 bin window or through the
  * generic path (the diagonal blocks are not tallied), [3] one varying axis answered by a rank query on the
- * chunk's sorted copy (6 probes per row point instead of 32 compares).  Synchronous. */
+ * chunk's sorted copy (8 probes per row point instead of 32 compares), [4] 2 x 2 bin window with the column-bit
+ * and row-bit sums from two such rank queries and only the "both bits" quadrant summed pair by pair.  Synchronous. */
 int tgp_pairbin_stats(unsigned long long* host8 /*host*/, int reset);
 
 /* Tuning knobs for experiments (not needed for normal use).  "gemm_config": -1 automatic,
  * 0 = 128x128 CTA tile (1 CTA/SM), 1 = 128x64 CTA tile (2 CTAs/SM); "potrf_fused": 0 = unfused panel chain;
- * "pairbin_block_sums": 0 = every pair of every in-range block is evaluated individually (no block forms). */
+ * "pairbin_block_sums": 0 = every pair of every in-range block is evaluated individually (no block forms);
+ * "pairbin_fast_paths": bit mask, default all on; bit 0 = short-cut dispatch of one-axis blocks that fit the open
+ * bin window, bit 1 = 2 x 2-window blocks take their marginal sums from rank queries (0 = the general paths only;
+ * results are identical either way). */
 int tgp_set_option(const char* name, int value);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */

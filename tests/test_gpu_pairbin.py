@@ -170,9 +170,19 @@ def test_pairbin_block_forms_equal_pair_by_pair(gpu_ready, weighted, kind):
     stats = backend.pairbin_stats(reset=True)
     assert stats["closed_form"] > 0
     if kind == "uniform":
-        assert stats["one_axis_sorted"] > 0
+        assert stats["one_axis_sorted"] > 0 and stats["two_axis_sorted"] > 0
     else:   # every chunk of a lattice has columns on a bin edge: the rank query hands its blocks back
         assert stats["one_axis"] > 0
+    # the same block forms through the general dispatch only (no short cuts): identical counts
+    backend.set_option("pairbin_fast_paths", 0)
+    try:
+        general = _gpu_pairbin(x, y, k, w, 0.0, mx, nb, "TwoD", hilbert=True)
+        stg = backend.pairbin_stats(reset=True)
+    finally:
+        backend.set_option("pairbin_fast_paths", 3)
+    assert stg["two_axis_sorted"] == 0 and stg["closed_form"] == stats["closed_form"]
+    np.testing.assert_array_equal(fast[0], general[0])
+    np.testing.assert_allclose(fast[2], general[2], rtol=0, atol=1e-11 * max(1.0, np.abs(general[2]).max()))
     backend.set_option("pairbin_block_sums", 0)
     try:
         slow = _gpu_pairbin(x, y, k, w, 0.0, mx, nb, "TwoD", hilbert=True)
@@ -180,6 +190,7 @@ def test_pairbin_block_forms_equal_pair_by_pair(gpu_ready, weighted, kind):
     finally:
         backend.set_option("pairbin_block_sums", 1)
     assert st0["closed_form"] == 0 and st0["one_axis_sorted"] == 0 and st0["one_axis"] == 0
+    assert st0["two_axis_sorted"] == 0
     np.testing.assert_array_equal(fast[0], slow[0])
     np.testing.assert_allclose(fast[1], slow[1], rtol=1e-12, atol=1e-12 * np.abs(slow[1]).max())
     np.testing.assert_allclose(fast[2], slow[2], rtol=0, atol=1e-11 * max(1.0, np.abs(slow[2]).max()))

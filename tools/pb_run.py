@@ -15,8 +15,15 @@ if os.environ.get("PB_SORT", "1") == "1":
     w = None if w is None else w[o].contiguous()
 off = backend.to_device(np.array([0, n]), torch.int64); mx = L * frac
 edges = backend.to_device(binning.twod_thresholds(mx, 21))
+if "PB_FAST" in os.environ:   # bit mask of the short-cut paths (default 3), see tgp_set_option
+    backend.set_option("pairbin_fast_paths", int(os.environ["PB_FAST"]))
+if "PB_BLOCK_SUMS" in os.environ:
+    backend.set_option("pairbin_block_sums", int(os.environ["PB_BLOCK_SUMS"]))
+backend.pairbin_stats(reset=True)
 for i in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); res = backend.pairbin(x, y, k, w, off, n, _cabi.BIN_TWOD, edges, 21, 0.0, mx); e1.record()
     torch.cuda.synchronize(); t = e0.elapsed_time(e1) * 1e-3
     print("n=%d t=%.4fs  %.1f Gpairs/s  in-range(x2)=%d" % (n, t, n * (n - 1) / 2 / t / 1e9, int(res[0].sum().item())), flush=True)
+st = backend.pairbin_stats(reset=True); tot = max(1, sum(st.values()))
+print("paths:", {k_: round(v / tot, 4) for k_, v in st.items()}, "checksum", int((res[0] * torch.arange(res[0].numel(), device=res[0].device).reshape(res[0].shape)).sum().item()), flush=True)

@@ -239,9 +239,8 @@ def hilbert_order(px, py):
     n = int(px.numel())
     if n == 0:
         return torch.zeros(0, dtype=torch.int64, device=px.device)
-    # one device->host transfer for the four extrema
-    ext = torch.stack([px.min(), px.max(), py.min(), py.max()]).cpu().numpy()
-    xmin, xmax, ymin, ymax = (float(v) for v in ext)
+    # two reductions and one device->host transfer for the four extrema
+    xmin, xmax, ymin, ymax = torch.stack(torch.aminmax(px) + torch.aminmax(py)).tolist()
     extent = max(xmax - xmin, ymax - ymin)
     extent = extent * (1.0 + 1e-9) if extent > 0 else 1.0
     order = int(min(16, max(1, np.ceil(np.log2(max(np.sqrt(n), 2.0))) + 1)))
@@ -255,7 +254,7 @@ def pairbin_stats(reset=True):
     """Pairs per kernel path since the last reset (see tgp_pairbin_stats); synchronises the device."""
     buf = (ctypes.c_ulonglong * 8)()
     check(_cabi.load().tgp_pairbin_stats(buf, int(bool(reset))), "tgp_pairbin_stats")
-    keys = ("closed_form", "one_axis", "pairwise", "one_axis_sorted")
+    keys = ("closed_form", "one_axis", "pairwise", "one_axis_sorted", "two_axis_sorted")
     return {k: int(buf[i]) for i, k in enumerate(keys)}
 
 

@@ -14,6 +14,7 @@ returns >= k.  Because both formulas are monotone in v the set {v >= threshold_k
 
 Also builds the half-plane mask and bin-centre coordinates of two_pcf.py:306-328.
 """
+import functools
 import math
 import struct
 import numpy as np
@@ -44,20 +45,31 @@ def _smallest_true(pred, lo, hi):
 
 
 def twod_thresholds(max_sep, nbins):
-    """edges[0] = -inf, edges[nbins] = +inf, edges[k] = smallest dx with int((dx+max_sep)/bin_size) >= k."""
-    max_sep = float(max_sep)
+    """edges[0] = -inf, edges[nbins] = +inf, edges[k] = smallest dx with int((dx+max_sep)/bin_size) >= k.
+    Memoised per (max_sep, nbins): the bisections cost ~2 ms of Python per geometry."""
+    return _twod_thresholds(float(max_sep), int(nbins)).copy()
+
+
+@functools.lru_cache(maxsize=64)
+def _twod_thresholds(max_sep, nbins):
     bin_size = 2.0 * max_sep / nbins
     edges = np.empty(nbins + 1)
     edges[0], edges[nbins] = -np.inf, np.inf
     for k in range(1, nbins):
         edges[k] = _smallest_true(lambda v: int((v + max_sep) / bin_size) >= k, -max_sep, max_sep)
+    edges.setflags(write=False)
     return edges
 
 
 def log_thresholds(min_sep, max_sep, nbins):
     """edges[k] (1 <= k < nbins) = smallest r^2 whose Log bin index is >= k; edges[0], edges[nbins] are
-    min_sep^2 and max_sep^2 (informational: the range test uses those two numbers directly)."""
-    min_sep, max_sep = float(min_sep), float(max_sep)
+    min_sep^2 and max_sep^2 (informational: the range test uses those two numbers directly).  Memoised like
+    twod_thresholds."""
+    return _log_thresholds(float(min_sep), float(max_sep), int(nbins)).copy()
+
+
+@functools.lru_cache(maxsize=64)
+def _log_thresholds(min_sep, max_sep, nbins):
     bin_size = math.log(max_sep / min_sep) / nbins
     logminsep = math.log(min_sep)
     lo, hi = min_sep * min_sep, max_sep * max_sep
@@ -66,6 +78,7 @@ def log_thresholds(min_sep, max_sep, nbins):
     for k in range(1, nbins):
         edges[k] = _smallest_true(lambda v: int((0.5 * math.log(v) - logminsep) / bin_size) >= k,
                                   lo * 0.5, hi * 2.0)
+    edges.setflags(write=False)
     return edges
 
 

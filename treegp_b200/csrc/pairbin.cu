@@ -75,11 +75,14 @@ struct PBParams {
   int32_t run;            // column chunks per work item (multiple of 32)
   int32_t ncat, nbins, nb, warps, rank, nranks;
   int32_t block_sums;     // 1: blocks whose pairs provably share a window bit use the block forms (default)
+  int32_t fast_paths;     // bit 0: short-cut dispatch of one-axis blocks that fit the open window; bit 1: 2 x 2-window
+                          // blocks with marginal sums from rank queries (default: both)
 };
 
 // Which path the pairs of all launches since the last reset took (in pairs): [0] closed form (block in one bin),
 // [1] one varying axis, pair by pair, [2] pair by pair (2 x 2 window with or without the per-pair range test,
-// generic sub-blocks), [3] one varying axis answered by a rank query on the sorted chunk.  Diagnostics.
+// generic sub-blocks), [3] one varying axis answered by a rank query on the sorted chunk, [4] 2 x 2 window with the
+// marginal sums from rank queries (one quadrant pair by pair).  Diagnostics.
 __device__ unsigned long long g_pb_stats[8];
 
 __device__ __forceinline__ int pb_bin_twod(double d, double hi, double inv_bin, int nbins,
@@ -100,6 +103,16 @@ __device__ __forceinline__ int pb_bin_twod_search(double d, int nbins, const dou
     if (d >= ed[mid]) lo = mid; else hi = mid - 1;
   }
   return lo;
+}
+
+// The same search out of line (rarely reached), and the bin of d given a guess g in [0, nbins-1]: two compares
+// when the guess is right (ed[0] = -inf, ed[nbins] = +inf, thresholds ascending: the bin is unique).
+__device__ __noinline__ int pb_bin_twod_search_cold(double d, int nbins, const double* ed) {
+  return pb_bin_twod_search(d, nbins, ed);
+}
+__device__ __forceinline__ int pb_bin_twod_guess(double d, int g, int nbins, const double* __restrict__ ed) {
+  if (d >= ed[g] && d < ed[g + 1]) return g;
+  return pb_bin_twod_search_cold(d, nbins, ed);
 }
 
 __device__ __forceinline__ int pb_bin_log(double r2, int nbins, const double* __restrict__ ed) {
@@ -323,6 +336,50 @@ __device__ __noinline__ double pb_coord_le(double xi, double t, bool& ok) {
       : "+d"(BS), "+d"(BW), "+r"(BC), "+r"(MMC)                                                     \
       : "d"(CJ), "d"(KJ), "d"(WJ), "d"(T), "d"(RT))
 
+// One pair of a 2 x 2-window block whose marginal sums (column bit, row bit) come from rank queries on the sorted
+// copies of the chunk: only the "both bits set" quadrant is accumulated per pair.
+#define PB_PAIR_Q(BS, BC, XJ, YJ, KJ, TX, TY)                                                       \
+  asm volatile(                                                                                     \
+      "{\n\t"                                                                                       \
+      ".reg .pred p, q;\n\t"                                                                        \
+      ".reg .f64 m;\n\t"                                                                            \
+      "setp.ge.f64 q, %2, %5;\n\t"                                                                  \
+      "setp.ge.and.f64 p, %3, %6, q;\n\t"                                                           \
+      "selp.f64 m, " PB_ONE ", " PB_ZERO ", p;\n\t"                                                 \
+      "fma.rn.f64 %0, %4, m, %0;\n\t"                                                               \
+      "@p add.u32 %1, %1, 1;\n\t"                                                                   \
+      "}\n"                                                                                         \
+      : "+d"(BS), "+r"(BC)                                                                          \
+      : "d"(XJ), "d"(YJ), "d"(KJ), "d"(TX), "d"(TY))
+#define PB_PAIR_Q_W(BS, BW, BC, XJ, YJ, KJ, WJ, TX, TY)                                             \
+  asm volatile(                                                                                     \
+      "{\n\t"                                                                                       \
+      ".reg .pred p, q;\n\t"                                                                        \
+      ".reg .f64 m;\n\t"                                                                            \
+      "setp.ge.f64 q, %3, %7;\n\t"                                                                  \
+      "setp.ge.and.f64 p, %4, %8, q;\n\t"                                                           \
+      "selp.f64 m, " PB_ONE ", " PB_ZERO ", p;\n\t"                                                 \
+      "fma.rn.f64 %0, %5, m, %0;\n\t"                                                               \
+      "fma.rn.f64 %1, %6, m, %1;\n\t"                                                               \
+      "@p add.u32 %2, %2, 1;\n\t"                                                                   \
+      "}\n"                                                                                         \
+      : "+d"(BS), "+d"(BW), "+r"(BC)                                                                \
+      : "d"(XJ), "d"(YJ), "d"(KJ), "d"(WJ), "d"(TX), "d"(TY))
+
+// Rank query in a chunk's sorted copy read straight from global memory (L1-resident after the first-level probes
+// p7, p15, p23 = xs[7], xs[15], xs[23], which the caller issues early): pos = number of columns with c_j < T;
+// returns whether the exact mirrored bits agree for this lane (see rank_query in the kernel).
+__device__ __forceinline__ bool pb_rank_query_g(const double* __restrict__ xs, double p7, double p15, double p23,
+                                                double T, double RT, bool live, int& pos) {
+  const int b = 8 * ((p7 < T ? 1 : 0) + (p15 < T ? 1 : 0) + (p23 < T ? 1 : 0));
+  const int sp = b + 2 * ((xs[b + 1] < T ? 1 : 0) + (xs[b + 3] < T ? 1 : 0) + (xs[b + 5] < T ? 1 : 0));
+  pos = sp + (xs[sp] < T ? 1 : 0) + (xs[sp + 1] < T ? 1 : 0);
+  return !live || ((pos == 0 || xs[pos - 1] <= RT) && (pos == PB_CHUNK || xs[pos] > RT));
+}
+__device__ __forceinline__ void pb_prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(p)));
+}
+
 enum { PB_OUT = 0, PB_REG_FULL = 1, PB_REG_CHECK = 2, PB_GENERIC = 3 };
 
 // Classification of one (row block, column block) pair from the two bounding boxes.
@@ -343,8 +400,10 @@ __device__ __forceinline__ int pb_classify_twod(double iminx, double imaxx, doub
   if (nx >= M || ny >= M || r2max < lo2) return PB_OUT;
   const int x0 = pb_bin_twod_search(dx0, nbins, ed), x1 = pb_bin_twod_search(dx1, nbins, ed);
   const int y0 = pb_bin_twod_search(dy0, nbins, ed), y1 = pb_bin_twod_search(dy1, nbins, ed);
-  const int rx0 = pb_bin_twod_search(-dx1, nbins, ed), rx1 = pb_bin_twod_search(-dx0, nbins, ed);
-  const int ry0 = pb_bin_twod_search(-dy1, nbins, ed), ry1 = pb_bin_twod_search(-dy0, nbins, ed);
+  // mirrored ends: the grid is point symmetric up to rounding of the thresholds, so bin(-d) is nbins-1-bin(d)
+  // unless d sits within a few ulp of an edge; the guess is verified against the thresholds (exact either way)
+  const int rx0 = pb_bin_twod_guess(-dx1, nbins - 1 - x1, nbins, ed), rx1 = pb_bin_twod_guess(-dx0, nbins - 1 - x0, nbins, ed);
+  const int ry0 = pb_bin_twod_guess(-dy1, nbins - 1 - y1, nbins, ed), ry1 = pb_bin_twod_guess(-dy0, nbins - 1 - y0, nbins, ed);
   if (x1 - x0 > 1 || y1 - y0 > 1 || rx1 - rx0 > 1 || ry1 - ry0 > 1) return PB_GENERIC;
   w[0] = x0 | ((x1 - x0) << 16);
   w[1] = y0 | ((y1 - y0) << 16);
@@ -520,6 +579,19 @@ pairbin_kernel(PBParams P) {
     __syncwarp();
   };
 
+  // Rank query of this lane's threshold T in the staged sorted copy of a chunk (cxy[].x = the coordinates along the
+  // varying axis in ascending order, cxy[].y = suffix sums of k w, cw[] = suffix sums of w): pos = number of columns
+  // with c_j < T, found by a 4-ary search -- 3 + 3 + 2 probes in three dependent steps instead of six dependent
+  // probes (the kernel is latency-bound here).  Returns whether the exact mirrored bits agree for this lane: columns
+  // below the split need c_j <= RT, columns from it on need c_j > RT, and in ascending order only the two
+  // neighbours of the split can fail.
+  auto rank_query = [&](double T, double RT, bool live, int& pos) -> bool {
+    const int b = 8 * ((cxy[7].x < T ? 1 : 0) + (cxy[15].x < T ? 1 : 0) + (cxy[23].x < T ? 1 : 0));
+    const int sp = b + 2 * ((cxy[b + 1].x < T ? 1 : 0) + (cxy[b + 3].x < T ? 1 : 0) + (cxy[b + 5].x < T ? 1 : 0));
+    pos = sp + (cxy[sp].x < T ? 1 : 0) + (cxy[sp + 1].x < T ? 1 : 0);          // 0 .. 32
+    return !live || ((pos == 0 || cxy[pos - 1].x <= RT) && (pos == PB_CHUNK || cxy[pos].x > RT));
+  };
+
   // per-lane open bin of the blocks booked whole at classification time (forward bin cf_bin and its mirror image)
   int cf_bin = -1;
   unsigned cf_cnt = 0u;
@@ -539,7 +611,7 @@ pairbin_kernel(PBParams P) {
   };
   const double M = P.hi, lo2 = P.lo2;
   const int R = P.run;
-  unsigned st_closed = 0, st_1d = 0, st_pw = 0, st_sorted = 0;   // column counts (x 32 rows = pairs) per path
+  unsigned st_closed = 0, st_1d = 0, st_pw = 0, st_sorted = 0, st_quad = 0;   // column counts (x 32 rows = pairs) per path
   int cur_cat = -1;
   int since_flush = 0;
   while (true) {
@@ -608,6 +680,10 @@ pairbin_kernel(PBParams P) {
       const int64_t mychunk = sc + lane;
       int cls = PB_OUT;
       int kind = 0;   // 0: raw points; 1 / 2: one-axis block answered from the x- / y-sorted copy of the chunk
+      // kind != 0 and the varying axis spans exactly two forward bins [v0, v0+1] whose mirrored window is the mirror
+      // image (the usual case): 1 | kind << 1 | x0 << 3 | y0 << 15, everything the warp needs to see whether the
+      // open window covers the block; 0 otherwise
+      int fastw = 0;
       int win[4] = {0, 0, 0, 0};
       if (mychunk < c_hi) {
         const int64_t j0g = mychunk * PB_CHUNK;
@@ -619,8 +695,8 @@ pairbin_kernel(PBParams P) {
         } else {
           const double* xs = P.px + off + j0g;
           const double* ys = P.py + off + j0g;
-#pragma unroll 8
-          for (int t = 0; t < PB_CHUNK; ++t) {
+#pragma unroll 1
+          for (int t = 0; t < PB_CHUNK; ++t) {   // only without a pre-pass (work == NULL): kept small
             if (t < cnt) {
               const double x = xs[t], y = ys[t];
               cminx = fmin(cminx, x); cmaxx = fmax(cmaxx, x);
@@ -660,6 +736,15 @@ pairbin_kernel(PBParams P) {
           const bool one_y = (win[1] >> 16) == 0 && (win[3] >> 16) == 0 && ry0 == nbins - 1 - y0;
           // exactly one varying axis: the block is answered from the chunk's points sorted along that axis
           if (P.sorted && cnt == PB_CHUNK) kind = (one_y && !one_x) ? 1 : ((one_x && !one_y) ? 2 : 0);
+          if (P.fast_paths & 1) {
+            const bool clean_x = (win[0] >> 16) == 1 && (win[2] >> 16) == 1 && rx0 == nbins - 2 - x0;
+            const bool clean_y = (win[1] >> 16) == 1 && (win[3] >> 16) == 1 && ry0 == nbins - 2 - y0;
+            if ((kind == 1 && clean_x) || (kind == 2 && clean_y)) fastw = 1 | (kind << 1) | (x0 << 3) | (y0 << 15);
+          }
+          // two bins along BOTH axes: the raw points are staged as usual (kind stays 0); field value 3
+          if ((P.fast_paths & 2) && P.sorted && cnt == PB_CHUNK && (win[0] >> 16) == 1 && (win[2] >> 16) == 1 &&
+              rx0 == nbins - 2 - x0 && (win[1] >> 16) == 1 && (win[3] >> 16) == 1 && ry0 == nbins - 2 - y0)
+            fastw = 1 | (3 << 1) | (x0 << 3) | (y0 << 15);
           if (one_x && one_y) {
             const double2 sums = *reinterpret_cast<const double2*>(rec0 + (size_t)PB_STRIDE * (size_t)mychunk + 4);
             const int o = y0 * nbins + x0;
@@ -728,6 +813,95 @@ pairbin_kernel(PBParams P) {
           if (rest) fetch(__ffs(rest) - 1);   // fetch_raw clobbered the prefetch registers
           ckind = 0;
         };
+        if constexpr (BS && BT == TGP_BIN_TWOD) {
+          // Short cut for the bulk of the one-axis blocks: a full chunk, every pair in range, two bins along the
+          // varying axis, and the OPEN window already covers it (one shuffle and four integer compares instead of
+          // the general dispatch below).  Anything else -- no open window, a window that has to move, a column
+          // within rounding of a bin edge -- falls through to the general path, which decides again from scratch.
+          const int fw = __shfl_sync(0xffffffffu, fastw, c);
+          if (fw != 0 && A.fx0 >= 0 && A.ownerI == owner) {
+            const bool vx = ((fw >> 1) & 3) == 1;
+            const int bx0 = (fw >> 3) & 0xfff, by0 = (fw >> 15) & 0xfff;
+            if (((fw >> 1) & 3) == 3) {
+              // 2 x 2 window, every pair in range, and the open window is exactly the block's: the column-bit and
+              // row-bit sums are rank queries on the x- / y-sorted copies (read from global memory: their lines
+              // are pulled in while the pair loop runs); only the "both bits" quadrant is summed pair by pair.
+              if (bx0 == A.fx0 && by0 == A.fy0) {
+                const double* srt = rec0 + (size_t)PB_STRIDE * (size_t)(sc + c) + PB_SLOT;
+                const double* srty = srt + 3 * PB_CHUNK;
+                const double x7 = srt[7], x15 = srt[15], x23 = srt[23];
+                const double y7 = srty[7], y15 = srty[15], y23 = srty[23];
+                pb_prefetch_l1(srt + PB_CHUNK + 8); pb_prefetch_l1(srt + PB_CHUNK + 24);
+                pb_prefetch_l1(srty + PB_CHUNK + 8); pb_prefetch_l1(srty + PB_CHUNK + 24);
+                if constexpr (WEIGHTED) {
+                  pb_prefetch_l1(srt + 2 * PB_CHUNK + 8); pb_prefetch_l1(srt + 2 * PB_CHUNK + 24);
+                  pb_prefetch_l1(srty + 2 * PB_CHUNK + 8); pb_prefetch_l1(srty + 2 * PB_CHUNK + 24);
+                }
+                double bsq = 0.0, bwq = 0.0;
+                unsigned bcq = 0u;
+#pragma unroll 4
+                for (int jj = 0; jj < PB_CHUNK; ++jj) {
+                  const double2 pj = cxy[jj];
+                  const double kj = ck[jj];
+                  if constexpr (WEIGHTED) { const double wj = cw[jj]; PB_PAIR_Q_W(bsq, bwq, bcq, pj.x, pj.y, kj, wj, A.Tx, A.Ty); }
+                  else PB_PAIR_Q(bsq, bcq, pj.x, pj.y, kj, A.Tx, A.Ty);
+                }
+                int posx, posy;
+                const bool okx = pb_rank_query_g(srt, x7, x15, x23, A.Tx, A.RTx, live, posx);
+                const bool oky = pb_rank_query_g(srty, y7, y15, y23, A.Ty, A.RTy, live, posy);
+                if (__all_sync(0xffffffffu, okx && oky)) {
+                  const unsigned n_add = live ? (unsigned)PB_CHUNK : 0u;
+                  A.tot += csum.x;
+                  A.nin += n_add;
+                  A.fsx += (posx < PB_CHUNK) ? srt[PB_CHUNK + posx] : 0.0;
+                  A.fsy += (posy < PB_CHUNK) ? srty[PB_CHUNK + posy] : 0.0;
+                  A.fcx += live ? (unsigned)(PB_CHUNK - posx) : 0u;
+                  A.fcy += live ? (unsigned)(PB_CHUNK - posy) : 0u;
+                  A.fsxy += bsq;
+                  A.fcxy += bcq;          // dead lanes: NaN thresholds, no compare is true
+                  if constexpr (WEIGHTED) {
+                    A.wtot += csum.y;
+                    A.fwx += (posx < PB_CHUNK) ? srt[2 * PB_CHUNK + posx] : 0.0;
+                    A.fwy += (posy < PB_CHUNK) ? srty[2 * PB_CHUNK + posy] : 0.0;
+                    A.fwxy += bwq;
+                  }
+                  st_quad += (unsigned)PB_CHUNK;
+                  continue;
+                }
+              }
+            } else {
+            const int dvar = vx ? bx0 - A.fx0 : by0 - A.fy0;      // varying axis: the window must start at its lower bin
+            const int dcon = vx ? by0 - A.fy0 : bx0 - A.fx0;      // constant axis: either bin of the window
+            if (dvar == 0 && (unsigned)dcon <= 1u) {
+              int pos;
+              const bool okl = rank_query(vx ? A.Tx : A.Ty, vx ? A.RTx : A.RTy, live, pos);
+              if (__all_sync(0xffffffffu, okl)) {
+                const unsigned n_add = live ? (unsigned)PB_CHUNK : 0u;
+                const unsigned bc = live ? (unsigned)(PB_CHUNK - pos) : 0u;
+                const double bs = (pos < PB_CHUNK) ? cxy[pos].y : 0.0;
+                double bw_ = 0.0;
+                if constexpr (WEIGHTED) bw_ = (pos < PB_CHUNK) ? cw[pos] : 0.0;
+                const bool other = dcon != 0;
+                A.tot += csum.x;
+                A.nin += n_add;
+                if constexpr (WEIGHTED) A.wtot += csum.y;
+                if (vx) {
+                  A.fsx += bs; A.fcx += bc;
+                  if constexpr (WEIGHTED) A.fwx += bw_;
+                  if (other) { A.fsy += csum.x; A.fcy += n_add; if constexpr (WEIGHTED) A.fwy += csum.y; }
+                } else {
+                  A.fsy += bs; A.fcy += bc;
+                  if constexpr (WEIGHTED) A.fwy += bw_;
+                  if (other) { A.fsx += csum.x; A.fcx += n_add; if constexpr (WEIGHTED) A.fwx += csum.y; }
+                }
+                if (other) { A.fsxy += bs; A.fcxy += bc; if constexpr (WEIGHTED) A.fwxy += bw_; }
+                st_sorted += (unsigned)PB_CHUNK;
+                continue;
+              }
+            }
+            }
+          }
+        }
         const int64_t j0g = (sc + c) * PB_CHUNK;
         const int jcount = (int)((n - j0g < PB_CHUNK) ? (n - j0g) : PB_CHUNK);
         int ccls = __shfl_sync(0xffffffffu, cls, c);
@@ -816,6 +990,7 @@ pairbin_kernel(PBParams P) {
           scls = PB_OUT;
           if (lane < 4 && lane * 8 < jcount) {
             double cminx = INFINITY, cmaxx = -INFINITY, cminy = INFINITY, cmaxy = -INFINITY;
+#pragma unroll 1
             for (int t = lane * 8; t < min(lane * 8 + 8, jcount); ++t) {
               const double2 pj = cxy[t];
               cminx = fmin(cminx, pj.x); cmaxx = fmax(cmaxx, pj.x);
@@ -914,13 +1089,8 @@ pairbin_kernel(PBParams P) {
                 // suffix sums of k w (cxy[].y) and w (cw[]).  The lane's bit "c_j >= T" is a rank query: lower
                 // bound by bisection (6 probes instead of 32 compares), count and sum read off the suffix arrays.
                 const double T = (ckind == 1) ? A.Tx : A.Ty, RT = (ckind == 1) ? A.RTx : A.RTy;
-                int pos = 0;
-#pragma unroll
-                for (int st = 16; st > 0; st >>= 1) pos += (cxy[pos + st - 1].x < T) ? st : 0;
-                pos += (cxy[pos].x < T) ? 1 : 0;           // number of columns with c_j < T, 0 .. 32
-                // exact mirrored bits: columns below pos need c_j <= RT, columns from pos on need c_j > RT; the
-                // order makes the two neighbours of the split the only ones to check
-                const bool okl = !live || ((pos == 0 || cxy[pos - 1].x <= RT) && (pos == PB_CHUNK || cxy[pos].x > RT));
+                int pos;
+                const bool okl = rank_query(T, RT, live, pos);
                 if (__all_sync(0xffffffffu, okl)) {
                   bc = live ? (unsigned)(PB_CHUNK - pos) : 0u;
                   bs = (pos < PB_CHUNK) ? cxy[pos].y : 0.0;
@@ -1047,6 +1217,7 @@ pairbin_kernel(PBParams P) {
     if (st_1d) atomicAdd(&g_pb_stats[1], 32ull * st_1d);
     if (st_pw) atomicAdd(&g_pb_stats[2], 32ull * st_pw);
     if (st_sorted) atomicAdd(&g_pb_stats[3], 32ull * st_sorted);
+    if (st_quad) atomicAdd(&g_pb_stats[4], 32ull * st_quad);
   }
 }
 
@@ -1114,6 +1285,8 @@ extern "C" int64_t tgp_pairbin_work_doubles(int64_t total_points, int32_t ncat) 
   return (int64_t)PB_STRIDE * (total_points / PB_CHUNK + (int64_t)ncat + 2);
 }
 
+static int g_pb_fast_paths = 3;   // tgp_set_option("pairbin_fast_paths", bits): see PBParams::fast_paths
+extern "C" int tgp_pairbin_set_fast_paths(int bits) { g_pb_fast_paths = bits; return TGP_OK; }
 static int g_pb_block_sums = 1;   // tgp_set_option("pairbin_block_sums", 0): every pair evaluated individually
 extern "C" int tgp_pairbin_set_block_sums(int on) { g_pb_block_sums = on ? 1 : 0; return TGP_OK; }
 
@@ -1149,6 +1322,7 @@ extern "C" int tgp_pairbin(const double* px, const double* py, const double* pk,
   P.npairs = npairs; P.sumw = sumw; P.sumwkk = sumwkk; P.sumwr = sumwr;
   P.ncat = ncat; P.nbins = nbins; P.rank = tile_rank; P.nranks = tile_nranks;
   P.block_sums = g_pb_block_sums;
+  P.fast_paths = g_pb_fast_paths;
   const bool twod = bin_type == TGP_BIN_TWOD;
   TGP_CHECK_ARG(!twod || nbins <= 4096, "nbins too large");
   P.nb = twod ? nbins * nbins : nbins;

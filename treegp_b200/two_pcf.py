@@ -225,16 +225,19 @@ class two_pcf(object):
             self.min_sep, self.max_sep, rank=rank, nranks=world)
         if world > 1:
             dist.allreduce_bins(self.group, npairs, sumw, sumwkk, sumwr)
-        sw = sumw.cpu().numpy()
+        # one device->host transfer for all bin arrays (the int64 counts ride along as raw 8-byte words)
+        parts = [sumw, sumwkk, npairs.to(torch.int64).view(torch.float64)] + ([] if sumwr is None else [sumwr])
+        host = torch.stack(parts).cpu().numpy()
+        sw, swkk = host[0], host[1]
         with np.errstate(invalid="ignore", divide="ignore"):
-            xi = np.where(sw != 0, sumwkk.cpu().numpy() / sw, 0.0)
+            xi = np.where(sw != 0, swkk / sw, 0.0)
             meanr = None
             if sumwr is not None:
                 # TreeCorr reports the nominal bin centre exp(ln min_sep + (k + 1/2) bin_size) where a bin is empty
                 bs = np.log(self.max_sep / self.min_sep) / self.nbins
                 rnom = np.exp(np.log(self.min_sep) + (np.arange(self.nbins) + 0.5) * bs)
-                meanr = np.where(sw != 0, sumwr.cpu().numpy() / sw, rnom[None, :])
-        self._last_npairs = npairs.cpu().numpy()
+                meanr = np.where(sw != 0, host[3] / sw, rnom[None, :])
+        self._last_npairs = np.ascontiguousarray(host[2]).view(np.int64)
         return xi, meanr
 
     def _assemble(self, xi, meanr):
@@ -252,17 +255,22 @@ class two_pcf(object):
         X = np.asarray(X, dtype=np.float64)
         y = np.asarray(y, dtype=np.float64)
         y_err = np.asarray(y_err, dtype=np.float64)
-        pw = None if np.sum(y_err) == 0 else backend.to_device(1.0 / y_err ** 2)
         n = len(y)
+        # The host only takes the two reductions the reference takes (sum(y_err), mean(y): two_pcf.py:291-297);
+        # the arrays go up as they are and the elementwise arithmetic (1 / y_err^2, y - mean) runs on the device
+        # -- the same IEEE operations, without three passes over host memory per call.
+        pw = None
+        if np.sum(y_err) != 0:
+            ed = backend.to_device(y_err)
+            pw = 1.0 / (ed * ed)
         Xd = backend.to_device(X)            # one upload of the (n, 2) array; the columns are split on the device
+        pk = backend.to_device(y) - float(np.mean(y))
+        # spatially sorted input lets the kernel keep 32 x 32 pair blocks inside a 2 x 2 bin window (TwoD) or
+        # inside one radial bin (Log)
         px, py = Xd[:, 0].contiguous(), Xd[:, 1].contiguous()
-        pk = backend.to_device(y - np.mean(y))
-        if True:
-            # spatially sorted input lets the kernel keep 32 x 32 pair blocks inside a 2 x 2 bin window (TwoD) or
-            # inside one radial bin (Log)
-            order = backend.hilbert_order(px, py)
-            px, py, pk = px[order].contiguous(), py[order].contiguous(), pk[order].contiguous()
-            pw = None if pw is None else pw[order].contiguous()
+        order = backend.hilbert_order(px, py)
+        px, py, pk = px[order], py[order], pk[order]
+        pw = None if pw is None else pw[order]
         xi, meanr = self._pairbin(px, py, pk, pw, backend.to_device(np.array([0, n]), torch.int64), n)
         return self._assemble(xi[0], None if meanr is None else meanr[0])
 
