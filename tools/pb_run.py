@@ -25,5 +25,8 @@ for i in range(reps):
     e0.record(); res = backend.pairbin(x, y, k, w, off, n, _cabi.BIN_TWOD, edges, 21, 0.0, mx); e1.record()
     torch.cuda.synchronize(); t = e0.elapsed_time(e1) * 1e-3
     print("n=%d t=%.4fs  %.1f Gpairs/s  in-range(x2)=%d" % (n, t, n * (n - 1) / 2 / t / 1e9, int(res[0].sum().item())), flush=True)
-st = backend.pairbin_stats(reset=True); tot = max(1, sum(st.values()))
-print("paths:", {k_: round(v / tot, 4) for k_, v in st.items()}, "checksum", int((res[0] * torch.arange(res[0].numel(), device=res[0].device).reshape(res[0].shape)).sum().item()), flush=True)
+import ctypes
+raw = (ctypes.c_ulonglong * 8)(); _cabi.check(_cabi.load().tgp_pairbin_stats(raw, 1), "stats"); raw = list(raw); tot = max(1, sum(raw[:5]))
+print("paths:", dict(zip(("closed_form", "one_axis", "pairwise", "one_axis_sorted", "two_axis_sorted"), (round(v / tot, 4) for v in raw[:5]))),
+      "one_axis_sorted via general dispatch: %.4f" % (raw[5] / tot),
+      "checksum", int((res[0] * torch.arange(res[0].numel(), device=res[0].device).reshape(res[0].shape)).sum().item()), flush=True)

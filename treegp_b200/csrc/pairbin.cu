@@ -111,6 +111,9 @@ __device__ __noinline__ int pb_bin_twod_search_cold(double d, int nbins, const d
   return pb_bin_twod_search(d, nbins, ed);
 }
 __device__ __forceinline__ int pb_bin_twod_guess(double d, int g, int nbins, const double* __restrict__ ed) {
+#ifdef PB_EXP_NOGUESS   // experiment: always search
+  return pb_bin_twod_search(d, nbins, ed);
+#endif
   if (d >= ed[g] && d < ed[g + 1]) return g;
   return pb_bin_twod_search_cold(d, nbins, ed);
 }
@@ -586,9 +589,16 @@ pairbin_kernel(PBParams P) {
   // below the split need c_j <= RT, columns from it on need c_j > RT, and in ascending order only the two
   // neighbours of the split can fail.
   auto rank_query = [&](double T, double RT, bool live, int& pos) -> bool {
+#ifdef PB_EXP_BISECT   // experiment: the six-probe bisection
+    pos = 0;
+#pragma unroll
+    for (int st = 16; st > 0; st >>= 1) pos += (cxy[pos + st - 1].x < T) ? st : 0;
+    pos += (cxy[pos].x < T) ? 1 : 0;
+#else
     const int b = 8 * ((cxy[7].x < T ? 1 : 0) + (cxy[15].x < T ? 1 : 0) + (cxy[23].x < T ? 1 : 0));
     const int sp = b + 2 * ((cxy[b + 1].x < T ? 1 : 0) + (cxy[b + 3].x < T ? 1 : 0) + (cxy[b + 5].x < T ? 1 : 0));
     pos = sp + (cxy[sp].x < T ? 1 : 0) + (cxy[sp + 1].x < T ? 1 : 0);          // 0 .. 32
+#endif
     return !live || ((pos == 0 || cxy[pos - 1].x <= RT) && (pos == PB_CHUNK || cxy[pos].x > RT));
   };
 
@@ -611,7 +621,7 @@ pairbin_kernel(PBParams P) {
   };
   const double M = P.hi, lo2 = P.lo2;
   const int R = P.run;
-  unsigned st_closed = 0, st_1d = 0, st_pw = 0, st_sorted = 0, st_quad = 0;   // column counts (x 32 rows = pairs) per path
+  unsigned st_closed = 0, st_1d = 0, st_pw = 0, st_sorted = 0, st_quad = 0, st_sorted_gen = 0;   // column counts (x 32 rows = pairs) per path
   int cur_cat = -1;
   int since_flush = 0;
   while (true) {
@@ -1141,7 +1151,7 @@ pairbin_kernel(PBParams P) {
               if (other) { A.fsxy += bs; A.fcxy += bc; if constexpr (WEIGHTED) A.fwxy += bw_; }
               if (!live) A.mmc = 0u;
               if (one_x && one_y) { if (lane == 0) st_closed += (unsigned)jn; }
-              else if (done) st_sorted += (unsigned)jn;
+              else if (done) { st_sorted += (unsigned)jn; st_sorted_gen += (unsigned)jn; }
               else st_1d += (unsigned)jn;
               if ((one_x && one_y) || done) continue;   // nothing can be inconsistent
             } else {
@@ -1218,6 +1228,7 @@ pairbin_kernel(PBParams P) {
     if (st_pw) atomicAdd(&g_pb_stats[2], 32ull * st_pw);
     if (st_sorted) atomicAdd(&g_pb_stats[3], 32ull * st_sorted);
     if (st_quad) atomicAdd(&g_pb_stats[4], 32ull * st_quad);
+    if (st_sorted_gen) atomicAdd(&g_pb_stats[5], 32ull * st_sorted_gen);   // the part of [3] through the general dispatch
   }
 }
 
