@@ -28,5 +28,4 @@ for i in range(reps):
 import ctypes
 raw = (ctypes.c_ulonglong * 8)(); _cabi.check(_cabi.load().tgp_pairbin_stats(raw, 1), "stats"); raw = list(raw); tot = max(1, sum(raw[:5]))
 print("paths:", dict(zip(("closed_form", "one_axis", "pairwise", "one_axis_sorted", "two_axis_sorted"), (round(v / tot, 4) for v in raw[:5]))),
-      "one_axis_sorted via general dispatch: %.4f" % (raw[5] / tot),
       "checksum", int((res[0] * torch.arange(res[0].numel(), device=res[0].device).reshape(res[0].shape)).sum().item()), flush=True)

@@ -621,7 +621,7 @@ pairbin_kernel(PBParams P) {
   };
   const double M = P.hi, lo2 = P.lo2;
   const int R = P.run;
-  unsigned st_closed = 0, st_1d = 0, st_pw = 0, st_sorted = 0, st_quad = 0, st_sorted_gen = 0;   // column counts (x 32 rows = pairs) per path
+  unsigned st_closed = 0, st_1d = 0, st_pw = 0, st_sorted = 0, st_quad = 0;   // column counts (x 32 rows = pairs) per path
   int cur_cat = -1;
   int since_flush = 0;
   while (true) {
@@ -1151,7 +1151,7 @@ pairbin_kernel(PBParams P) {
               if (other) { A.fsxy += bs; A.fcxy += bc; if constexpr (WEIGHTED) A.fwxy += bw_; }
               if (!live) A.mmc = 0u;
               if (one_x && one_y) { if (lane == 0) st_closed += (unsigned)jn; }
-              else if (done) { st_sorted += (unsigned)jn; st_sorted_gen += (unsigned)jn; }
+              else if (done) st_sorted += (unsigned)jn;
               else st_1d += (unsigned)jn;
               if ((one_x && one_y) || done) continue;   // nothing can be inconsistent
             } else {
@@ -1228,7 +1228,6 @@ pairbin_kernel(PBParams P) {
     if (st_pw) atomicAdd(&g_pb_stats[2], 32ull * st_pw);
     if (st_sorted) atomicAdd(&g_pb_stats[3], 32ull * st_sorted);
     if (st_quad) atomicAdd(&g_pb_stats[4], 32ull * st_quad);
-    if (st_sorted_gen) atomicAdd(&g_pb_stats[5], 32ull * st_sorted_gen);   // the part of [3] through the general dispatch
   }
 }
 
