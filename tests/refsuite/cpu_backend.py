@@ -39,7 +39,7 @@ def install():
     dev = torch.device("cpu")
     backend.require_cuda = lambda: dev
 
-    def to_device(a, dtype=F64):
+    def to_device(a, dtype=F64, non_blocking=False):
         if isinstance(a, torch.Tensor):
             return a.to(dtype=dtype).contiguous()
         return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype)

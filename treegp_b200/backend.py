@@ -27,12 +27,14 @@ def _p(t):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
-def to_device(a, dtype=F64):
-    """numpy / tensor -> contiguous CUDA tensor (no copy if already there)."""
+def to_device(a, dtype=F64, non_blocking=False):
+    """numpy / tensor -> contiguous CUDA tensor (no copy if already there).  non_blocking: the copy is only
+    enqueued on the current stream -- it overlaps host work when the source is page-locked (a pageable source
+    is staged before the call returns); the caller must not change the source before the stream has passed it."""
     dev = require_cuda()
     if isinstance(a, torch.Tensor):
-        return a.to(device=dev, dtype=dtype).contiguous()
-    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(dev)
+        return a.to(device=dev, dtype=dtype, non_blocking=non_blocking).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(dev, non_blocking=non_blocking)
 
 
 def as_points(X):

@@ -259,12 +259,14 @@ class two_pcf(object):
         # The host only takes the two reductions the reference takes (sum(y_err), mean(y): two_pcf.py:291-297);
         # the arrays go up as they are and the elementwise arithmetic (1 / y_err^2, y - mean) runs on the device
         # -- the same IEEE operations, without three passes over host memory per call.
+        # The uploads are enqueued first: from page-locked arrays they run while the host takes its reductions.
+        Xd = backend.to_device(X, non_blocking=True)   # one upload of the (n, 2) array; the columns are split on the device
+        yd = backend.to_device(y, non_blocking=True)
         pw = None
         if np.sum(y_err) != 0:
-            ed = backend.to_device(y_err)
+            ed = backend.to_device(y_err, non_blocking=True)
             pw = 1.0 / (ed * ed)
-        Xd = backend.to_device(X)            # one upload of the (n, 2) array; the columns are split on the device
-        pk = backend.to_device(y) - float(np.mean(y))
+        pk = yd - float(np.mean(y))
         # spatially sorted input lets the kernel keep 32 x 32 pair blocks inside a 2 x 2 bin window (TwoD) or
         # inside one radial bin (Log)
         px, py = Xd[:, 0].contiguous(), Xd[:, 1].contiguous()
