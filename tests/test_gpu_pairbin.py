@@ -179,7 +179,7 @@ def test_pairbin_block_forms_equal_pair_by_pair(gpu_ready, weighted, kind):
         general = _gpu_pairbin(x, y, k, w, 0.0, mx, nb, "TwoD", hilbert=True)
         stg = backend.pairbin_stats(reset=True)
     finally:
-        backend.set_option("pairbin_fast_paths", 3)
+        backend.set_option("pairbin_fast_paths", 7)
     assert stg["two_axis_sorted"] == 0 and stg["closed_form"] == stats["closed_form"]
     np.testing.assert_array_equal(fast[0], general[0])
     np.testing.assert_allclose(fast[2], general[2], rtol=0, atol=1e-11 * max(1.0, np.abs(general[2]).max()))
@@ -187,8 +187,15 @@ def test_pairbin_block_forms_equal_pair_by_pair(gpu_ready, weighted, kind):
     try:
         slow = _gpu_pairbin(x, y, k, w, 0.0, mx, nb, "TwoD", hilbert=True)
         st0 = backend.pairbin_stats(reset=True)
+        # ... and the pair-by-pair kernel with the mirrored bits evaluated for every pair (no per-block check)
+        backend.set_option("pairbin_fast_paths", 0)
+        slow_pp = _gpu_pairbin(x, y, k, w, 0.0, mx, nb, "TwoD", hilbert=True)
+        backend.pairbin_stats(reset=True)
     finally:
         backend.set_option("pairbin_block_sums", 1)
+        backend.set_option("pairbin_fast_paths", 7)
+    np.testing.assert_array_equal(slow[0], slow_pp[0])
+    np.testing.assert_allclose(slow[2], slow_pp[2], rtol=0, atol=1e-11 * max(1.0, np.abs(slow_pp[2]).max()))
     assert st0["closed_form"] == 0 and st0["one_axis_sorted"] == 0 and st0["one_axis"] == 0
     assert st0["two_axis_sorted"] == 0
     np.testing.assert_array_equal(fast[0], slow[0])

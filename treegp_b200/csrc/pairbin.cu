@@ -76,7 +76,8 @@ struct PBParams {
   int32_t ncat, nbins, nb, warps, rank, nranks;
   int32_t block_sums;     // 1: blocks whose pairs provably share a window bit use the block forms (default)
   int32_t fast_paths;     // bit 0: short-cut dispatch of one-axis blocks that fit the open window; bit 1: 2 x 2-window
-                          // blocks with marginal sums from rank queries (default: both)
+                          // blocks with marginal sums from rank queries; bit 2: pair-by-pair kernel, mirrored-bin
+                          // consistency settled per block from the sorted copies (default: all)
 };
 
 // Which path the pairs of all launches since the last reset took (in pairs): [0] closed form (block in one bin),
@@ -303,6 +304,60 @@ __device__ __noinline__ double pb_coord_le(double xi, double t, bool& ok) {
 #define PB_PAIR_W(A, XJ, YJ, KJ, WJ)                                                                \
   asm volatile(PB_PAIR_W_BODY("add.f64 %0, %0, %12;\n\tadd.f64 %4, %4, %13;\n\t") PB_PAIR_W_OPS(A, XJ, YJ, KJ, WJ))
 #define PB_PAIR_W_NT(A, XJ, YJ, KJ, WJ) asm volatile(PB_PAIR_W_BODY("") PB_PAIR_W_OPS(A, XJ, YJ, KJ, WJ))
+
+// The same pair without the mirrored bits (two compares, no mismatch counter): for blocks whose mirrored
+// consistency has been established for ALL their columns at once (pb_rank_query_g on the chunk's sorted copies).
+#define PB_PAIR_NM_BODY(TOT)                                                                        \
+      "{\n\t"                                                                                       \
+      ".reg .pred px, py, pxy;\n\t"                                                                 \
+      ".reg .f64 m0, m1, m2;\n\t"                                                                   \
+      "setp.ge.f64 px, %8, %10;\n\t"                                                                \
+      "setp.ge.f64 py, %9, %11;\n\t"                                                                \
+      "and.pred pxy, px, py;\n\t"                                                                   \
+      "selp.f64 m0, " PB_ONE ", " PB_ZERO ", px;\n\t"                                               \
+      "selp.f64 m1, " PB_ONE ", " PB_ZERO ", py;\n\t"                                               \
+      "selp.f64 m2, " PB_ONE ", " PB_ZERO ", pxy;\n\t"                                              \
+      TOT                                                                                           \
+      "fma.rn.f64 %1, %7, m0, %1;\n\t"                                                              \
+      "fma.rn.f64 %2, %7, m1, %2;\n\t"                                                              \
+      "fma.rn.f64 %3, %7, m2, %3;\n\t"                                                              \
+      "@px add.u32 %4, %4, 1;\n\t"                                                                  \
+      "@py add.u32 %5, %5, 1;\n\t"                                                                  \
+      "@pxy add.u32 %6, %6, 1;\n\t"                                                                 \
+      "}\n"
+#define PB_PAIR_NM_OPS(A, XJ, YJ, KJ)                                                               \
+      : "+d"(A.tot), "+d"(A.fsx), "+d"(A.fsy), "+d"(A.fsxy), "+r"(A.fcx), "+r"(A.fcy), "+r"(A.fcxy) \
+      : "d"(KJ), "d"(XJ), "d"(YJ), "d"(A.Tx), "d"(A.Ty)
+#define PB_PAIR_NM(A, XJ, YJ, KJ) asm volatile(PB_PAIR_NM_BODY("add.f64 %0, %0, %7;\n\t") PB_PAIR_NM_OPS(A, XJ, YJ, KJ))
+#define PB_PAIR_NM_NT(A, XJ, YJ, KJ) asm volatile(PB_PAIR_NM_BODY("") PB_PAIR_NM_OPS(A, XJ, YJ, KJ))
+#define PB_PAIR_NM_W_BODY(TOT)                                                                      \
+      "{\n\t"                                                                                       \
+      ".reg .pred px, py, pxy;\n\t"                                                                 \
+      ".reg .f64 m0, m1, m2;\n\t"                                                                   \
+      "setp.ge.f64 px, %13, %15;\n\t"                                                               \
+      "setp.ge.f64 py, %14, %16;\n\t"                                                               \
+      "and.pred pxy, px, py;\n\t"                                                                   \
+      "selp.f64 m0, " PB_ONE ", " PB_ZERO ", px;\n\t"                                               \
+      "selp.f64 m1, " PB_ONE ", " PB_ZERO ", py;\n\t"                                               \
+      "selp.f64 m2, " PB_ONE ", " PB_ZERO ", pxy;\n\t"                                              \
+      TOT                                                                                           \
+      "fma.rn.f64 %1, %11, m0, %1;\n\t"                                                             \
+      "fma.rn.f64 %2, %11, m1, %2;\n\t"                                                             \
+      "fma.rn.f64 %3, %11, m2, %3;\n\t"                                                             \
+      "fma.rn.f64 %5, %12, m0, %5;\n\t"                                                             \
+      "fma.rn.f64 %6, %12, m1, %6;\n\t"                                                             \
+      "fma.rn.f64 %7, %12, m2, %7;\n\t"                                                             \
+      "@px add.u32 %8, %8, 1;\n\t"                                                                  \
+      "@py add.u32 %9, %9, 1;\n\t"                                                                  \
+      "@pxy add.u32 %10, %10, 1;\n\t"                                                               \
+      "}\n"
+#define PB_PAIR_NM_W_OPS(A, XJ, YJ, KJ, WJ)                                                         \
+      : "+d"(A.tot), "+d"(A.fsx), "+d"(A.fsy), "+d"(A.fsxy), "+d"(A.wtot), "+d"(A.fwx), "+d"(A.fwy), \
+        "+d"(A.fwxy), "+r"(A.fcx), "+r"(A.fcy), "+r"(A.fcxy)                                        \
+      : "d"(KJ), "d"(WJ), "d"(XJ), "d"(YJ), "d"(A.Tx), "d"(A.Ty)
+#define PB_PAIR_NM_W(A, XJ, YJ, KJ, WJ)                                                             \
+  asm volatile(PB_PAIR_NM_W_BODY("add.f64 %0, %0, %11;\n\tadd.f64 %4, %4, %12;\n\t") PB_PAIR_NM_W_OPS(A, XJ, YJ, KJ, WJ))
+#define PB_PAIR_NM_W_NT(A, XJ, YJ, KJ, WJ) asm volatile(PB_PAIR_NM_W_BODY("") PB_PAIR_NM_W_OPS(A, XJ, YJ, KJ, WJ))
 
 // One pair of a block whose displacements span two bins along ONE axis only (the other window bit is the same
 // for every pair of the block): CJ = the column point's coordinate on the varying axis, T / RT the lane's
@@ -786,6 +841,13 @@ pairbin_kernel(PBParams P) {
         if (P.boxes) nsum_ = *reinterpret_cast<const double2*>(rec + 4);   // chunk sums of k w and w (pre-pass)
         if constexpr (!BS) {
           fetch_raw(c);
+          if (BT == TGP_BIN_TWOD && P.sorted && (P.fast_paths & 4)) {
+            // the sorted coordinates of the chunk (x: doubles 0..31, y: 96..127 of the sorted record) on their way
+            // to L1 for the mirrored-consistency queries of the next block
+            const double* sp = rec + PB_SLOT;
+            pb_prefetch_l1(sp); pb_prefetch_l1(sp + 16); pb_prefetch_l1(sp + 31);
+            pb_prefetch_l1(sp + 3 * PB_CHUNK); pb_prefetch_l1(sp + 3 * PB_CHUNK + 16); pb_prefetch_l1(sp + 3 * PB_CHUNK + 31);
+          }
           return;
         }
         nkind_ = __shfl_sync(0xffffffffu, kind, c);
@@ -1071,6 +1133,21 @@ pairbin_kernel(PBParams P) {
             if (!whole_generic) st_pw += (unsigned)jn;
             continue;
           }
+          // Pair-by-pair kernel: the mirrored-bin consistency of ALL pairs of the block is settled once, by two
+          // rank queries per row point on the chunk's sorted copies (a pair is inconsistent iff its column
+          // coordinate falls between the lane's forward and mirrored thresholds, and in ascending order only the two
+          // neighbours of the split can); the pair loop then evaluates the forward bits only.
+          bool nm = false;
+          if constexpr (!BS && BT == TGP_BIN_TWOD) {
+            if (P.sorted && nsub == 1 && jcount == PB_CHUNK && (P.fast_paths & 4)) {
+              const double* srt = rec0 + (size_t)PB_STRIDE * (size_t)(sc + c) + PB_SLOT;
+              const double* srty = srt + 3 * PB_CHUNK;
+              int posx, posy;
+              const bool okx = pb_rank_query_g(srt, srt[7], srt[15], srt[23], A.Tx, A.RTx, live, posx);
+              const bool oky = pb_rank_query_g(srty, srty[7], srty[15], srty[23], A.Ty, A.RTy, live, posy);
+              nm = __all_sync(0xffffffffu, okx && oky);
+            }
+          }
           if (bcls == PB_REG_FULL) {
             // Every pair of the block is in range.  How many bins do its displacements span?  one_x: all dx in ONE
             // forward bin, all -dx in ONE mirrored bin, and that bin is the mirror image (the usual case: bins are
@@ -1158,7 +1235,21 @@ pairbin_kernel(PBParams P) {
             // all pairs of the block are in range: the unmasked sums (sum of k w, of w) are the chunk sums of the
             // pre-pass when the whole chunk is processed, so only the masked sums are accumulated per pair
             const bool tot_from_sums = P.boxes && nsub == 1;
-            if (tot_from_sums) {
+            if (!BS && tot_from_sums && nm) {
+#pragma unroll 4
+              for (int jj = j0; jj < j0 + jn; ++jj) {
+                const double2 pj = cxy[jj];
+                const double kj = ck[jj];
+                if constexpr (WEIGHTED) {
+                  const double wj = cw[jj];
+                  PB_PAIR_NM_W_NT(A, pj.x, pj.y, kj, wj);
+                } else {
+                  PB_PAIR_NM_NT(A, pj.x, pj.y, kj);
+                }
+              }
+              A.tot += csum.x;
+              if constexpr (WEIGHTED) A.wtot += csum.y;
+            } else if (tot_from_sums) {
 #pragma unroll 4
               for (int jj = j0; jj < j0 + jn; ++jj) {
                 const double2 pj = cxy[jj];
@@ -1188,6 +1279,25 @@ pairbin_kernel(PBParams P) {
             A.nin += n_add;
             if (!live) A.mmc = 0u;  // dead lanes (NaN coordinates) compare false everywhere: not a mismatch
             st_pw += (unsigned)jn;
+            }
+          } else if (!BS && nm) {
+            st_pw += (unsigned)jn;
+#pragma unroll 2
+            for (int jj = j0; jj < j0 + jn; ++jj) {
+              const double2 pj = cxy[jj];
+              const double dx = pj.x - xi, dy = pj.y - yi;
+              const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+              const bool ok = r2 >= lo2 && fabs(dx) < M && fabs(dy) < M;  // false for dead lanes (NaN)
+              if (ok) {
+                const double kj = ck[jj];
+                if constexpr (WEIGHTED) {
+                  const double wj = cw[jj];
+                  PB_PAIR_NM_W(A, pj.x, pj.y, kj, wj);
+                } else {
+                  PB_PAIR_NM(A, pj.x, pj.y, kj);
+                }
+                A.nin += 1u;
+              }
             }
           } else {
             st_pw += (unsigned)jn;
@@ -1295,7 +1405,7 @@ extern "C" int64_t tgp_pairbin_work_doubles(int64_t total_points, int32_t ncat) 
   return (int64_t)PB_STRIDE * (total_points / PB_CHUNK + (int64_t)ncat + 2);
 }
 
-static int g_pb_fast_paths = 3;   // tgp_set_option("pairbin_fast_paths", bits): see PBParams::fast_paths
+static int g_pb_fast_paths = 7;   // tgp_set_option("pairbin_fast_paths", bits): see PBParams::fast_paths
 extern "C" int tgp_pairbin_set_fast_paths(int bits) { g_pb_fast_paths = bits; return TGP_OK; }
 static int g_pb_block_sums = 1;   // tgp_set_option("pairbin_block_sums", 0): every pair evaluated individually
 extern "C" int tgp_pairbin_set_block_sums(int on) { g_pb_block_sums = on ? 1 : 0; return TGP_OK; }
