@@ -236,8 +236,8 @@ int tgp_pairbin_stats(unsigned long long* host8 /*host*/, int reset);
  * "pairbin_block_sums": 0 = every pair of every in-range block is evaluated individually (no block forms);
  * "pairbin_fast_paths": bit mask, default all on; bit 0 = short-cut dispatch of one-axis blocks that fit the open
  * bin window, bit 1 = 2 x 2-window blocks take their marginal sums from rank queries, bit 2 = the pair-by-pair kernel
- * ("pairbin_block_sums" 0) settles the mirrored-bin consistency of a block once from the sorted chunk copies instead
- * of per pair (0 = the general paths only; results are identical either way). */
+ * ("pairbin_block_sums" 0) skips the per-pair mirrored-bin check in blocks whose bounding boxes prove it
+ * (0 = the general paths only; results are identical either way). */
 int tgp_set_option(const char* name, int value);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */

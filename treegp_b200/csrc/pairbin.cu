@@ -76,8 +76,8 @@ struct PBParams {
   int32_t ncat, nbins, nb, warps, rank, nranks;
   int32_t block_sums;     // 1: blocks whose pairs provably share a window bit use the block forms (default)
   int32_t fast_paths;     // bit 0: short-cut dispatch of one-axis blocks that fit the open window; bit 1: 2 x 2-window
-                          // blocks with marginal sums from rank queries; bit 2: pair-by-pair kernel, mirrored-bin
-                          // consistency settled per block from the sorted copies (default: all)
+                          // blocks with marginal sums from rank queries; bit 2: pair-by-pair kernel, no mirrored bits
+                          // per pair in blocks that provably sit in one bin and its mirror image (default: all)
 };
 
 // Which path the pairs of all launches since the last reset took (in pairs): [0] closed form (block in one bin),
@@ -305,8 +305,8 @@ __device__ __noinline__ double pb_coord_le(double xi, double t, bool& ok) {
   asm volatile(PB_PAIR_W_BODY("add.f64 %0, %0, %12;\n\tadd.f64 %4, %4, %13;\n\t") PB_PAIR_W_OPS(A, XJ, YJ, KJ, WJ))
 #define PB_PAIR_W_NT(A, XJ, YJ, KJ, WJ) asm volatile(PB_PAIR_W_BODY("") PB_PAIR_W_OPS(A, XJ, YJ, KJ, WJ))
 
-// The same pair without the mirrored bits (two compares, no mismatch counter): for blocks whose mirrored
-// consistency has been established for ALL their columns at once (pb_rank_query_g on the chunk's sorted copies).
+// The same pair without the mirrored bits (no mismatch counter): for blocks whose bounding boxes prove that the
+// mirrored bin of every pair is the mirror image of its forward bin.
 #define PB_PAIR_NM_BODY(TOT)                                                                        \
       "{\n\t"                                                                                       \
       ".reg .pred px, py, pxy;\n\t"                                                                 \
@@ -841,13 +841,6 @@ pairbin_kernel(PBParams P) {
         if (P.boxes) nsum_ = *reinterpret_cast<const double2*>(rec + 4);   // chunk sums of k w and w (pre-pass)
         if constexpr (!BS) {
           fetch_raw(c);
-          if (BT == TGP_BIN_TWOD && P.sorted && (P.fast_paths & 4)) {
-            // the sorted coordinates of the chunk (x: doubles 0..31, y: 96..127 of the sorted record) on their way
-            // to L1 for the mirrored-consistency queries of the next block
-            const double* sp = rec + PB_SLOT;
-            pb_prefetch_l1(sp); pb_prefetch_l1(sp + 16); pb_prefetch_l1(sp + 31);
-            pb_prefetch_l1(sp + 3 * PB_CHUNK); pb_prefetch_l1(sp + 3 * PB_CHUNK + 16); pb_prefetch_l1(sp + 3 * PB_CHUNK + 31);
-          }
           return;
         }
         nkind_ = __shfl_sync(0xffffffffu, kind, c);
@@ -1133,21 +1126,6 @@ pairbin_kernel(PBParams P) {
             if (!whole_generic) st_pw += (unsigned)jn;
             continue;
           }
-          // Pair-by-pair kernel: the mirrored-bin consistency of ALL pairs of the block is settled once, by two
-          // rank queries per row point on the chunk's sorted copies (a pair is inconsistent iff its column
-          // coordinate falls between the lane's forward and mirrored thresholds, and in ascending order only the two
-          // neighbours of the split can); the pair loop then evaluates the forward bits only.
-          bool nm = false;
-          if constexpr (!BS && BT == TGP_BIN_TWOD) {
-            if (P.sorted && nsub == 1 && jcount == PB_CHUNK && (P.fast_paths & 4)) {
-              const double* srt = rec0 + (size_t)PB_STRIDE * (size_t)(sc + c) + PB_SLOT;
-              const double* srty = srt + 3 * PB_CHUNK;
-              int posx, posy;
-              const bool okx = pb_rank_query_g(srt, srt[7], srt[15], srt[23], A.Tx, A.RTx, live, posx);
-              const bool oky = pb_rank_query_g(srty, srty[7], srty[15], srty[23], A.Ty, A.RTy, live, posy);
-              nm = __all_sync(0xffffffffu, okx && oky);
-            }
-          }
           if (bcls == PB_REG_FULL) {
             // Every pair of the block is in range.  How many bins do its displacements span?  one_x: all dx in ONE
             // forward bin, all -dx in ONE mirrored bin, and that bin is the mirror image (the usual case: bins are
@@ -1156,6 +1134,12 @@ pairbin_kernel(PBParams P) {
             const bool whole = BS && (nsub == 1);
             const bool one_x = whole && x1 == x0 && rx1 == rx0 && rx0 == nbins - 1 - x0;
             const bool one_y = whole && y1 == y0 && ry1 == ry0 && ry0 == nbins - 1 - y0;
+            // Pair-by-pair kernel: when the bounding boxes put the whole block into ONE forward bin per axis and its
+            // mirrored window is that bin's mirror image, the mirrored bits of every pair are the complement of the
+            // forward bits by construction; the pair loop then evaluates the forward bits only (every pair is still
+            // binned individually).
+            const bool nm = !BS && (P.fast_paths & 4) && x1 == x0 && rx1 == rx0 && rx0 == nbins - 1 - x0 &&
+                            y1 == y0 && ry1 == ry0 && ry0 == nbins - 1 - y0;
             const unsigned n_add = live ? (unsigned)jn : 0u;
             if (one_x || one_y) {
               // chunk sums of the column values (dead columns were staged as zero)
@@ -1279,25 +1263,6 @@ pairbin_kernel(PBParams P) {
             A.nin += n_add;
             if (!live) A.mmc = 0u;  // dead lanes (NaN coordinates) compare false everywhere: not a mismatch
             st_pw += (unsigned)jn;
-            }
-          } else if (!BS && nm) {
-            st_pw += (unsigned)jn;
-#pragma unroll 2
-            for (int jj = j0; jj < j0 + jn; ++jj) {
-              const double2 pj = cxy[jj];
-              const double dx = pj.x - xi, dy = pj.y - yi;
-              const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-              const bool ok = r2 >= lo2 && fabs(dx) < M && fabs(dy) < M;  // false for dead lanes (NaN)
-              if (ok) {
-                const double kj = ck[jj];
-                if constexpr (WEIGHTED) {
-                  const double wj = cw[jj];
-                  PB_PAIR_NM_W(A, pj.x, pj.y, kj, wj);
-                } else {
-                  PB_PAIR_NM(A, pj.x, pj.y, kj);
-                }
-                A.nin += 1u;
-              }
             }
           } else {
             st_pw += (unsigned)jn;
