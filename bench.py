@@ -319,8 +319,12 @@ def run_ours(args):
                         "figure describes the pair-by-pair kernel (block forms off, every pair through the compare / "
                         "masked-FMA loop), which is what achieved / frac are measured on here, live, on the same data "
                         "(ms_per_launch).  The TIMED kernel (value, ms_per_step) books blocks of 32 x 32 pairs that "
-                        "provably fall into one bin from pre-computed chunk sums and answers one-axis blocks by a rank "
-                        "query on sorted chunks: identical counts, see timed_kernel",
+                        "provably fall into one bin from pre-computed chunk sums, answers one-axis blocks by a rank "
+                        "query on sorted chunks and takes the marginal sums of 2 x 2-window blocks from two such "
+                        "queries: identical counts, see timed_kernel.  In the pair-by-pair kernel every pair's forward "
+                        "bin bits are evaluated individually; the mirrored-entry cross-check is evaluated per pair "
+                        "except in blocks whose bounding boxes prove it (one bin per axis, mirrored window = its "
+                        "mirror image)",
                 "ms_per_launch": pp_s * 1e3, "pairs_per_s": my_pairs * world / pp_s,
                 "timed_kernel": {"kernel": "pairbin_kernel<TwoD, unweighted, block forms>", "ms_per_launch": kern_s * 1e3,
                                  "speedup_over_pair_by_pair": pp_s / kern_s, "path_fractions": frac_paths,
