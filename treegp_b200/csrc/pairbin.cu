@@ -25,12 +25,17 @@
 // Two instantiations per bin type (template parameter BS):
 //   BS = false  the pair-by-pair kernel: every pair of every in-range block is evaluated individually
 //               (tgp_set_option("pairbin_block_sums", 0)); the 10-FP64-ops-per-pair roofline is stated for it.
+//               Blocks that provably sit in one bin per axis whose mirrored window is the mirror image skip the
+//               per-pair mirrored bits (the forward bits are still evaluated for every pair).
 //   BS = true   (default) block forms on top of the same classification, all exact:
 //               * TwoD, block in ONE forward bin whose mirrored window is its mirror image: booked whole by the
 //                 classifying lane from the chunk sums of the pre-pass (points never loaded);
-//               * TwoD, one varying axis: rank query (bisection, 6 probes per row point) on the chunk's copy
+//               * TwoD, one varying axis: rank query (4-ary search, 8 probes per row point) on the chunk's copy
 //                 sorted along that axis with suffix sums (pre-pass); the exact mirrored bits need only the two
-//                 neighbours of the split, a failed check hands the block back to the pair-by-pair loop;
+//                 neighbours of the split, a failed check hands the block back to the pair-by-pair loop.  Blocks
+//                 that the open window already covers take a short cut in front of the general dispatch;
+//               * TwoD, two bins along both axes: column-bit and row-bit sums from two rank queries on the x- and
+//                 y-sorted copies, only the "both bits" quadrant summed per pair;
 //               * Log, block in one radial bin or two adjacent ones: counts / k-sums from row and chunk sums,
 //                 one square root per pair for sum w r, no atomics.
 //
