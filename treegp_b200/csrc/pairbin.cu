@@ -54,6 +54,7 @@
 // catalogue.  Multi-GPU: items are dealt round-robin to ranks; the caller all-reduces the bin sums.
 #include <float.h>
 #include <math.h>
+#include <atomic>
 #include "tgp_common.cuh"
 
 constexpr int PB_CHUNK = 32;          // column points per block (= row points per warp)
@@ -1479,10 +1480,10 @@ extern "C" int tgp_pairbin(const double* px, const double* py, const double* pk,
     P.sorted = work + PB_SLOT;
   }
 
-  static unsigned launch_seq = 0;
+  static std::atomic<unsigned> launch_seq{0};   // host threads launching on different streams get different slots
   void* cbase = nullptr;
   TGP_CUDA(cudaGetSymbolAddress(&cbase, g_pb_counters));
-  P.counter = reinterpret_cast<unsigned long long*>(cbase) + (launch_seq++ % PB_COUNTER_SLOTS);
+  P.counter = reinterpret_cast<unsigned long long*>(cbase) + (launch_seq.fetch_add(1u) % PB_COUNTER_SLOTS);
   TGP_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), st));
 
 #define TGP_PB_LAUNCH(BT, W, BS)                                                                          \
