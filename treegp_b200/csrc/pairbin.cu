@@ -518,6 +518,19 @@ pairbin_kernel(PBParams P) {
   A.zero();
   A.fx0 = -1;
   A.ownerI = -1;
+  // TwoD: the warp histogram holds the FORWARD entries only; every booking is point symmetric, so flush_hist adds
+  // the mirror image (bin nb-1-b) when it writes a bin out.  The rare pair whose exact mirrored bin is not the
+  // mirror image of its forward bin is corrected directly in global memory: -1 at the assumed bin, +1 at the exact.
+  int cur_cat = -1;
+  auto move_mirrored = [&](int assumed, int exact, double kk, double ww) {
+    const size_t g = (size_t)cur_cat * nb;
+    atomicAdd(reinterpret_cast<unsigned long long*>(P.npairs) + g + assumed, ~0ull);   // -1 (mod 2^64)
+    atomicAdd(reinterpret_cast<unsigned long long*>(P.npairs) + g + exact, 1ull);
+    atomicAdd(P.sumwkk + g + assumed, -kk);
+    atomicAdd(P.sumwkk + g + exact, kk);
+    atomicAdd(P.sumw + g + assumed, -ww);
+    atomicAdd(P.sumw + g + exact, ww);
+  };
   // Move the lane registers of the open window into the warp's shared histogram.
   auto flush_regs = [&]() {
     if (BT != TGP_BIN_TWOD) return;
@@ -541,13 +554,10 @@ pairbin_kernel(PBParams P) {
         for (int b = 0; b < 4; ++b) {
           if (fc[b]) {  // a non-empty bin is always inside the grid; the histogram is private to this warp
             const int bx = A.fx0 + (b & 1), by = A.fy0 + (b >> 1);
-            const int o = by * nbins + bx;                                 // forward entry
-            const int om = (nbins - 1 - by) * nbins + (nbins - 1 - bx);    // mirrored entry
+            const int o = by * nbins + bx;       // forward entry; flush_hist adds the mirror image
             my_c[o] += fc[b];
             my_s[o] += fs[b];
-            my_c[om] += fc[b];
-            my_s[om] += fs[b];
-            if constexpr (WEIGHTED) { my_w[o] += fw[b]; my_w[om] += fw[b]; }
+            if constexpr (WEIGHTED) my_w[o] += fw[b];
           }
         }
       }
@@ -573,16 +583,9 @@ pairbin_kernel(PBParams P) {
         if ((px != qx) && (py != qy)) continue;  // consistent
         const int assumed = (nbins - 1 - (A.fy0 + (py ? 1 : 0))) * nbins + (nbins - 1 - (A.fx0 + (px ? 1 : 0)));
         const int exact = (ry0 + (qy ? 1 : 0)) * nbins + (rx0 + (qx ? 1 : 0));
-        const double kk = ki * ck[jj];
-        atomicAdd(my_c + assumed, 0xffffffffu);  // -1 (mod 2^32); the +1 arrives with the register flush
-        atomicAdd(my_c + exact, 1u);
-        atomicAdd(my_s + assumed, -kk);
-        atomicAdd(my_s + exact, kk);
-        if constexpr (WEIGHTED) {
-          const double ww = wi * cw[jj];
-          atomicAdd(my_w + assumed, -ww);
-          atomicAdd(my_w + exact, ww);
-        }
+        double ww = 1.0;
+        if constexpr (WEIGHTED) ww = wi * cw[jj];
+        move_mirrored(assumed, exact, ki * ck[jj], ww);
       }
       A.mmc = 0u;
     }
@@ -592,18 +595,37 @@ pairbin_kernel(PBParams P) {
   auto flush_hist = [&](int cat) {   // the window registers were flushed at the end of the last item
     __syncwarp();
     if (cat >= 0) {
-      for (int b = lane; b < nb; b += 32) {
-        const unsigned c = my_c[b];
-        if (c) {
-          const size_t o = (size_t)cat * nb + b;
-          atomicAdd(reinterpret_cast<unsigned long long*>(P.npairs) + o, (unsigned long long)c);
-          atomicAdd(P.sumwkk + o, my_s[b]);
-          atomicAdd(P.sumw + o, WEIGHTED ? my_w[b] : (double)c);
-          if (BT == TGP_BIN_LOG && P.sumwr) atomicAdd(P.sumwr + o, my_r[b]);
+      if (BT == TGP_BIN_TWOD) {
+        for (int b = lane; b < nb; b += 32) {       // forward entries of bin b + those of its mirror image
+          const int bm = nb - 1 - b;
+          const unsigned long long c = (unsigned long long)my_c[b] + (unsigned long long)my_c[bm];
+          if (c) {
+            const size_t o = (size_t)cat * nb + b;
+            atomicAdd(reinterpret_cast<unsigned long long*>(P.npairs) + o, c);
+            atomicAdd(P.sumwkk + o, my_s[b] + my_s[bm]);
+            atomicAdd(P.sumw + o, WEIGHTED ? my_w[b] + my_w[bm] : (double)c);
+          }
+        }
+        __syncwarp();   // every bin is read twice: clear after all reads
+        for (int b = lane; b < nb; b += 32) {
           my_c[b] = 0u;
           my_s[b] = 0.0;
           if constexpr (WEIGHTED) my_w[b] = 0.0;
-          if (BT == TGP_BIN_LOG) my_r[b] = 0.0;
+        }
+      } else {
+        for (int b = lane; b < nb; b += 32) {
+          const unsigned c = my_c[b];
+          if (c) {
+            const size_t o = (size_t)cat * nb + b;
+            atomicAdd(reinterpret_cast<unsigned long long*>(P.npairs) + o, (unsigned long long)c);
+            atomicAdd(P.sumwkk + o, my_s[b]);
+            atomicAdd(P.sumw + o, WEIGHTED ? my_w[b] : (double)c);
+            if (P.sumwr) atomicAdd(P.sumwr + o, my_r[b]);
+            my_c[b] = 0u;
+            my_s[b] = 0.0;
+            if constexpr (WEIGHTED) my_w[b] = 0.0;
+            my_r[b] = 0.0;
+          }
         }
       }
     }
@@ -623,9 +645,12 @@ pairbin_kernel(PBParams P) {
             const int b1 = pb_bin_twod(dy, P.hi, P.inv_bin, nbins, ed) * nbins + pb_bin_twod(dx, P.hi, P.inv_bin, nbins, ed);
             const int b2 = pb_bin_twod(-dy, P.hi, P.inv_bin, nbins, ed) * nbins + pb_bin_twod(-dx, P.hi, P.inv_bin, nbins, ed);
             const double kk = ki * ck[jj];
-            atomicAdd(my_c + b1, 1u); atomicAdd(my_c + b2, 1u);
-            atomicAdd(my_s + b1, kk); atomicAdd(my_s + b2, kk);
-            if constexpr (WEIGHTED) { const double ww = wi * cw[jj]; atomicAdd(my_w + b1, ww); atomicAdd(my_w + b2, ww); }
+            double ww = 1.0;
+            if constexpr (WEIGHTED) ww = wi * cw[jj];
+            atomicAdd(my_c + b1, 1u);
+            atomicAdd(my_s + b1, kk);
+            if constexpr (WEIGHTED) atomicAdd(my_w + b1, ww);
+            if (b2 != nb - 1 - b1) move_mirrored(nb - 1 - b1, b2, kk, ww);   // displacement on a bin edge
           }
         } else {
           if (r2 >= P.lo2 && r2 < P.hi) {
@@ -669,12 +694,9 @@ pairbin_kernel(PBParams P) {
   double cf_s = 0.0, cf_w = 0.0;
   auto cf_spill = [&]() {
     if (cf_bin >= 0 && cf_cnt) {
-      const int om = nb - 1 - cf_bin;      // (nbins-1-y) * nbins + (nbins-1-x)
-      atomicAdd(my_c + cf_bin, cf_cnt);
-      atomicAdd(my_c + om, cf_cnt);
+      atomicAdd(my_c + cf_bin, cf_cnt);    // forward entry; the mirror image is added by flush_hist
       atomicAdd(my_s + cf_bin, cf_s);
-      atomicAdd(my_s + om, cf_s);
-      if constexpr (WEIGHTED) { atomicAdd(my_w + cf_bin, cf_w); atomicAdd(my_w + om, cf_w); }
+      if constexpr (WEIGHTED) atomicAdd(my_w + cf_bin, cf_w);
     }
     cf_cnt = 0u;
     cf_s = 0.0;
@@ -683,7 +705,6 @@ pairbin_kernel(PBParams P) {
   const double M = P.hi, lo2 = P.lo2;
   const int R = P.run;
   unsigned st_closed = 0, st_1d = 0, st_pw = 0, st_sorted = 0, st_quad = 0;   // column counts (x 32 rows = pairs) per path
-  int cur_cat = -1;
   int since_flush = 0;
   while (true) {
     // ---- next work item for this warp ----
