@@ -30,6 +30,23 @@ def test_twod_thresholds_reproduce_the_formula(max_sep, nbins):
     np.testing.assert_array_equal(f, g)
 
 
+def test_thresholds_are_memoised_and_returned_as_private_copies():
+    """two_pcf asks for the thresholds on every comp_2pcf call (1.7 ms of Python bisections per geometry): the
+    second request is served from the memo, and a caller writing into its array cannot poison it."""
+    from treegp_b200 import binning
+
+    a = binning.twod_thresholds(3.25, 7)
+    a_copy = a.copy()
+    a[3] = 123.0
+    np.testing.assert_array_equal(binning.twod_thresholds(3.25, 7), a_copy)
+    assert binning.twod_thresholds(np.float64(3.25), np.int64(7)) is not binning.twod_thresholds(3.25, 7)
+    assert binning._twod_thresholds.cache_info().hits >= 2
+    b = binning.log_thresholds(0.2, 9.0, 11)
+    b_copy = b.copy()
+    b[:] = 0.0
+    np.testing.assert_array_equal(binning.log_thresholds(0.2, 9.0, 11), b_copy)
+
+
 def test_log_thresholds_reproduce_the_formula():
     from treegp_b200 import binning
 
