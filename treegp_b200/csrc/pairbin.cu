@@ -118,9 +118,6 @@ __device__ __noinline__ int pb_bin_twod_search_cold(double d, int nbins, const d
   return pb_bin_twod_search(d, nbins, ed);
 }
 __device__ __forceinline__ int pb_bin_twod_guess(double d, int g, int nbins, const double* __restrict__ ed) {
-#ifdef PB_EXP_NOGUESS   // experiment: always search
-  return pb_bin_twod_search(d, nbins, ed);
-#endif
   if (d >= ed[g] && d < ed[g + 1]) return g;
   return pb_bin_twod_search_cold(d, nbins, ed);
 }
@@ -675,16 +672,9 @@ pairbin_kernel(PBParams P) {
   // below the split need c_j <= RT, columns from it on need c_j > RT, and in ascending order only the two
   // neighbours of the split can fail.
   auto rank_query = [&](double T, double RT, bool live, int& pos) -> bool {
-#ifdef PB_EXP_BISECT   // experiment: the six-probe bisection
-    pos = 0;
-#pragma unroll
-    for (int st = 16; st > 0; st >>= 1) pos += (cxy[pos + st - 1].x < T) ? st : 0;
-    pos += (cxy[pos].x < T) ? 1 : 0;
-#else
     const int b = 8 * ((cxy[7].x < T ? 1 : 0) + (cxy[15].x < T ? 1 : 0) + (cxy[23].x < T ? 1 : 0));
     const int sp = b + 2 * ((cxy[b + 1].x < T ? 1 : 0) + (cxy[b + 3].x < T ? 1 : 0) + (cxy[b + 5].x < T ? 1 : 0));
     pos = sp + (cxy[sp].x < T ? 1 : 0) + (cxy[sp + 1].x < T ? 1 : 0);          // 0 .. 32
-#endif
     return !live || ((pos == 0 || cxy[pos - 1].x <= RT) && (pos == PB_CHUNK || cxy[pos].x > RT));
   };
 
