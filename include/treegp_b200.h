@@ -211,14 +211,21 @@ int tgp_bootstrap_multiplicities(uint64_t* state, int64_t n, int64_t b, const in
 /* Pair sums of a VECTOR field's 2-point functions in log-radius bins (E/B diagnostics; replaces the all-pairs numpy
  * loop of utils.py:5-74 and TreeCorr's VVCorrelation of utils.py:110-155 in the bin_slop -> 0 limit).
  *  x, y, vx, vy : n points and the vector field there.
- *  edges        : device double[nbins+1] thresholds on r^2 (treegp_b200.binning.logr_thresholds): a pair with
- *                 d = z_j - z_i, r2 = |d|^2 != 0 goes to bin k = #{1 <= m <= nbins-1 : r2 >= edges[m]} iff
- *                 edges[0] <= r2 < edges[nbins].
+ *  edges        : device double[nbins+1] thresholds on r^2 (treegp_b200.binning.hist_thresholds_r2): edges[k] = h_k^2,
+ *                 h_k the smallest double with np.log(h_k) >= bin_edges[k] of the reference's np.histogram call
+ *                 (utils.py:52-55; for k = nbins: > instead of >=, the last bin is closed).  A pair with d = z_j - z_i,
+ *                 r2 = |d|^2 != 0 goes to bin k = #{0 <= m <= nbins : r2 >= edges[m]} - 1 if that is in [0, nbins).
  *  counts       : device int64[nbins], ACCUMULATED.
  *  sums         : device double[6 * nbins], ACCUMULATED: {ln r, Re(v_i conj v_j), Re(v_i v_j), Im(v_i v_j),
- *                 Re(v_i v_j conj(d)^2 / r2), Im(same)} each over nbins. */
+ *                 Re(v_i v_j conj(d)^2 / r2), Im(same)} each over nbins.
+ *  amb_pairs    : device int64[2 * amb_cap]: pairs (i, j) whose r2 lies within 1e-14 (relative) of a threshold are
+ *                 NOT accumulated -- hypot() of the reference and sqrt(r2) may round to different sides there --
+ *                 but listed here for the caller to settle with the reference's own expression.
+ *  amb_count    : device int32[1], ACCUMULATED: number of such pairs (may exceed amb_cap: then the list is
+ *                 truncated and the caller must retry with a larger one). */
 int tgp_vcorr(const double* x, const double* y, const double* vx, const double* vy, int64_t n,
-              const double* edges, int32_t nbins, int64_t* counts, double* sums, void* stream);
+              const double* edges, int32_t nbins, int64_t* counts, double* sums, int64_t* amb_pairs,
+              int32_t amb_cap, int32_t* amb_count, void* stream);
 
 /* Points per pair block: 32 (informational). */
 int tgp_pairbin_tile(void);

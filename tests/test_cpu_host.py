@@ -309,16 +309,19 @@ def test_eb_oracle_matches_all_pairs_formula():
     vv = v[i1] * v[i2] * np.conj(dr) ** 2 / np.abs(dr) ** 2
     np.testing.assert_allclose(sm.real, np.histogram(ld, bins=bins, range=hr, weights=vv.real)[0], atol=1e-11)
     np.testing.assert_allclose(sm.imag, np.histogram(ld, bins=bins, range=hr, weights=vv.imag)[0], atol=1e-11)
-    # thresholds on r^2 reproduce the floor formula
-    ed = binning.logr_thresholds(np.log(rmin), dlogr, bins)
-    r2 = np.abs(dr) ** 2
-    k_formula = np.floor((0.5 * np.log(r2) - np.log(rmin)) / dlogr).astype(int)
+    # thresholds on r^2: outside the undecided band (1e-14 relative, settled on the host) they give np.histogram's bin
+    ed = binning.hist_thresholds_r2(np.log(rmin), dlogr, bins)
+    r2 = (x[i2] - x[i1]) ** 2 + (y[i2] - y[i1]) ** 2
+    k_hist = binning.hist_bin(ld, binning.hist_edges(np.log(rmin), dlogr, bins))
     k_thr = np.searchsorted(ed, r2, side="right") - 1
-    inside = (k_formula >= 0) & (k_formula < bins)
-    assert np.mean(k_thr[inside] == k_formula[inside]) > 0.9999     # numpy's vector log may differ from libm by 1 ulp
+    k_thr[(k_thr < 0) | (k_thr >= bins)] = -1
+    near = np.min(np.abs(r2[:, None] / ed[None, :] - 1.0), axis=1) <= 1e-14
+    np.testing.assert_array_equal(k_thr[~near], k_hist[~near])
+    assert near.sum() < 5
+    edges = binning.hist_edges(np.log(rmin), dlogr, bins)
     for k in range(bins + 1):
-        assert np.floor((0.5 * np.log(ed[k]) - np.log(rmin)) / dlogr) >= k > np.floor(
-            (0.5 * np.log(np.nextafter(ed[k], 0)) - np.log(rmin)) / dlogr)
+        h = np.sqrt(ed[k])
+        assert abs(np.log(h) - edges[k]) < 1e-14 * max(1.0, abs(edges[k]))
 
 
 def test_truncation_thresholds_are_below_1e_minus_40():

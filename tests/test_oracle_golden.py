@@ -64,3 +64,21 @@ def test_not_positive_definite_gives_minus_inf(golden):
     K = go.kmat("rbf", X, amp=1.0, length_scale=50.0)
     logl, _ = go.log_likelihood(K, np.ones(len(X)))
     assert logl == -np.inf and float(golden["logL_notpd"]) == -np.inf
+
+
+def test_eb_oracle_matches_reference_vcorr():
+    """oracle/eb_oracle.py against the reference's own `vcorr` (utils.py:5-74) on a random field with a coincident
+    pair and on a lattice (tests/golden/make_golden_r2.py): EQUAL per-bin counts, correlation functions 1e-12."""
+    import os
+    from oracle import eb_oracle
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors_r2.npz"))
+    for pre, (rmin, rmax, dlogr) in (("eb", tuple(float(v) for v in g["eb_par"])), ("ebl", (0.01, 1.0, 0.05))):
+        bins = int(np.ceil(np.log(rmax / rmin) / dlogr))
+        c, slr, sp, sz2, sm = eb_oracle.pair_sums(g[pre + "_x"], g[pre + "_y"], g[pre + "_dx"], g[pre + "_dy"],
+                                                  np.log(rmin), dlogr, bins)
+        np.testing.assert_array_equal(c, g[pre + "_counts"])
+        ok = c > 0
+        for got, key in ((slr, "_logr"), (sp, "_xip"), (sm.real, "_xim"), (sm.imag, "_xix"), (sz2, "_xiz2")):
+            ref = g[pre + key]
+            np.testing.assert_allclose((got / np.where(ok, c, 1))[ok], ref[ok], rtol=0, atol=1e-12 * np.abs(ref[ok]).max())

@@ -221,18 +221,47 @@ def pairbin(px, py, pk, pw, cat_off, max_cat_len, bin_type, edges, nbins, min_se
 
 def vcorr_sums(x, y, dx, dy, logrmin, dlogr, bins):
     """Pair sums of the vector-field correlation functions (utils.py:5-74) as numpy arrays:
-    counts, sum ln r, sum Re(v1 conj v2), sum v1 v2 (complex), sum v1 v2 conj(d)^2/|d|^2 (complex)."""
+    counts, sum ln r, sum Re(v1 conj v2), sum v1 v2 (complex), sum v1 v2 conj(d)^2/|d|^2 (complex).
+
+    The device bins by thresholds on r^2; the pairs it reports as undecided (r^2 within 1e-14 of a threshold,
+    where hypot and sqrt(r^2) may round apart: none for generic inputs) are placed here with the reference's own
+    expression np.log(np.absolute(d)), so the counts equal np.histogram's bit for bit."""
     from . import binning
 
-    xd, yd, vxd, vyd = (to_device(np.asarray(a, dtype=np.float64)) for a in (x, y, dx, dy))
+    x, y, dx, dy = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, dx, dy))
+    xd, yd, vxd, vyd = (to_device(a) for a in (x, y, dx, dy))
     n = int(xd.numel())
-    edges = to_device(binning.logr_thresholds(logrmin, dlogr, bins))
-    counts = torch.zeros(bins, dtype=torch.int64, device=xd.device)
-    sums = torch.zeros((6, bins), dtype=F64, device=xd.device)
-    check(_cabi.load().tgp_vcorr(_p(xd), _p(yd), _p(vxd), _p(vyd), n, _p(edges), int(bins), _p(counts), _p(sums),
-                                 _stream()), "tgp_vcorr")
+    edges = to_device(binning.hist_thresholds_r2(logrmin, dlogr, bins))
+    cap = 1 << 16
+    while True:
+        counts = torch.zeros(bins, dtype=torch.int64, device=xd.device)
+        sums = torch.zeros((6, bins), dtype=F64, device=xd.device)
+        amb = torch.empty((cap, 2), dtype=torch.int64, device=xd.device)
+        namb = torch.zeros(1, dtype=torch.int32, device=xd.device)
+        check(_cabi.load().tgp_vcorr(_p(xd), _p(yd), _p(vxd), _p(vyd), n, _p(edges), int(bins), _p(counts), _p(sums),
+                                     _p(amb), cap, _p(namb), _stream()), "tgp_vcorr")
+        na = int(namb.item())
+        if na <= cap:
+            break
+        cap = 1 << int(np.ceil(np.log2(na)))
     s = sums.cpu().numpy()
-    return (counts.cpu().numpy().astype(np.float64), s[0], s[1], s[2] + 1j * s[3], s[4] + 1j * s[5])
+    c = counts.cpu().numpy().astype(np.float64)
+    if na:
+        i1, i2 = amb[:na].cpu().numpy().T
+        dr = 1j * (y[i2] - y[i1])
+        dr += x[i2] - x[i1]
+        with np.errstate(divide="ignore"):
+            logdr = np.log(np.absolute(dr))
+        k = binning.hist_bin(logdr, binning.hist_edges(logrmin, dlogr, bins))
+        ok = k >= 0
+        k, dr, logdr, i1, i2 = k[ok], dr[ok], logdr[ok], i1[ok], i2[ok]
+        v = dx + 1j * dy
+        vv = v[i1] * v[i2]
+        rot = vv * np.conj(dr) ** 2 / (dr.real * dr.real + dr.imag * dr.imag)
+        c += np.bincount(k, minlength=bins)
+        for row, wgt in enumerate((logdr, dx[i1] * dx[i2] + dy[i1] * dy[i2], vv.real, vv.imag, rot.real, rot.imag)):
+            s[row] += np.bincount(k, weights=wgt, minlength=bins)
+    return (c, s[0], s[1], s[2] + 1j * s[3], s[4] + 1j * s[5])
 
 
 def hilbert_order(px, py):

@@ -82,16 +82,37 @@ def _log_thresholds(min_sep, max_sep, nbins):
     return edges
 
 
-def logr_thresholds(logrmin, dlogr, bins):
-    """edges[k], k = 0..bins: smallest r^2 with floor((0.5 ln(r^2) - logrmin) / dlogr) >= k -- the log-radius
-    binning of utils.py:50-53 (`vcorr`); a pair is kept iff edges[0] <= r^2 < edges[bins]."""
-    logrmin, dlogr = float(logrmin), float(dlogr)
-    edges = np.empty(bins + 1)
+def hist_edges(logrmin, dlogr, bins):
+    """bin_edges of np.histogram(logdr, bins=bins, range=(logrmin, logrmin + bins * dlogr)) (utils.py:50-55)."""
+    return np.linspace(float(logrmin), float(logrmin) + bins * float(dlogr), bins + 1)
+
+
+def hist_bin(logdr, edges):
+    """Bin index np.histogram gives each value for equal-width `edges` (-1: outside): edges[k] <= v < edges[k+1],
+    the last bin closed on the right."""
+    logdr = np.asarray(logdr, dtype=np.float64)
+    k = np.searchsorted(edges, logdr, side="right") - 1
+    k[logdr == edges[-1]] = len(edges) - 2
+    k[(logdr < edges[0]) | (logdr > edges[-1]) | ~np.isfinite(logdr)] = -1
+    return k
+
+
+def hist_thresholds_r2(logrmin, dlogr, bins):
+    """r^2 thresholds for the log-radius binning of utils.py:50-55 (`vcorr`): out[k] = h_k^2 with h_k the smallest
+    double whose np.log (numpy's own, the function the reference bins with) is >= bin_edges[k]; for k = bins the
+    smallest with np.log(h) > bin_edges[bins] (np.histogram closes the last bin).  h^2 is rounded; the device
+    treats r^2 within 1e-14 of a threshold as undecided (csrc/vcorr.cu), so that rounding is immaterial."""
+    edges = hist_edges(logrmin, dlogr, bins)
+    out = np.empty(bins + 1)
     for k in range(bins + 1):
-        lo = math.exp(2.0 * (logrmin + (k - 1.0) * dlogr))
-        hi = math.exp(2.0 * (logrmin + (k + 1.0) * dlogr))
-        edges[k] = _smallest_true(lambda v: math.floor((0.5 * math.log(v) - logrmin) / dlogr) >= k, lo, hi)
-    return edges
+        e = edges[k]
+        lo, hi = math.exp(e - 1e-6 - 1e-9 * abs(e)), math.exp(e + 1e-6 + 1e-9 * abs(e))
+        if k < bins:
+            h = _smallest_true(lambda v: bool(np.log(np.float64(v)) >= e), lo, hi)
+        else:
+            h = _smallest_true(lambda v: bool(np.log(np.float64(v)) > e), lo, hi)
+        out[k] = h * h
+    return out
 
 
 def twod_mask(nbins):

@@ -5,8 +5,13 @@
 // bin_slop -> 0 limit.  For every unordered pair with separation d = z_j - z_i != 0 and
 // log-radius bin k = floor((ln|d| - ln rmin) / dlogr) in [0, nbins):
 //     count, sum ln|d|, sum Re(v_i conj v_j), sum v_i v_j (complex), sum v_i v_j conj(d)^2 / |d|^2 (complex).
-// As in the pair-binning kernel the bin is decided by comparing r^2 against host-supplied thresholds (the
-// smallest double the formula sends to bin >= k), so no logarithm decides a bin on the device.
+// The reference places a pair with np.histogram on v = np.log(np.absolute(d)) (utils.py:50-55): bin k iff
+// bin_edges[k] <= v < bin_edges[k+1] (last bin closed).  The host turns every edge into the smallest double h with
+// np.log(h) >= edge and passes h^2; the device compares r^2 = dx^2 + dy^2 against them.  hypot(dx, dy) is within
+// one ulp of sqrt(r^2), so the comparison is decisive unless r^2 lies within a relative band (VC_BAND, ~45 ulp)
+// of a threshold: such AMBIGUOUS pairs are not accumulated but appended to a list (i, j) that the host settles
+// with the reference's own numpy expressions -- counts are bit-exact by construction, the list is empty for
+// all but lattice-like inputs.
 //
 // Shape: the pair matrix is cut into 256 x 256 tiles (I <= J, linearised); thread = row point, the column
 // points of the tile are staged in shared memory; every warp owns a private histogram in shared memory
@@ -17,11 +22,13 @@
 
 constexpr int VC_T = 256;
 constexpr int VC_NSUM = 6;   // ln r, plus, z2 re, z2 im, minus re, minus im
+constexpr double VC_BAND = 1e-14;
 
 __global__ void __launch_bounds__(VC_T)
 vcorr_kernel(const double* __restrict__ x, const double* __restrict__ y, const double* __restrict__ vx,
              const double* __restrict__ vy, int64_t n, const double* __restrict__ edges, int nbins,
-             unsigned long long* __restrict__ counts, double* __restrict__ sums) {
+             unsigned long long* __restrict__ counts, double* __restrict__ sums,
+             int64_t* __restrict__ amb_pairs, int32_t amb_cap, int32_t* __restrict__ amb_count) {
   extern __shared__ __align__(16) double vsh[];
   double* ed = vsh;                                   // nbins + 1
   double4* cp = reinterpret_cast<double4*>(ed + ((nbins + 2) & ~1));   // VC_T column points (x, y, vx, vy)
@@ -46,17 +53,25 @@ vcorr_kernel(const double* __restrict__ x, const double* __restrict__ y, const d
     unsigned* my_c = hc + warp * nbins;
     const int jn = (int)((n - J * VC_T < VC_T) ? (n - J * VC_T) : VC_T);
     const int j0 = (I == J) ? tid + 1 : 0;            // diagonal tile: j > i
-    const double lo = ed[0], hi = ed[nbins];
+    const double lo = ed[0] * (1.0 - VC_BAND), hi = ed[nbins] * (1.0 + VC_BAND);
     for (int jj = j0; jj < jn; ++jj) {
       const double4 p = cp[jj];
       const double dx = p.x - xi, dy = p.y - yi;
       const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-      if (!(r2 > 0.0) || r2 < lo || !(r2 < hi)) continue;
-      int a = 0, b = nbins - 1;                       // largest k with ed[k] <= r2
+      if (!(r2 > 0.0) || r2 < lo || !(r2 <= hi)) continue;
+      int a = -1, b = nbins;                          // largest k in [-1, nbins] with ed[k] <= r2 (ed[-1] = -inf)
       while (a < b) {
         const int mid = (a + b + 1) >> 1;
         if (r2 >= ed[mid]) a = mid; else b = mid - 1;
       }
+      const bool near_lower = a >= 0 && r2 <= ed[a] * (1.0 + VC_BAND);
+      const bool near_upper = a < nbins && r2 >= ed[a + 1] * (1.0 - VC_BAND);
+      if (near_lower || near_upper) {                 // the host decides (see the header)
+        const int slot = atomicAdd(amb_count, 1);
+        if (slot < amb_cap) { amb_pairs[2 * slot] = i; amb_pairs[2 * slot + 1] = J * VC_T + jj; }
+        continue;
+      }
+      if (a < 0 || a >= nbins) continue;
       // v_i conj(v_j), v_i v_j, v_i v_j conj(d)^2 / r2
       const double bx = p.z, by = p.w;
       const double plus = ax * bx + ay * by;
@@ -87,10 +102,12 @@ vcorr_kernel(const double* __restrict__ x, const double* __restrict__ y, const d
 }
 
 extern "C" int tgp_vcorr(const double* x, const double* y, const double* vx, const double* vy, int64_t n,
-                         const double* edges, int32_t nbins, int64_t* counts, double* sums, void* stream) {
+                         const double* edges, int32_t nbins, int64_t* counts, double* sums, int64_t* amb_pairs,
+                         int32_t amb_cap, int32_t* amb_count, void* stream) {
   TGP_CHECK_ARG(n >= 0 && nbins >= 1 && nbins <= 512, "n / nbins (1..512)");
   if (n < 2) return TGP_OK;
-  TGP_CHECK_ARG(x && y && vx && vy && edges && counts && sums, "null pointer");
+  TGP_CHECK_ARG(x && y && vx && vy && edges && counts && sums && amb_count && (amb_pairs || amb_cap == 0), "null pointer");
+  TGP_CHECK_ARG(amb_cap >= 0, "amb_cap");
   const int64_t nt = tgp_cdiv(n, VC_T);
   const int64_t ntiles = nt * (nt + 1) / 2;
   TGP_CHECK_ARG(ntiles < (1ll << 31), "too many points for one launch");
@@ -101,7 +118,7 @@ extern "C" int tgp_vcorr(const double* x, const double* y, const double* vx, con
     attr_set = true;
   }
   vcorr_kernel<<<(unsigned)ntiles, VC_T, smem, (cudaStream_t)stream>>>(
-      x, y, vx, vy, n, edges, nbins, reinterpret_cast<unsigned long long*>(counts), sums);
+      x, y, vx, vy, n, edges, nbins, reinterpret_cast<unsigned long long*>(counts), sums, amb_pairs, amb_cap, amb_count);
   TGP_LAUNCH_CHECK();
   return TGP_OK;
 }

@@ -11,8 +11,8 @@ import numpy as np
 
 def _pair_sums(x, y, dx, dy, logrmin, dlogr, bins):
     """Per log-r bin: counts, sum log r, sum v1.v2*, sum v1 v2, sum v1 v2 exp(-2 i phi) over all pairs -- on the
-    device (csrc/vcorr.cu); the bins are decided by thresholds on r^2 that reproduce
-    floor((ln r - ln rmin) / dlogr) (binning.logr_thresholds)."""
+    device (csrc/vcorr.cu); the bins are np.histogram's of utils.py:52-55, decided by thresholds on r^2
+    (binning.hist_thresholds_r2) with the undecided pairs settled on the host (backend.vcorr_sums)."""
     from . import backend
 
     return backend.vcorr_sums(x, y, dx, dy, logrmin, dlogr, bins)
