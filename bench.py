@@ -278,7 +278,7 @@ def run_ours(args):
     Xp, yp, yerrp = pinned(np.ascontiguousarray(X)), pinned(y), pinned(y_err)
     e2e_ms = []
     tp = treegp.two_pcf(Xp, yp, yerrp, mn, mx, nbins=NBINS, anisotropic=True)
-    tp.group = None if world > 1 else False
+    tp.group = dist.WORLD if world > 1 else False
     for i in range(1 + args.steps):
         barrier()
         t0 = time.perf_counter()

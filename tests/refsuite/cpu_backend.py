@@ -136,6 +136,13 @@ def install():
         st = lambda key: torch.as_tensor(np.stack([r[key] for r in rows]))
         return st("npairs"), st("weight"), st("sumwkk"), (st("sumwr") if bt == "Log" else None)
 
+    def pairbin_packed(px, py, pk, pw, cat_off, max_cat_len, bin_type, edges, nbins, min_sep, max_sep, rank=0, nranks=1):
+        npairs, sw, swkk, swr = pairbin(px, py, pk, pw, cat_off, max_cat_len, bin_type, edges, nbins, min_sep, max_sep)
+        planes = [npairs.to(torch.int64).view(F64), sw, swkk] + ([] if swr is None else [swr])
+        return torch.stack(planes)
+
+    backend.pairbin_packed = pairbin_packed
+
     def knn_mean(X0, y0, Xq, k):
         from sklearn.neighbors import KNeighborsRegressor   # what the reference itself calls (gp_interp.py:236-238)
 

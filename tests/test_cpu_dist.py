@@ -41,8 +41,15 @@ def _worker(rank, world, port, ret):
             t = lambda a: torch.as_tensor(a).reshape(1, -1).clone()
             return t(r["npairs"]), t(r["weight"]), t(r["sumwkk"]), (t(r["sumwr"]) if bt == "Log" else None)
 
-        backend.pairbin = fake_pairbin
+        def fake_packed(*a, **kw):
+            c, sw, swkk, swr = fake_pairbin(*a, **kw)
+            return torch.stack([c.to(torch.int64).view(torch.float64), sw, swkk] + ([] if swr is None else [swr]))
+
+        backend.pairbin_packed = fake_packed
         assert dist.rank_world(None) == (rank, world)
+        assert dist.rank_world(False) == (0, 1) and dist.rank_world(dist.WORLD) == (rank, world)
+        # sharding is opt-in: by default every process counts all pairs of its own catalogue
+        assert treegp.two_pcf(np.zeros((3, 2)), np.zeros(3), np.zeros(3), 0.0, 1.0).group is False
 
         rng = np.random.default_rng(5)
         n = 900
@@ -51,6 +58,7 @@ def _worker(rank, world, port, ret):
         y_err = np.full(n, 0.2)
         for aniso, mn, mx, nb in ((True, 0.0, 3.0, 11), (False, 0.2, 4.0, 10)):
             t = treegp.two_pcf(X, y, y_err, mn, mx, nbins=nb, anisotropic=aniso)
+            t.group = dist.WORLD
             xi, dist_, coord, mask = t.comp_2pcf(X, y, y_err)
             rxi, rdist, _, rmask = po.comp_2pcf(X, y, y_err, mn, mx, nb, aniso)
             np.testing.assert_allclose(xi, rxi, rtol=0, atol=1e-12)

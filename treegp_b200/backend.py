@@ -57,9 +57,19 @@ def alloc_matrix(rows, cols, device=None):
     return torch.empty((int(rows), even(cols)), dtype=F64, device=dev)
 
 
+def _check_dims(kdesc, X, Xs=None):
+    """The device kernels index coordinates with the descriptor's ndim: a mismatch would read past the buffers
+    (the reference raises from pdist / cdist in that case)."""
+    if X.shape[1] != kdesc.ndim:
+        raise ValueError("kernel is %d-dimensional but the coordinates have %d columns" % (kdesc.ndim, X.shape[1]))
+    if Xs is not None and Xs.shape[1] != X.shape[1]:
+        raise ValueError("XA and XB must have the same number of columns (%d vs %d)" % (Xs.shape[1], X.shape[1]))
+
+
 def kmat_sym(X, kdesc, diag_add=None, out=None, lower_only=False):
     """K(X,X) + diag(diag_add).  Returns the (N, ld) workspace; the matrix is out[:, :N]."""
     X = as_points(X)
+    _check_dims(kdesc, X)
     N = X.shape[0]
     if out is None:
         out = alloc_matrix(N, N, X.device)
@@ -71,6 +81,7 @@ def kmat_sym(X, kdesc, diag_add=None, out=None, lower_only=False):
 
 def kmat_cross(Xs, X, kdesc, out=None):
     Xs, X = as_points(Xs), as_points(X)
+    _check_dims(kdesc, X, Xs)
     M, N = Xs.shape[0], X.shape[0]
     if out is None:
         out = alloc_matrix(M, N, X.device)
@@ -139,6 +150,7 @@ def predict_mean(Xs, X, kdesc, alpha, out=None, truncate=None):
     gather: plumbing) and tgp_predict_mean_trunc skips blocks of pairs whose correlation is provably below
     1e-40; the result differs from the full sum by at most 1e-40 * sum|amp alpha| (and by summation order)."""
     Xs, X = as_points(Xs), as_points(X)
+    _check_dims(kdesc, X, Xs)
     M, N = Xs.shape[0], X.shape[0]
     if out is None:
         out = torch.empty(M, dtype=F64, device=X.device)
@@ -185,6 +197,7 @@ def knn_mean(X0, y0, Xq, k):
 
 def predict_var(Xs, X, kdesc, L, chunk=None, out=None, work=None):
     Xs, X = as_points(Xs), as_points(X)
+    _check_dims(kdesc, X, Xs)
     M, N = Xs.shape[0], X.shape[0]
     if chunk is None:
         # keep the K(Xs_chunk, X) workspace around 2 GiB
@@ -199,24 +212,47 @@ def predict_var(Xs, X, kdesc, L, chunk=None, out=None, work=None):
     return out
 
 
-def pairbin(px, py, pk, pw, cat_off, max_cat_len, bin_type, edges, nbins, min_sep, max_sep,
-            rank=0, nranks=1):
-    """Accumulate pair bins for `ncat` catalogues.  Returns (npairs int64, sumw, sumwkk, sumwr|None),
-    each shaped (ncat, nb)."""
+_PB_SCRATCH = {}
+
+
+def _pairbin_scratch(dev, doubles):
+    """The pre-pass workspace of tgp_pairbin (chunk boxes + sorted chunk copies, ~50 MB at N = 1e6), kept per
+    (device, stream) and grown on demand: launches on one stream are ordered, so they can share it; launches on
+    different streams get different buffers."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _PB_SCRATCH.get(key)
+    if buf is None or buf.numel() < doubles:
+        buf = torch.empty(int(doubles), dtype=F64, device=dev)
+        _PB_SCRATCH[key] = buf
+    return buf
+
+
+def pairbin_packed(px, py, pk, pw, cat_off, max_cat_len, bin_type, edges, nbins, min_sep, max_sep,
+                   rank=0, nranks=1):
+    """Accumulate pair bins for `ncat` catalogues into ONE zeroed device buffer of shape (3 | 4, ncat, nb), FP64:
+    plane 0 holds the int64 pair counts (raw 8-byte words), plane 1 sum w, plane 2 sum w k k, plane 3 (Log
+    binning only) sum w r -- one allocation, and later one all-reduce / one device->host copy for all of them."""
     ncat = int(cat_off.numel()) - 1
     nb = nbins * nbins if bin_type == _cabi.BIN_TWOD else nbins
     dev = px.device
-    npairs = torch.zeros((ncat, nb), dtype=torch.int64, device=dev)
-    sumw = torch.zeros((ncat, nb), dtype=F64, device=dev)
-    sumwkk = torch.zeros((ncat, nb), dtype=F64, device=dev)
-    sumwr = torch.zeros((ncat, nb), dtype=F64, device=dev) if bin_type == _cabi.BIN_LOG else None
+    planes = 4 if bin_type == _cabi.BIN_LOG else 3
+    out = torch.zeros((planes, ncat, nb), dtype=F64, device=dev)
     lib = _cabi.load()
-    work = torch.empty(int(lib.tgp_pairbin_work_doubles(int(px.numel()), ncat)), dtype=F64, device=dev)
+    work = _pairbin_scratch(dev, lib.tgp_pairbin_work_doubles(int(px.numel()), ncat))
     check(lib.tgp_pairbin(_p(px), _p(py), _p(pk), _p(pw), _p(cat_off), ncat, int(max_cat_len),
-                                   int(bin_type), _p(edges), int(nbins), float(min_sep) ** 2, float(max_sep),
-                      int(rank), int(nranks), _p(npairs), _p(sumw), _p(sumwkk), _p(sumwr), _p(work),
-                      _stream()), "tgp_pairbin")
-    return npairs, sumw, sumwkk, sumwr
+                          int(bin_type), _p(edges), int(nbins), float(min_sep) ** 2, float(max_sep),
+                          int(rank), int(nranks), _p(out[0]), _p(out[1]), _p(out[2]),
+                          _p(out[3]) if planes == 4 else _p(None), _p(work), _stream()), "tgp_pairbin")
+    return out
+
+
+def pairbin(px, py, pk, pw, cat_off, max_cat_len, bin_type, edges, nbins, min_sep, max_sep,
+            rank=0, nranks=1):
+    """Accumulate pair bins for `ncat` catalogues.  Returns (npairs int64, sumw, sumwkk, sumwr|None),
+    each shaped (ncat, nb) (views of one packed buffer, see pairbin_packed)."""
+    out = pairbin_packed(px, py, pk, pw, cat_off, max_cat_len, bin_type, edges, nbins, min_sep, max_sep,
+                         rank=rank, nranks=nranks)
+    return out[0].view(torch.int64), out[1], out[2], (out[3] if out.shape[0] == 4 else None)
 
 
 def vcorr_sums(x, y, dx, dy, logrmin, dlogr, bins):

@@ -170,15 +170,14 @@ template <int BN_, int WARPS_M, int WARPS_N, int MIN_CTAS>
 static int gemm_launch_cfg(double* C, int64_t M, int64_t Nc, int64_t ldc, const double* A, int64_t lda,
                            const double* B, int64_t ldb, int64_t Kd, int lower_only, cudaStream_t st) {
   constexpr int SMEM = STAGES * (BM + BN_) * BK * 8;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static TgpPerDeviceOnce attr_once;
+  if (tgp_first_use_on_device(attr_once)) {
     TGP_CUDA(cudaFuncSetAttribute(gemm_nt_sub_kernel<BN_, WARPS_M, WARPS_N, MIN_CTAS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     // same shared-memory carve-out for every kernel of the factorisation: no L1/shared reconfiguration
     // between the back-to-back small launches of a panel
     TGP_CUDA(cudaFuncSetAttribute(gemm_nt_sub_kernel<BN_, WARPS_M, WARPS_N, MIN_CTAS>,
                                   cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
   }
   dim3 grid((unsigned)tgp_cdiv(Nc, BN_), (unsigned)tgp_cdiv(M, BM));
   TGP_CHECK_ARG(grid.y <= 65535u, "M too large for one launch");
@@ -457,14 +456,13 @@ trsm_panel_kernel(const double* __restrict__ L, int nb, int64_t ldl, double* __r
 static int trsm_panel_launch(const double* L, int nb, int64_t ldl, double* B, int64_t M, int64_t ldb,
                              cudaStream_t st) {
   if (M <= 0 || nb <= 0) return TGP_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static TgpPerDeviceOnce attr_once;
+  if (tgp_first_use_on_device(attr_once)) {
     TGP_CUDA(cudaFuncSetAttribute(trsm_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
     TGP_CUDA(cudaFuncSetAttribute(trsm_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSM_SMEM));
     TGP_CUDA(cudaFuncSetAttribute(trsm_panel_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TGP_CUDA(cudaFuncSetAttribute(trsm_panel_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     TGP_CUDA(cudaFuncSetAttribute(potf2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
   }
   const bool full = (nb == NB) && ((ldb & 1) == 0) && (((uintptr_t)B & 15) == 0);
   const unsigned grid = (unsigned)tgp_cdiv(M, TRSM_ROWS);
@@ -814,12 +812,11 @@ panel_left_kernel(double* __restrict__ Akk, int64_t ld, int w, int64_t below, in
 // Factorise the w x w (w <= OB) diagonal block at Akk and solve the `below` rows under it (L21 = A21 L11^-T).
 static int panel_factor(double* Akk, int64_t w, int64_t ld, int64_t below, int32_t* info, int64_t goff,
                         cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static TgpPerDeviceOnce attr_once;
+  if (tgp_first_use_on_device(attr_once)) {
     TGP_CUDA(cudaFuncSetAttribute(panel_left_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PL_SMEM));
     TGP_CUDA(cudaFuncSetAttribute(panel_left_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                   cudaSharedmemCarveoutMaxShared));
-    attr_set = true;
   }
   const int ndiag = (int)tgp_cdiv(w, NB);
   const int64_t nbelow = tgp_cdiv(below, NB);
@@ -922,33 +919,49 @@ static int potrf_rec(double* A, int64_t n, int64_t ld, int bs, int32_t* info, in
 // with panel(b+1).  The caller's stream is joined with P before returning.
 // --------------------------------------------------------------------------------------------
 #include <vector>
+// Helper stream + events of the look-ahead schedule: one set per host thread AND device (streams and events
+// belong to the device that was current when they were created).
 struct LookaheadCtx {
   cudaStream_t panel = nullptr;
   std::vector<cudaEvent_t> ev;
-  cudaEvent_t get(size_t i) {
-    while (ev.size() <= i) {
+  bool ensure(size_t n) {
+    while (ev.size() < n) {
       cudaEvent_t e;
-      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
       ev.push_back(e);
     }
-    return ev[i];
+    return true;
   }
+  cudaEvent_t get(size_t i) { return ev[i]; }
 };
-static LookaheadCtx& lookahead_ctx() {
-  static thread_local LookaheadCtx c;
-  if (!c.panel) {
+static LookaheadCtx* lookahead_ctx() {
+  static thread_local LookaheadCtx c[TGP_MAX_DEVICES];
+  LookaheadCtx& L = c[tgp_current_device()];
+  if (!L.panel) {
     int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    cudaStreamCreateWithPriority(&c.panel, cudaStreamNonBlocking, hi);
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) return nullptr;
+    if (cudaStreamCreateWithPriority(&L.panel, cudaStreamNonBlocking, hi) != cudaSuccess) {
+      L.panel = nullptr;
+      return nullptr;
+    }
   }
-  return c;
+  return &L;
 }
 static int potrf_lookahead(double* A, int64_t n, int64_t ld, int32_t* info, cudaStream_t U, int64_t extra = 0) {
-  LookaheadCtx& L = lookahead_ctx();
+  LookaheadCtx* Lp = lookahead_ctx();
+  if (!Lp) {
+    tgp_set_error("potrf: could not create the look-ahead stream: %s", cudaGetErrorString(cudaGetLastError()));
+    return TGP_ERR_CUDA;
+  }
+  LookaheadCtx& L = *Lp;
   cudaStream_t P = L.panel;
   // K = 1024 trailing updates amortise the C read-modify-write better once the updates dominate (measured: K = 1024 from N ~ 14k, 2048 from ~ 28k)
   const int64_t OBL = (g_ob_large > 0) ? g_ob_large : (n >= 28000 ? 2048 : (n >= 14000 ? 1024 : 512));
   const int64_t nblk = tgp_cdiv(n, OBL);
+  if (!L.ensure((size_t)(3 + 2 * nblk))) {
+    tgp_set_error("potrf: cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return TGP_ERR_CUDA;
+  }
   cudaEvent_t e_start = L.get(0);
   TGP_CUDA(cudaEventRecord(e_start, U));
   TGP_CUDA(cudaStreamWaitEvent(P, e_start, 0));
@@ -1214,10 +1227,9 @@ trsv_step_kernel(const double* __restrict__ L, int64_t ld, int64_t N, int64_t k0
 
 template <bool FWD>
 static int trsv_sweep(const double* L, int64_t N, int64_t ld, double* b, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static TgpPerDeviceOnce attr_once;
+  if (tgp_first_use_on_device(attr_once)) {
     TGP_CUDA(cudaFuncSetAttribute(trsv_step_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
-    attr_set = true;
   }
   const int64_t nblk = tgp_cdiv(N, TB);
   for (int64_t s = 0; s < nblk; ++s) {
@@ -1299,7 +1311,10 @@ extern "C" int tgp_logdet_chi2(const double* L, int64_t N, int64_t ld, const dou
 __global__ void loglike_finish_kernel(const double* tmp, int64_t N, const int32_t* __restrict__ info, double* out) {
   const double logdet = tmp[0], chi2 = tmp[1];
   double ll = -0.5 * chi2 - 0.5 * (double)N * log(2.0 * TGP_PI) - 0.5 * logdet;
-  if (*info != 0 || isnan(ll)) ll = -INFINITY;
+  // info > 0: leading minor not positive definite -> -inf (log_likelihood.py:38-39).  info < 0: an internal
+  // flag wait timed out -- NOT a property of the matrix: NaN here, and the host raises when it sees info < 0.
+  if (*info > 0 || isnan(ll)) ll = -INFINITY;
+  if (*info < 0) ll = NAN;
   out[0] = ll;
   out[1] = chi2;
   out[2] = logdet;

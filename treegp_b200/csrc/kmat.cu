@@ -27,24 +27,25 @@ extern "C" const char* tgp_last_error(void) { return g_err; }
 extern "C" int tgp_abi_version(void) { return TGP_ABI_VERSION; }
 
 int tgp_num_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static int sms[TGP_MAX_DEVICES] = {};
+  const int dev = tgp_current_device();
+  if (!sms[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = v > 0 ? v : 148;
   }
-  return sms;
+  return sms[dev];
 }
 
 __device__ const double g_vk_phi_dev[TGP_VK_PHI_SIZE] = TGP_VK_PHI_TABLE;
 const double* tgp_phi_device() {
-  static const double* p = nullptr;
-  if (!p) {
+  static const double* p[TGP_MAX_DEVICES] = {};
+  const int dev = tgp_current_device();
+  if (!p[dev]) {
     void* q = nullptr;
-    if (cudaGetSymbolAddress(&q, g_vk_phi_dev) == cudaSuccess) p = (const double*)q;
+    if (cudaGetSymbolAddress(&q, g_vk_phi_dev) == cudaSuccess) p[dev] = (const double*)q;
   }
-  return p;
+  return p[dev];
 }
 
 // ---- kernels -----------------------------------------------------------------------------------

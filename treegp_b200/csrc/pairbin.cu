@@ -1492,15 +1492,18 @@ extern "C" int tgp_pairbin(const double* px, const double* py, const double* pk,
   }
 
   static std::atomic<unsigned> launch_seq{0};   // host threads launching on different streams get different slots
-  void* cbase = nullptr;
-  TGP_CUDA(cudaGetSymbolAddress(&cbase, g_pb_counters));
+  static void* cbase_dev[TGP_MAX_DEVICES] = {};
+  void*& cbase = cbase_dev[tgp_current_device()];
+  if (!cbase) TGP_CUDA(cudaGetSymbolAddress(&cbase, g_pb_counters));
   P.counter = reinterpret_cast<unsigned long long*>(cbase) + (launch_seq.fetch_add(1u) % PB_COUNTER_SLOTS);
   TGP_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(unsigned long long), st));
 
 #define TGP_PB_LAUNCH(BT, W, BS)                                                                          \
   do {                                                                                                    \
-    TGP_CUDA(cudaFuncSetAttribute(pairbin_kernel<BT, W, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  (int)budget));                                                          \
+    static TgpPerDeviceOnce once_;                                                                        \
+    if (tgp_first_use_on_device(once_))                                                                   \
+      TGP_CUDA(cudaFuncSetAttribute(pairbin_kernel<BT, W, BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    (int)budget));                                                        \
     pairbin_kernel<BT, W, BS><<<(unsigned)grid, warps * 32, smem, st>>>(P);                               \
   } while (0)
   if (twod && P.block_sums) {

@@ -39,6 +39,25 @@ static inline int64_t tgp_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 int tgp_num_sms();
 
+// Per-device "done once" flags: function attributes, symbol addresses and helper streams belong to ONE device, and
+// a process may switch devices between calls (the caller follows torch.cuda.current_device()).
+constexpr int TGP_MAX_DEVICES = 64;
+struct TgpPerDeviceOnce {
+  unsigned char done[TGP_MAX_DEVICES] = {};
+};
+static inline int tgp_current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= TGP_MAX_DEVICES) d = 0;
+  return d;
+}
+// true the first time it is called for the current device
+static inline bool tgp_first_use_on_device(TgpPerDeviceOnce& o) {
+  const int d = tgp_current_device();
+  if (o.done[d]) return false;
+  o.done[d] = 1;
+  return true;
+}
+
 // ---- kernel descriptor as the device sees it ------------------------------------------------
 struct KDesc {
   double amp, m00, m01x2, m11;  // m01x2 = 2*m01

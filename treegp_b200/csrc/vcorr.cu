@@ -112,10 +112,9 @@ extern "C" int tgp_vcorr(const double* x, const double* y, const double* vx, con
   const int64_t ntiles = nt * (nt + 1) / 2;
   TGP_CHECK_ARG(ntiles < (1ll << 31), "too many points for one launch");
   const size_t smem = (size_t)((nbins + 2) & ~1) * 8 + VC_T * 32 + (size_t)8 * VC_NSUM * nbins * 8 + (size_t)8 * nbins * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static TgpPerDeviceOnce attr_once;
+  if (tgp_first_use_on_device(attr_once)) {
     TGP_CUDA(cudaFuncSetAttribute(vcorr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
   }
   vcorr_kernel<<<(unsigned)ntiles, VC_T, smem, (cudaStream_t)stream>>>(
       x, y, vx, vy, n, edges, nbins, reinterpret_cast<unsigned long long*>(counts), sums, amb_pairs, amb_cap, amb_count);

@@ -14,20 +14,38 @@ import torch
 import torch.distributed as tdist
 
 
+WORLD = "world"   # sentinel: shard over the default process group
+
+
+def _pg(group):
+    return None if group in (None, False, WORLD) else group
+
+
 def rank_world(group=None):
-    """(rank, world) of `group`; (0, 1) when torch.distributed is not initialised and no group given."""
-    if group is None and not (tdist.is_available() and tdist.is_initialized()):
+    """(rank, world) of `group`.  False: explicitly single-process -> (0, 1).  None / WORLD: the default process
+    group, or (0, 1) when torch.distributed is not initialised.  Otherwise a ProcessGroup."""
+    if group is False:
         return 0, 1
-    if group is False:  # explicit single-process
+    if group in (None, WORLD) and not (tdist.is_available() and tdist.is_initialized()):
         return 0, 1
-    return tdist.get_rank(group), tdist.get_world_size(group)
+    return tdist.get_rank(_pg(group)), tdist.get_world_size(_pg(group))
 
 
 def allreduce_bins(group, *tensors):
-    """Sum the per-rank bin arrays in place (one collective per array, tiny messages)."""
+    """Sum the per-rank bin arrays in place (one collective per array)."""
     for t in tensors:
         if t is not None:
-            tdist.all_reduce(t, op=tdist.ReduceOp.SUM, group=group if group not in (None, False) else None)
+            tdist.all_reduce(t, op=tdist.ReduceOp.SUM, group=_pg(group))
+
+
+def allreduce_packed_bins(group, packed):
+    """ONE all-reduce for the packed bin buffer of backend.pairbin_packed: plane 0 (int64 pair counts stored as raw
+    words) is first converted to FP64 values -- exact below 2^53 pairs per bin, and sums of integer-valued doubles
+    below 2^53 are exact in any order, so the counts stay bit-identical for any number of ranks.  Returns the buffer
+    with plane 0 holding the summed counts as FP64 VALUES."""
+    packed[0] = packed[0].view(torch.int64).to(torch.float64)
+    tdist.all_reduce(packed, op=tdist.ReduceOp.SUM, group=_pg(group))
+    return packed
 
 
 def slab(n, rank, world):
@@ -47,5 +65,5 @@ def gather_slabs(local, n, group=None):
     buf = torch.zeros(pad, dtype=local.dtype, device=local.device)
     buf[: local.numel()] = local
     outs = [torch.empty_like(buf) for _ in range(world)]
-    tdist.all_gather(outs, buf, group=group if group not in (None, False) else None)
+    tdist.all_gather(outs, buf, group=_pg(group))
     return torch.cat([o[:s] for o, s in zip(outs, sizes)])

@@ -16,7 +16,7 @@ import copy
 
 import numpy as np
 
-from . import backend
+from . import _cabi, backend
 from .kernels import eval_kernel, lower_kernel
 from .log_likelihood import log_likelihood
 from .two_pcf import two_pcf
@@ -150,6 +150,8 @@ class GPInterpolation(object):
         yd = backend.to_device(np.asarray(y, dtype=np.float64).reshape(-1))
         _, info, alpha, ws = backend.loglike(Xd, yd, e2, desc, want_alpha=True)
         bad = int(info.item())
+        if bad < 0:
+            raise _cabi.TgpError("tgp_loglike: internal synchronisation timed out (info = %d)" % bad)
         if bad != 0:
             # scipy.linalg.cholesky raises LinAlgError here (gp_interp.py:181)
             raise np.linalg.LinAlgError("%d-th leading minor of the array is not positive definite" % bad)

@@ -58,7 +58,11 @@ class log_likelihood(object):
             return -np.inf
         out, info, _, _ = backend.loglike(Xd, yd, e2, desc, work=work, want_alpha=False)
         self.n_evaluations += 1
-        return float(out[0].item())  # -inf when the factorisation failed (info != 0)
+        value = float(out[0].item())  # -inf when the matrix is not positive definite (info > 0)
+        if value != value:            # NaN marks info < 0: an internal synchronisation timeout, never a -inf
+            from ._cabi import TgpError
+            raise TgpError("tgp_loglike: internal synchronisation timed out (info = %d)" % int(info.item()))
+        return value
 
     @staticmethod
     def _value_and_fd_gradient(fun, rank, world):

@@ -190,8 +190,11 @@ class two_pcf(object):
         self.p0_robust_fit = p0
         self.seed = seed
         self._rng = None
-        # multi-GPU: pair tiles are dealt to `world` ranks and the bin sums all-reduced (dist.py)
-        self.group = None
+        # Multi-GPU is OPT-IN: False = this process counts all pairs itself (the default: in a data-parallel job
+        # every rank fits its own field).  Set to treegp_b200.dist.WORLD (or a ProcessGroup) to deal the pair
+        # tiles to the ranks of that group and all-reduce the bin sums; all ranks must then hold IDENTICAL
+        # data and call comp_2pcf / return_2pcf / optimizer together.
+        self.group = False
 
     @property
     def rng(self):
@@ -220,25 +223,34 @@ class two_pcf(object):
 
         bt, edges = self._bin_geometry()
         rank, world = dist.rank_world(self.group)
-        npairs, sumw, sumwkk, sumwr = backend.pairbin(
-            px, py, pk, pw, offsets, max_len, bt, backend.to_device(edges), self.nbins,
+        packed = backend.pairbin_packed(
+            px, py, pk, pw, offsets, max_len, bt, self._device_edges(edges), self.nbins,
             self.min_sep, self.max_sep, rank=rank, nranks=world)
         if world > 1:
-            dist.allreduce_bins(self.group, npairs, sumw, sumwkk, sumwr)
-        # one device->host transfer for all bin arrays (the int64 counts ride along as raw 8-byte words)
-        parts = [sumw, sumwkk, npairs.to(torch.int64).view(torch.float64)] + ([] if sumwr is None else [sumwr])
-        host = torch.stack(parts).cpu().numpy()
-        sw, swkk = host[0], host[1]
+            packed = dist.allreduce_packed_bins(self.group, packed)   # ONE collective for all bin arrays
+        host = packed.cpu().numpy()                                   # ONE device->host transfer
+        # plane 0: pair counts -- raw int64 words from the kernel, FP64 values after an all-reduce
+        counts = host[0].astype(np.int64) if world > 1 else np.ascontiguousarray(host[0]).view(np.int64)
+        sw, swkk = host[1], host[2]
+        has_wr = host.shape[0] == 4
         with np.errstate(invalid="ignore", divide="ignore"):
             xi = np.where(sw != 0, swkk / sw, 0.0)
             meanr = None
-            if sumwr is not None:
+            if has_wr:
                 # TreeCorr reports the nominal bin centre exp(ln min_sep + (k + 1/2) bin_size) where a bin is empty
                 bs = np.log(self.max_sep / self.min_sep) / self.nbins
                 rnom = np.exp(np.log(self.min_sep) + (np.arange(self.nbins) + 0.5) * bs)
                 meanr = np.where(sw != 0, host[3] / sw, rnom[None, :])
-        self._last_npairs = np.ascontiguousarray(host[2]).view(np.int64)
+        self._last_npairs = counts
         return xi, meanr
+
+    def _device_edges(self, edges):
+        """Bin thresholds on the device, uploaded once per geometry (a fit makes hundreds of calls with one)."""
+        key = (backend.require_cuda(), self.anisotropic, self.min_sep, self.max_sep, self.nbins)
+        cached = getattr(self, "_edges_dev", None)
+        if cached is None or cached[0] != key:
+            self._edges_dev = (key, backend.to_device(edges))
+        return self._edges_dev[1]
 
     def _assemble(self, xi, meanr):
         if self.anisotropic:
