@@ -227,6 +227,12 @@ int tgp_vcorr(const double* x, const double* y, const double* vx, const double* 
               const double* edges, int32_t nbins, int64_t* counts, double* sums, int64_t* amb_pairs,
               int32_t amb_cap, int32_t* amb_count, void* stream);
 
+/* Sticky device-side error word: set (never cleared by the kernels) when an inter-CTA flag wait inside
+ * tgp_potrs_vec / tgp_loglike(want_alpha) timed out -- which cannot happen with the cooperative launch those
+ * sweeps use, but would otherwise leave unknowns unsolved without any other sign.  Synchronises the device and
+ * returns the word (0 = fine, < 0 = the query itself failed); reset != 0 clears it. */
+int tgp_device_error(int reset);
+
 /* Points per pair block: 32 (informational). */
 int tgp_pairbin_tile(void);
 

@@ -81,6 +81,49 @@ def test_potrs_vec(gpu_ready, n):
     np.testing.assert_allclose(x, xref, rtol=1e-9, atol=1e-10 * np.abs(xref).max())
 
 
+@pytest.mark.parametrize("n", [9601, 20011])
+def test_potrs_vec_persistent_sweep_many_slabs_per_cta(gpu_ready, n):
+    """csrc/trsv.cu with more 64-row slabs than CTAs (every CTA owns several, ring stages wrap many times), a short
+    last block, against the residual of the factor itself: || L L^T x - b || small, and bit-identical repeats
+    (fixed accumulation order)."""
+    import torch
+    from treegp_b200 import _cabi, backend
+
+    g = torch.Generator(device="cuda").manual_seed(n)
+    ws = backend.alloc_matrix(n, n)
+    ws.normal_(generator=g)
+    ws.mul_(0.5 / np.sqrt(n))
+    ws[:, :n].diagonal().copy_(1.0 + torch.rand(n, dtype=torch.float64, device="cuda", generator=g))
+    b = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+    x = backend.potrs_vec(ws, n, b.clone())
+    Lm = torch.tril(ws[:, :n])
+    resid = Lm @ (Lm.T @ x) - b
+    assert float(resid.abs().max()) <= 1e-11 * float(b.abs().max()) * np.sqrt(n)
+    for _ in range(3):
+        assert torch.equal(backend.potrs_vec(ws, n, b.clone()), x)
+    assert _cabi.load().tgp_device_error(0) == 0
+
+
+def test_potrs_vec_unaligned_matrix(gpu_ready):
+    """Odd leading dimension / base address: the sweep falls back to plain loads and still solves."""
+    import ctypes
+    import torch
+    from treegp_b200 import _cabi, backend
+
+    n, ld = 777, 779
+    A = _spd(n, 5)
+    Lh = np.linalg.cholesky(A)
+    buf = torch.zeros(n * ld + 1, dtype=torch.float64, device="cuda")
+    view = buf[1:].reshape(n, ld)                 # 8-byte aligned base, odd pitch
+    view[:, :n] = backend.to_device(Lh)
+    b = np.random.default_rng(1).normal(size=n)
+    bd = backend.to_device(b).clone()
+    _cabi.check(_cabi.load().tgp_potrs_vec(ctypes.c_void_p(view.data_ptr()), n, ld, ctypes.c_void_p(bd.data_ptr()),
+                                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "tgp_potrs_vec")
+    xref = sla.cho_solve((Lh, True), b)
+    np.testing.assert_allclose(bd.cpu().numpy(), xref, rtol=1e-9, atol=1e-10 * np.abs(xref).max())
+
+
 @pytest.mark.parametrize("m,nc,kd", [(1, 1, 1), (128, 128, 16), (130, 70, 33), (300, 300, 64), (257, 129, 512), (64, 500, 7)])
 def test_gemm_nt_sub(gpu_ready, m, nc, kd):
     from treegp_b200 import backend

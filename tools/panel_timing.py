@@ -6,7 +6,7 @@ import ctypes, os, subprocess, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = "/tmp/libtgp_timing.so"
-srcs = ["kmat.cu", "dense.cu", "predict.cu", "pairbin.cu", "microbench.cu"]
+srcs = ["kmat.cu", "dense.cu", "trsv.cu", "predict.cu", "pairbin.cu", "microbench.cu", "hostrng.cu", "vcorr.cu"]
 subprocess.check_call(["/usr/local/cuda/bin/nvcc", "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
                        "-DTGP_PANEL_TIMING", "-Xcompiler", "-fPIC", "-shared", "-o", so] +
                       [os.path.join(ROOT, "treegp_b200/csrc", f) for f in srcs])

@@ -1065,191 +1065,11 @@ extern "C" int tgp_gemm_nt_sub(double* C, int64_t M, int64_t Nc, int64_t ldc, co
 }
 
 // ============================================================================================
-// Single right-hand-side solves  L w = b  (forward) and  L^T x = w  (backward).
-// One launch per TB = 128 unknowns.  CTA 0 stages the 128 x 128 diagonal block in shared memory and solves it
-// (32-wide chunks: warp-shuffle substitution on pre-scaled columns, one shuffle + one DFMA per unknown on the
-// critical path), then publishes the 128 new unknowns behind a flag.  Every other CTA owns a tile of the
-// 128-wide strip that the new unknowns update; it issues ALL its loads (32 per thread) before it looks at the
-// flag, so the HBM traffic of the strip -- the 4 N^2 bytes per sweep that bound this operation -- streams in
-// while the diagonal block is being solved.
+// Single right-hand-side solves  L w = b  (forward) and  L^T x = w  (backward): persistent sweep kernels in trsv.cu.
 // ============================================================================================
-constexpr int TB = 128;
-constexpr int TB_P = TB + 1;
-constexpr int TRSV_SMEM = (TB * TB_P + 2 * TB) * 8;
-
-__device__ __forceinline__ void wait_flag(unsigned* flag, unsigned epoch) {
-  if (threadIdx.x == 0) {
-    unsigned spins = 0;
-    while (*reinterpret_cast<volatile unsigned*>(flag) != epoch) {
-      __nanosleep(40);
-      if (++spins > (1u << 26)) break;       // seconds: never hang the GPU
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-template <bool FWD>
-__global__ void __launch_bounds__(256)
-trsv_step_kernel(const double* __restrict__ L, int64_t ld, int64_t N, int64_t k0, int w, double* __restrict__ b,
-                 unsigned slot, unsigned epoch) {
-  extern __shared__ __align__(16) double vsm[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  unsigned* flag = &g_panel_flags[slot];
-
-  if (blockIdx.x == 0) {
-    // ---- diagonal block ---------------------------------------------------------------------
-    double* Ls = vsm;                 // TB x TB_P, identity padded
-    double* xs = vsm + TB * TB_P;     // right-hand side -> unknowns
-    double* dinv = xs + TB;
-    const double* Lb = L + k0 * ld + k0;
-#pragma unroll 8
-    for (int idx = tid; idx < TB * TB; idx += 256) {
-      const int r = idx / TB, c = idx % TB;
-      Ls[r * TB_P + c] = (r < w && c <= r) ? Lb[(int64_t)r * ld + c] : (r == c ? 1.0 : 0.0);
-    }
-    if (tid < TB) xs[tid] = (tid < w) ? b[k0 + tid] : 0.0;
-    __syncthreads();
-    if (tid < TB) dinv[tid] = 1.0 / Ls[tid * TB_P + tid];
-    __syncthreads();
-    for (int s = 0; s < TB / 32; ++s) {
-      const int ch = FWD ? s : TB / 32 - 1 - s;
-      const int c0 = ch * 32;
-      if (warp == 0) {
-        // unscaled unknowns u_i = x_i L_ii; coefficients pre-scaled by 1 / L_kk of the pivot they multiply
-        double coef[32];
-        double u = xs[c0 + lane];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          // forward : u_lane -= (L[lane][k] / L[k][k]) u_k, k < lane;  backward: u_lane -= (L[k][lane] / L[k][k]) u_k, k > lane
-          const double l = FWD ? Ls[(c0 + lane) * TB_P + c0 + k] : Ls[(c0 + k) * TB_P + c0 + lane];
-          const bool on = FWD ? (k < lane) : (k > lane);
-          coef[k] = on ? l * dinv[c0 + k] : 0.0;
-        }
-#pragma unroll
-        for (int s2 = 0; s2 < 32; ++s2) {
-          const int k = FWD ? s2 : 31 - s2;
-          const double uk = __shfl_sync(0xffffffffu, u, k);
-          u = fma(-coef[k], uk, u);
-        }
-        xs[c0 + lane] = u * dinv[c0 + lane];
-      }
-      __syncthreads();
-      // the other unknowns of the block absorb the 32 new values
-      const bool mine = FWD ? (tid >= c0 + 32 && tid < TB) : (tid < c0);
-      if (mine) {
-        double a0 = 0.0, a1 = 0.0;
-#pragma unroll 8
-        for (int k = 0; k < 32; k += 2) {
-          const double l0 = FWD ? Ls[tid * TB_P + c0 + k] : Ls[(c0 + k) * TB_P + tid];
-          const double l1 = FWD ? Ls[tid * TB_P + c0 + k + 1] : Ls[(c0 + k + 1) * TB_P + tid];
-          a0 = fma(l0, xs[c0 + k], a0);
-          a1 = fma(l1, xs[c0 + k + 1], a1);
-        }
-        xs[tid] -= (a0 + a1);
-      }
-      __syncthreads();
-    }
-    if (tid < w) b[k0 + tid] = xs[tid];
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) atomicExch(flag, epoch);
-    return;
-  }
-
-  double* xs = vsm;             // TB unknowns
-  double* red = vsm + TB;       // partial sums
-  const int64_t tile = blockIdx.x - 1;
-  if (FWD) {
-    // rows r0 .. r0+63 below the block; warp -> 8 rows, lane -> columns 4 lane .. 4 lane + 3 of the strip
-    const int64_t r0 = k0 + w + tile * 64 + warp * 8;
-    const bool vec = ((ld & 1) == 0) && ((((uintptr_t)L) & 15) == 0);
-    double2 v[8][2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int64_t r = r0 + i;
-      const double* p = L + r * ld + k0 + 4 * lane;
-      v[i][0] = v[i][1] = make_double2(0.0, 0.0);
-      if (r < N) {
-        if (vec && 4 * lane + 3 < w) {
-          v[i][0] = *reinterpret_cast<const double2*>(p);
-          v[i][1] = *reinterpret_cast<const double2*>(p + 2);
-        } else {
-          if (4 * lane < w) v[i][0].x = p[0];
-          if (4 * lane + 1 < w) v[i][0].y = p[1];
-          if (4 * lane + 2 < w) v[i][1].x = p[2];
-          if (4 * lane + 3 < w) v[i][1].y = p[3];
-        }
-      }
-    }
-    wait_flag(flag, epoch);
-    if (tid < TB) xs[tid] = (tid < w) ? __ldcg(b + k0 + tid) : 0.0;
-    __syncthreads();
-    const double x0 = xs[4 * lane], x1 = xs[4 * lane + 1], x2 = xs[4 * lane + 2], x3 = xs[4 * lane + 3];
-    double sums[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sums[i] = fma(v[i][0].x, x0, v[i][0].y * x1) + fma(v[i][1].x, x2, v[i][1].y * x3);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) sums[i] += __shfl_xor_sync(0xffffffffu, sums[i], o);
-    if (lane < 8) {
-      double sv = sums[0];
-#pragma unroll
-      for (int i = 1; i < 8; ++i) sv = (lane == i) ? sums[i] : sv;
-      const int64_t r = r0 + lane;
-      if (r < N) b[r] -= sv;
-    }
-  } else {
-    // columns j0 .. j0+63 left of the block; thread (c = tid % 64, rg = tid / 64) holds rows 32 rg .. 32 rg + 31
-    const int c = tid & 63, rg = tid >> 6;
-    const int64_t j = tile * 64 + c;
-    double v[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int r = rg * 32 + i;
-      v[i] = (r < w && j < k0) ? L[(k0 + r) * ld + j] : 0.0;
-    }
-    wait_flag(flag, epoch);
-    if (tid < TB) xs[tid] = (tid < w) ? __ldcg(b + k0 + tid) : 0.0;
-    __syncthreads();
-    double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      a0 = fma(v[i], xs[rg * 32 + i], a0);
-      a1 = fma(v[i + 1], xs[rg * 32 + i + 1], a1);
-    }
-    red[rg * 64 + c] = a0 + a1;
-    __syncthreads();
-    if (tid < 64 && j < k0) b[j] -= (red[c] + red[64 + c]) + (red[128 + c] + red[192 + c]);
-  }
-}
-
-template <bool FWD>
-static int trsv_sweep(const double* L, int64_t N, int64_t ld, double* b, cudaStream_t st) {
-  static TgpPerDeviceOnce attr_once;
-  if (tgp_first_use_on_device(attr_once)) {
-    TGP_CUDA(cudaFuncSetAttribute(trsv_step_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TRSV_SMEM));
-  }
-  const int64_t nblk = tgp_cdiv(N, TB);
-  for (int64_t s = 0; s < nblk; ++s) {
-    const int64_t kb = FWD ? s : nblk - 1 - s;
-    const int64_t k0 = kb * TB;
-    const int w = (int)((N - k0 < TB) ? (N - k0) : TB);
-    const int64_t other = FWD ? (N - k0 - w) : k0;          // rows below / columns left of the block
-    const unsigned epoch = next_flag_epoch();
-    trsv_step_kernel<FWD><<<(unsigned)(1 + tgp_cdiv(other, 64)), 256, TRSV_SMEM, st>>>(L, ld, N, k0, w, b,
-                                                                                     epoch % PL_NFLAGS, epoch);
-    TGP_LAUNCH_CHECK();
-  }
-  return TGP_OK;
-}
-
-static int trsv_forward(const double* L, int64_t N, int64_t ld, double* b, cudaStream_t st) {
-  return trsv_sweep<true>(L, N, ld, b, st);
-}
+int tgp_trsv_sweeps(const double* L, int64_t N, int64_t ld, double* b, int which, cudaStream_t st);
 static int trsv_backward(const double* L, int64_t N, int64_t ld, double* b, cudaStream_t st) {
-  return trsv_sweep<false>(L, N, ld, b, st);
+  return tgp_trsv_sweeps(L, N, ld, b, 2, st);
 }
 
 extern "C" int tgp_potrs_vec(const double* L, int64_t N, int64_t ld, double* b, void* stream) {
@@ -1257,9 +1077,7 @@ extern "C" int tgp_potrs_vec(const double* L, int64_t N, int64_t ld, double* b, 
   if (N == 0) return TGP_OK;
   TGP_CHECK_ARG(L && b, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = trsv_forward(L, N, ld, b, st);
-  if (rc) return rc;
-  return trsv_backward(L, N, ld, b, st);
+  return tgp_trsv_sweeps(L, N, ld, b, 3, st);   // forward, then backward (one workspace, one set of inverses)
 }
 
 // ============================================================================================
