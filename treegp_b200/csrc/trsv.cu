@@ -3,37 +3,59 @@
 //
 // The operation is HBM-bound: each sweep reads the 4 N^2-byte triangle once.  ONE
 // persistent kernel per sweep, one CTA per SM, launched cooperatively (all CTAs co-resident, so waiting on
-// another CTA's flag always makes progress -- no assumption about dispatch order):
+// another CTA's result always makes progress -- no assumption about dispatch order):
 //
 //  * the triangle is cut into 64 x 64 tiles; block row k ("slab") is owned by CTA k mod G, which keeps the slab's
 //    64 partial sums in shared memory and accumulates them in a FIXED order (column blocks ascending): the
 //    result is deterministic, bit-identical from run to run;
-//  * a CTA walks the column blocks j = 0, 1, ... and, for each, its slabs k > j.  The tiles of this sequence are
-//    streamed into a 5-stage shared-memory ring by bulk async copies (cp.async.bulk, one 512-byte row segment per
-//    thread, completion on an mbarrier) issued 4 tiles ahead: the tile data do not depend on the unknowns, so HBM
-//    keeps streaming while a CTA waits for a dependency;
-//  * the only serial chain: when x_j is published, the owner of slab j + 1 applies its last tile and multiplies by
-//    the INVERSE of the 64 x 64 diagonal block (computed beforehand for all blocks by trsv_diag_inv_kernel,
-//    prefetched into shared memory) -- two 64 x 64 mat-vecs per 64 unknowns instead of a 64-step substitution.
-//    Publication is the payload itself: the 64 unknowns are stored into a buffer pre-filled with an all-ones
-//    pattern and every waiting thread polls its own word, i.e. ONE L2 round trip per chain step (no flag + fence
-//    + second load).
+//  * a CTA walks the column blocks j = 0, 1, ... and, for each, its slabs k >= j + 2.  The tiles of this sequence
+//    are streamed into a 4-stage shared-memory ring by bulk async copies (cp.async.bulk, one 512-byte row segment
+//    per thread, completion on an mbarrier) issued 3 tiles ahead: the tile data do not depend on the unknowns, so
+//    HBM keeps streaming while a CTA waits for a dependency.  The unknowns are fetched in windows of up to four
+//    column blocks, so the per-column bookkeeping (wait, two barriers, one L2 read) is paid once per window;
+//  * the serial chain.  For every diagonal block a pre-pass (trsv_prep_kernel) computes D_k = L_kk^-1 and the
+//    product W_k = D_k L_{k,k-1} (forward; M_k = L_{k+1,k} D_k for the backward sweep), so that
+//        x_k = D_k (b_k - sum_{j<k-1} L_kj x_j)  -  W_k x_{k-1} :
+//    the first term is ready before x_{k-1} exists, and the step on the critical path is ONE 64 x 64 mat-vec
+//    between "x_{k-1} seen" and "x_k published" instead of a 64-step substitution;
+//  * publication is the payload itself: the 64 unknowns are stored into a buffer pre-filled with an all-ones
+//    pattern and the waiting threads poll their own words, i.e. one L2 round trip per chain step (no flag + fence
+//    + second load).  Only the CTA whose slab is next polls with all 64 threads; the others poll with one.
 //
 // The backward sweep is the same kernel on the mirrored index set (block i' = nb-1-i) with transposed tile
-// products.  Workspace (inverse diagonal blocks + publication buffers) comes from the stream-ordered allocator and is freed
-// on the stream: nothing persists.  A wait that times out (cannot happen with co-resident CTAs; guards
-// against a lost launch) sets a sticky device error word that tgp_device_error() reports.
+// products.  Workspace (inverses, products, publication buffers) comes from a library-private stream-ordered
+// memory pool and is returned to it on the stream.  A wait that times out (cannot happen with co-resident CTAs;
+// guards against a lost launch) sets a sticky device error word that tgp_device_error() reports.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "tgp_common.cuh"
 
 constexpr int TS = 64;                 // tile edge = diagonal block = unknowns per chain step
 constexpr int TS_P = TS + 2;           // shared-memory row pitch in doubles (528 B: 16-byte aligned rows)
-constexpr int TS_STAGES = 5;
+constexpr int TS_STAGES = 4;
 constexpr int TS_THREADS = 256;
 constexpr int TS_TILE_D = TS * TS_P;   // doubles per staged tile
+constexpr int TS_WIN = 4;              // column blocks of unknowns fetched per wait
+constexpr int TS_NEAR = 6;             // ... but one at a time this close to the CTA's own next chain step
 
 __device__ int g_tgp_device_error = 0;
+
+#ifdef TGP_TRSV_TIMING
+// debug build (tools/trsv_timing.py): globaltimer stamps of the serial chain, per block: [0] unknowns of the
+// previous block seen, [1] (unused), [2] own unknowns published
+__device__ unsigned long long g_trsv_stamps[3 * 4096];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+extern "C" int tgp_debug_trsv_stamps(unsigned long long* host, int n) {
+  return cudaMemcpyFromSymbol(host, g_trsv_stamps, sizeof(unsigned long long) * n) == cudaSuccess ? 0 : -1;
+}
+#define TRSV_STAMP(kp, which) do { if (tid == 0 && (kp) < 4096) g_trsv_stamps[3 * (kp) + (which)] = gtime(); } while (0)
+#else
+#define TRSV_STAMP(kp, which) do { } while (0)
+#endif
 
 extern "C" int tgp_device_error(int reset) {
   int v = 0;
@@ -81,38 +103,96 @@ __device__ __forceinline__ double ld_relaxed_f64(const double* p) {
 __device__ __forceinline__ void st_relaxed_f64(double* p, double v) {
   asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+__device__ __forceinline__ bool unpublished(double v) { return __double_as_longlong(v) == -1ll; }
 
-// ---- inverse of every 64 x 64 diagonal block ---------------------------------------------------
-// One CTA (64 threads) per block; thread c solves L z = e_c by forward substitution from a shared-memory copy.
-// Output block: dense 64 x 64, row-major, zero above the diagonal, identity in the padding of a short last block.
-__global__ void __launch_bounds__(TS)
-trsv_diag_inv_kernel(const double* __restrict__ L, int64_t ld, int64_t N, double* __restrict__ dinv) {
-  extern __shared__ __align__(16) double dism[];
-  double (*Ls)[TS + 1] = reinterpret_cast<double (*)[TS + 1]>(dism);
-  double (*Zs)[TS + 1] = reinterpret_cast<double (*)[TS + 1]>(dism + TS * (TS + 1));
-  const int64_t k0 = (int64_t)blockIdx.x * TS;
+// ---- pre-pass: inverse of every 64 x 64 diagonal block and its product with the neighbouring tile -------
+// One CTA (256 threads) per block k.  dinv[k] = L_kk^-1 (dense 64 x 64 row-major, zero above the diagonal,
+// identity in the padding of a short last block); wf[k] = dinv[k] . L[blk k, blk k-1] (k >= 1, forward sweep);
+// wb[k] = L[blk k+1, blk k] . dinv[k] (k <= nb-2, backward sweep; rows beyond N are zero).
+constexpr int TP_P = TS + 1;
+constexpr int TP_SMEM = 3 * TS * TP_P * 8;
+__global__ void __launch_bounds__(256)
+trsv_prep_kernel(const double* __restrict__ L, int64_t ld, int64_t N, int nb, double* __restrict__ dinv,
+                 double* __restrict__ wf, double* __restrict__ wb) {
+  extern __shared__ __align__(16) double psm[];
+  double (*Lk)[TP_P] = reinterpret_cast<double (*)[TP_P]>(psm);
+  double (*Z)[TP_P] = reinterpret_cast<double (*)[TP_P]>(psm + TS * TP_P);
+  double (*T)[TP_P] = reinterpret_cast<double (*)[TP_P]>(psm + 2 * TS * TP_P);
+  const int tid = threadIdx.x;
+  const int k = blockIdx.x;
+  const int64_t k0 = (int64_t)k * TS;
   const int w = (int)((N - k0 < TS) ? (N - k0) : TS);
-  const int c = threadIdx.x;
-  for (int r = 0; r < TS; ++r) {
+  for (int i = tid; i < TS * TS; i += 256) {
+    const int r = i >> 6, c = i & 63;
     double v = (r == c) ? 1.0 : 0.0;
     if (r < w && c <= r) v = L[(k0 + r) * ld + k0 + c];
-    Ls[r][c] = v;
+    Lk[r][c] = v;
+    Z[r][c] = 0.0;
   }
   __syncthreads();
-  // column c of the inverse: z_r = (delta_rc - sum_{m<r} L_rm z_m) / L_rr
-  for (int r = 0; r < TS; ++r) {
-    double s0 = (r == c) ? 1.0 : 0.0, s1 = 0.0;
-    int m = c;
-    for (; m + 1 < r; m += 2) {
-      s0 = fma(-Ls[r][m], Zs[m][c], s0);
-      s1 = fma(-Ls[r][m + 1], Zs[m + 1][c], s1);
+  // Z = Lk^-1 row by row: Z[r][c] = (delta_rc - sum_{m<r} Lk[r][m] Z[m][c]) / Lk[r][r]; 4 adjacent lanes share a column
+  {
+    const int c = tid >> 2, part = tid & 3;
+    for (int r = 0; r < TS; ++r) {
+      double s = 0.0;
+      for (int m = part; m < r; m += 4) s = fma(Lk[r][m], Z[m][c], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (part == 0 && c <= r) Z[r][c] = (((r == c) ? 1.0 : 0.0) - s) / Lk[r][r];
+      __syncthreads();
     }
-    if (m < r) s0 = fma(-Ls[r][m], Zs[m][c], s0);
-    Zs[r][c] = (r >= c) ? (s0 + s1) / Ls[r][r] : 0.0;
   }
-  __syncthreads();
-  double* out = dinv + (int64_t)blockIdx.x * TS * TS;
-  for (int r = 0; r < TS; ++r) out[r * TS + c] = Zs[r][c];
+  double* out = dinv + (int64_t)k * TS * TS;
+  for (int i = tid; i < TS * TS; i += 256) out[i] = Z[i >> 6][i & 63];
+  const int r4 = (tid >> 4) * 4, c4 = (tid & 15) * 4;
+  if (wf != nullptr && k >= 1) {
+    // T = L[blk k, blk k-1] (rows beyond N zero);  W = Z T
+    for (int i = tid; i < TS * TS; i += 256) {
+      const int r = i >> 6, c = i & 63;
+      T[r][c] = (r < w) ? L[(k0 + r) * ld + (k0 - TS) + c] : 0.0;
+    }
+    __syncthreads();
+    double a[4][4] = {};
+    for (int m = 0; m < TS; ++m) {
+      double zr[4], tc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { zr[i] = Z[r4 + i][m]; tc[i] = T[m][c4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[i][j] = fma(zr[i], tc[j], a[i][j]);
+    }
+    double* o = wf + (int64_t)k * TS * TS;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[(r4 + i) * TS + c4 + j] = a[i][j];
+    __syncthreads();
+  }
+  if (wb != nullptr && k + 1 < nb) {
+    // T = L[blk k+1, blk k] (rows beyond N zero);  M = T Z
+    const int w1 = (int)((N - (k0 + TS) < TS) ? (N - (k0 + TS)) : TS);
+    for (int i = tid; i < TS * TS; i += 256) {
+      const int r = i >> 6, c = i & 63;
+      T[r][c] = (r < w1) ? L[(k0 + TS + r) * ld + k0 + c] : 0.0;
+    }
+    __syncthreads();
+    double a[4][4] = {};
+    for (int m = 0; m < TS; ++m) {
+      double tr[4], zc[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { tr[i] = T[r4 + i][m]; zc[i] = Z[m][c4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[i][j] = fma(tr[i], zc[j], a[i][j]);
+    }
+    double* o = wb + (int64_t)k * TS * TS;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[(r4 + i) * TS + c4 + j] = a[i][j];
+  }
 }
 
 // ---- the sweep ---------------------------------------------------------------------------------
@@ -120,14 +200,15 @@ struct TrsvParams {
   const double* L;
   int64_t ld, N;
   double* b;             // right-hand side in, unknowns out
-  const double* dinv;    // nb blocks of 64 x 64
+  const double* dinv;    // nb blocks of 64 x 64: inverse diagonal blocks
+  const double* wmat;    // nb blocks of 64 x 64: W_k (forward) or M_k (backward)
   double* xpub;          // nb * 64 words, all-ones on entry: block kp's unknowns are published at xpub + 64 kp
   int nb, G, aligned;
 };
 
 // position in a CTA's tile sequence: column block j (primed index), slab index m among the CTA's slabs
 struct TileIter {
-  int j, m, m0;          // m0 = first slab of this CTA with k > j
+  int j, m, m0;          // m0 = first slab of this CTA with k >= j + 2
   bool done;
 };
 
@@ -136,10 +217,12 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
 trsv_sweep_kernel(TrsvParams P) {
   extern __shared__ __align__(128) unsigned char smraw[];
   double* ring = reinterpret_cast<double*>(smraw);                 // TS_STAGES tiles
-  double* dtile = ring + TS_STAGES * TS_TILE_D;                    // inverse diagonal block of the next solve
-  double* xs = dtile + TS_TILE_D;                                  // unknowns of the current column block
-  double* vs = xs + TS;                                            // right-hand side of the current solve
-  double* bs = vs + TS;                                            // b of the next solve (prefetched)
+  double* dtile = ring + TS_STAGES * TS_TILE_D;                    // D_k of the next chain step
+  double* wtile = dtile + TS_TILE_D;                               // W_k / M_k of the next chain step
+  double* xs = wtile + TS_TILE_D;                                  // window of unknowns: TS_WIN column blocks
+  double* xc = xs + TS_WIN * TS;                                   // unknowns the chain step waits for
+  double* vs = xc + TS;                                            // b_k - partial sums
+  double* bs = vs + TS;                                            // b of the next chain step (prefetched)
   double* red = bs + TS;                                           // 4 x 64 partials (backward)
   uint64_t* full = reinterpret_cast<uint64_t*>(red + 4 * TS);      // TS_STAGES + 1 barriers
   double* acc = reinterpret_cast<double*>(full + TS_STAGES + 2);   // [slabs of this CTA][64]
@@ -165,22 +248,26 @@ trsv_sweep_kernel(TrsvParams P) {
   for (int i = tid; i < M * TS; i += TS_THREADS) acc[i] = 0.0;
   __syncthreads();
 
+  // streamed tiles of slab k: column blocks 0 .. k-2 (block k-1 enters through W_k in the chain step)
+  auto settle = [&](TileIter& it) {
+    while (it.m0 < M && c + it.m0 * G < it.j + 2) ++it.m0;
+    it.m = it.m0;
+    if (it.m0 >= M) it.done = true;
+  };
   auto advance = [&](TileIter& it) {
     if (it.done) return;
     ++it.m;
     if (it.m >= M) {
       ++it.j;
-      while (it.m0 < M && c + it.m0 * G <= it.j) ++it.m0;
-      it.m = it.m0;
-      if (it.m0 >= M || it.j >= nb - 1) it.done = true;
+      settle(it);
     }
   };
   auto start = [&]() {
     TileIter it;
     it.j = 0;
-    it.m0 = (c == 0) ? 1 : 0;       // slab 0 has no tiles
-    it.m = it.m0;
-    it.done = (it.m0 >= M) || nb < 2;
+    it.m0 = 0;
+    it.done = false;
+    settle(it);
     return it;
   };
   // issue the bulk copies of one tile into ring stage `s` (threads 0..63: one row each)
@@ -191,16 +278,17 @@ trsv_sweep_kernel(TrsvParams P) {
     if (tid == 0) mbar_expect_tx(&full[s], (uint32_t)rows * TS * 8);
     if (tid < rows) bulk_g2s(ring + s * TS_TILE_D + tid * TS_P, tile_src(kp, it.j) + (int64_t)tid * ld, TS * 8, &full[s]);
   };
-  // prefetch what the next solve (slab index ms) needs: inverse diagonal block (bulk) and its right-hand side
+  // prefetch what the next chain step (slab index ms) needs: D_k, W_k (bulk) and its right-hand side
   auto prefetch_solve = [&](int ms) {
     if (ms >= M) return;
     const int kp = c + ms * G;
     const int64_t r0 = blk0(kp);
     const int w = blkw(kp);
-    const double* src = P.dinv + (int64_t)(FWD ? kp : nb - 1 - kp) * TS * TS;
-    if (tid == 0) mbar_expect_tx(&full[TS_STAGES], TS * TS * 8);
+    const int64_t blk = (int64_t)(FWD ? kp : nb - 1 - kp) * TS * TS;
+    if (tid == 0) mbar_expect_tx(&full[TS_STAGES], (kp >= 1 ? 2u : 1u) * TS * TS * 8);
     if (tid < TS) {
-      bulk_g2s(dtile + tid * TS_P, src + tid * TS, TS * 8, &full[TS_STAGES]);
+      bulk_g2s(dtile + tid * TS_P, P.dinv + blk + tid * TS, TS * 8, &full[TS_STAGES]);
+      if (kp >= 1) bulk_g2s(wtile + tid * TS_P, P.wmat + blk + tid * TS, TS * 8, &full[TS_STAGES]);
       bs[tid] = (tid < w) ? P.b[r0 + tid] : 0.0;
     }
   };
@@ -242,33 +330,50 @@ trsv_sweep_kernel(TrsvParams P) {
       }
       red[q * TS + cc] = (s0 + s1) + (s2 + s3);
       __syncthreads();
-      return (tid < TS) ? (red[tid] + red[TS + tid]) + (red[2 * TS + tid] + red[3 * TS + tid]) : 0.0;
+      const double sv = (tid < TS) ? (red[tid] + red[TS + tid]) + (red[2 * TS + tid] + red[3 * TS + tid]) : 0.0;
+      __syncthreads();                             // red may be rewritten by the next product
+      return sv;
     }
   };
 
   uint32_t dphase = 0;
-  // Solve slab index ms given the finished partial sums `accv` (owner threads): x = Dinv (b - acc).  The unknowns
-  // are PUBLISHED as the payload itself: every waiting thread polls its own word of xpub until it differs from
-  // the all-ones pattern the workspace was filled with -- one L2 round trip per chain step, no flag, no fence.
-  auto solve = [&](int ms, double accv) {
+  // Chain step of slab index ms (block kp): x_k = D_k (b_k - acc) - W_k x_{k-1}.  The first term is formed before
+  // x_{k-1} is waited for; between "x_{k-1} seen" and "x_k published" there is one mat-vec.
+  auto chain_step = [&](int ms) {
     const int kp = c + ms * G;
     const int64_t r0 = blk0(kp);
     const int w = blkw(kp);
-    if (owner) vs[idx] = (idx < w) ? bs[idx] - accv : 0.0;
+    if (owner) vs[idx] = (idx < w) ? bs[idx] - acc[ms * TS + idx] : 0.0;
     mbar_wait(&full[TS_STAGES], dphase);
     dphase ^= 1;
     __syncthreads();
     double xv = matvec(dtile, vs, TS);
+    if (kp >= 1) {
+      const double* src = P.xpub + (int64_t)(kp - 1) * TS;
+      if (tid < TS) {
+        double v = ld_relaxed_f64(src + tid);
+        unsigned spins = 0;
+        while (unpublished(v)) {
+          if (++spins > (1u << 25)) { atomicExch(&g_tgp_device_error, 1); break; }
+          v = ld_relaxed_f64(src + tid);
+        }
+        xc[tid] = v;
+      }
+      __syncthreads();
+      TRSV_STAMP(kp, 0);
+      xv -= matvec(wtile, xc, tile_rows(kp, kp - 1));
+    }
     if (owner) {
-      if (__double_as_longlong(xv) == -1ll) xv = __longlong_as_double(0x7ff8000000000000ll);  // never publish the sentinel
+      if (unpublished(xv)) xv = __longlong_as_double(0x7ff8000000000000ll);   // never publish the sentinel
       st_relaxed_f64(P.xpub + (int64_t)kp * TS + idx, xv);
       if (idx < w) P.b[r0 + idx] = xv;
     }
-    __syncthreads();                               // dtile, bs, vs are free again
+    TRSV_STAMP(kp, 2);
+    __syncthreads();                               // dtile, wtile, bs, vs, xc are free again
     prefetch_solve(ms + 1);
   };
 
-  // ---- prologue: prefetch the first solve and the first tiles ------------------------------------
+  // ---- prologue: prefetch the first chain step's inputs and the first tiles --------------------------
   prefetch_solve(0);
   TileIter pf = start();
   int pf_stage = 0;
@@ -279,46 +384,46 @@ trsv_sweep_kernel(TrsvParams P) {
       pf_stage = (pf_stage + 1) % TS_STAGES;
     }
   }
-  int ms_next = 0;                                // next slab (index) this CTA has to solve
-  if (c == 0) {
-    __syncthreads();
-    solve(0, 0.0);
-    ms_next = 1;
-  }
+  __syncthreads();
 
   TileIter it = start();
+  int ms_next = 0;                                 // next slab (index) whose chain step this CTA owes
   int stage = 0;
   uint32_t phase = 0;                              // parity of ring stage 0's current fill
-  int cur_j = -1;
-  while (!it.done) {
-    if (it.j != cur_j) {
-      // ---- new column block: wait until its unknowns are published, bring them into shared memory ----
-      cur_j = it.j;
-      __syncthreads();                             // everyone is done with the previous xs
-      // Only the CTA that owns slab j + 1 is on the serial chain: its 64 threads poll their own words back to
-      // back.  Every other CTA has streaming work queued behind this column and polls lazily with ONE thread
-      // (thousands of threads hammering the same 512 bytes would delay the very store they wait for).
-      const bool urgent = (c + it.m * G == cur_j + 1);
-      const double* src = P.xpub + (int64_t)cur_j * TS;
-      if (!urgent) {
-        if (tid == 0) {
-          unsigned spins = 0;
-          while (__double_as_longlong(ld_relaxed_f64(src)) == -1ll) {
-            __nanosleep(spins < 8u ? 100 : 400);
-            if (++spins > (1u << 23)) { atomicExch(&g_tgp_device_error, 1); break; }
-          }
+  int win0 = 0, wincnt = 0;                        // column blocks currently held in xs
+  for (;;) {
+    const int k_next = (ms_next < M) ? c + ms_next * G : 0x7fffffff;
+    if (ms_next < M && (it.done || it.j >= k_next - 1)) {
+      chain_step(ms_next);
+      ++ms_next;
+      continue;
+    }
+    if (it.done) break;
+    if (it.j < win0 || it.j >= win0 + wincnt) {
+      // ---- fetch a new window of unknowns: column blocks it.j .. it.j + cnt - 1 (all needed before k_next - 1) ----
+      int cnt = k_next - 1 - it.j;                 // >= 1 here
+      cnt = (cnt <= TS_NEAR) ? 1 : (cnt < TS_WIN ? cnt : TS_WIN);
+      __syncthreads();                             // everyone is done with the previous window
+      const double* src = P.xpub + (int64_t)it.j * TS;
+      if (tid == 0) {                              // blocks are published in order: wait for the last one, lazily
+        unsigned spins = 0;
+        while (unpublished(ld_relaxed_f64(src + (cnt - 1) * TS))) {
+          if (spins > 16u) __nanosleep(32);
+          if (++spins > (1u << 23)) { atomicExch(&g_tgp_device_error, 1); break; }
         }
-        __syncthreads();
       }
-      if (tid < TS) {
+      __syncthreads();
+      if (tid < cnt * TS) {
         double v = ld_relaxed_f64(src + tid);
         unsigned spins = 0;
-        while (__double_as_longlong(v) == -1ll) {
+        while (unpublished(v)) {
           if (++spins > (1u << 25)) { atomicExch(&g_tgp_device_error, 1); break; }
           v = ld_relaxed_f64(src + tid);
         }
         xs[tid] = v;
       }
+      win0 = it.j;
+      wincnt = cnt;
       __syncthreads();
     }
     const int kp = c + it.m * G;
@@ -335,17 +440,9 @@ trsv_sweep_kernel(TrsvParams P) {
       }
       __syncthreads();
     }
-    const double sv = matvec(T, xs, rows);
-    const double accv = owner ? acc[it.m * TS + idx] + sv : 0.0;
-    const bool solve_now = (kp == it.j + 1) && (it.m == ms_next);   // that was the slab's last tile
-    if (!solve_now) {
-      if (owner) acc[it.m * TS + idx] = accv;
-      __syncthreads();                             // the ring stage is free again
-    }
-    if (solve_now) {
-      solve(ms_next, accv);                        // (its first __syncthreads also frees the ring stage)
-      ++ms_next;
-    }
+    const double sv = matvec(T, xs + (it.j - win0) * TS, rows);
+    if (owner) acc[it.m * TS + idx] += sv;
+    __syncthreads();                               // the ring stage is free again
     if (!pf.done) {                                // refill the ring, TS_STAGES - 1 tiles ahead
       issue(pf, pf_stage);
       advance(pf);
@@ -358,12 +455,10 @@ trsv_sweep_kernel(TrsvParams P) {
 }
 
 static size_t trsv_smem_bytes(int slabs_per_cta) {
-  return (size_t)(TS_STAGES + 1) * TS_TILE_D * 8 + (size_t)(3 * TS + 4 * TS) * 8 + (TS_STAGES + 2) * 8 +
+  return (size_t)(TS_STAGES + 2) * TS_TILE_D * 8 + (size_t)(TS_WIN * TS + 3 * TS + 4 * TS) * 8 + (TS_STAGES + 2) * 8 +
          (size_t)slabs_per_cta * TS * 8;
 }
 
-// Workspace layout: [nb * 64 * 64 doubles: inverse diagonal blocks][2 * nb * 64 doubles: published unknowns of the
-// forward and of the backward sweep, filled with 0xFF bytes = "not yet published"]
 template <bool FWD>
 static int trsv_launch(const TrsvParams& P0, cudaStream_t st) {
   TrsvParams P = P0;
@@ -377,7 +472,29 @@ static int trsv_launch(const TrsvParams& P0, cudaStream_t st) {
   return TGP_OK;
 }
 
-// which = 1: forward only, 2: backward only, 3: both (forward then backward)
+// Library-private stream-ordered pool (one per device) that keeps what it was given: the sweeps' workspace is
+// allocated and freed on the caller's stream at every call without going back to the driver.
+static cudaMemPool_t trsv_pool() {
+  static cudaMemPool_t pools[TGP_MAX_DEVICES] = {};
+  const int dev = tgp_current_device();
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t p = nullptr;
+    if (cudaMemPoolCreate(&p, &props) != cudaSuccess) return nullptr;
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &keep);
+    pools[dev] = p;
+  }
+  return pools[dev];
+}
+
+// Workspace layout: [nb * 4096 doubles: inverse diagonal blocks][nb * 4096: W (forward)][nb * 4096: M (backward)]
+// [2 * nb * 64 doubles: published unknowns of the forward and of the backward sweep, filled with 0xFF bytes =
+// "not yet published"].  which = 1: forward only, 2: backward only, 3: both (forward then backward).
 int tgp_trsv_sweeps(const double* L, int64_t N, int64_t ld, double* b, int which, cudaStream_t st) {
   if (N <= 0) return TGP_OK;
   const int nb = (int)tgp_cdiv(N, TS);
@@ -386,31 +503,40 @@ int tgp_trsv_sweeps(const double* L, int64_t N, int64_t ld, double* b, int which
   P.L = L; P.ld = ld; P.N = N; P.b = b; P.nb = nb;
   P.G = nb < sms ? nb : sms;
   P.aligned = ((ld & 1) == 0) && ((((uintptr_t)L) & 15) == 0);
-  const size_t dinv_bytes = (size_t)nb * TS * TS * 8;
-  const size_t flag_bytes = (size_t)2 * nb * TS * sizeof(double);
+  const size_t blk_d = (size_t)nb * TS * TS;
+  const size_t pub_d = (size_t)2 * nb * TS;
+  cudaMemPool_t pool = trsv_pool();
+  if (!pool) {
+    tgp_set_error("tgp_trsv_sweeps: cudaMemPoolCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return TGP_ERR_CUDA;
+  }
   void* ws = nullptr;
-  TGP_CUDA(cudaMallocAsync(&ws, dinv_bytes + flag_bytes, st));
+  TGP_CUDA(cudaMallocFromPoolAsync(&ws, (3 * blk_d + pub_d) * sizeof(double), pool, st));
   double* dinv = reinterpret_cast<double*>(ws);
-  double* xpub = dinv + (size_t)nb * TS * TS;
+  double* wf = dinv + blk_d;
+  double* wb = wf + blk_d;
+  double* xpub = wb + blk_d;
   int rc = TGP_OK;
   do {
-    if (cudaMemsetAsync(xpub, 0xFF, flag_bytes, st) != cudaSuccess) { rc = TGP_ERR_CUDA; break; }
-    static TgpPerDeviceOnce inv_once;
-    constexpr int inv_smem = 2 * TS * (TS + 1) * 8;
-    if (tgp_first_use_on_device(inv_once) &&
-        cudaFuncSetAttribute(trsv_diag_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, inv_smem) != cudaSuccess) {
+    if (cudaMemsetAsync(xpub, 0xFF, pub_d * sizeof(double), st) != cudaSuccess) { rc = TGP_ERR_CUDA; break; }
+    static TgpPerDeviceOnce prep_once;
+    if (tgp_first_use_on_device(prep_once) &&
+        cudaFuncSetAttribute(trsv_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM) != cudaSuccess) {
       rc = TGP_ERR_CUDA;
       break;
     }
-    trsv_diag_inv_kernel<<<(unsigned)nb, TS, inv_smem, st>>>(L, ld, N, dinv);
+    trsv_prep_kernel<<<(unsigned)nb, 256, TP_SMEM, st>>>(L, ld, N, nb, dinv, (which & 1) ? wf : nullptr,
+                                                         (which & 2) ? wb : nullptr);
     if (cudaGetLastError() != cudaSuccess) { rc = TGP_ERR_CUDA; break; }
     P.dinv = dinv;
     if (which & 1) {
+      P.wmat = wf;
       P.xpub = xpub;
       rc = trsv_launch<true>(P, st);
       if (rc) break;
     }
     if (which & 2) {
+      P.wmat = wb;
       P.xpub = xpub + (size_t)nb * TS;
       rc = trsv_launch<false>(P, st);
       if (rc) break;
@@ -420,3 +546,9 @@ int tgp_trsv_sweeps(const double* L, int64_t N, int64_t ld, double* b, int which
   cudaFreeAsync(ws, st);
   return rc;
 }
+
+#ifdef TGP_TRSV_TIMING
+extern "C" int tgp_trsv_only(const double* L, int64_t N, int64_t ld, double* b, int which, void* stream) {
+  return tgp_trsv_sweeps(L, N, ld, b, which, (cudaStream_t)stream);
+}
+#endif
