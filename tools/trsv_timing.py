@@ -29,3 +29,11 @@ for n in (4096, 10000, 40000):
     print("n=%d forward sweep: chain step median %.0f ns (p10 %.0f, p90 %.0f) | previous publish -> seen %.0f ns | seen -> published %.0f ns"
           " | total %.3f ms" % (n, np.median(step), np.percentile(step, 10), np.percentile(step, 90),
           np.median(hop), np.median(comp), (t[-1, 2] - t[0, 0]) * 1e-6))
+    for which, name in ((1, "forward"), (5, "forward, dependencies off (streaming only)"), (2, "backward"), (6, "backward, dependencies off")):
+        ts = []
+        for _ in range(4):
+            bb = b.clone(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); lib.tgp_trsv_only(ws.data_ptr(), n, n, bb.data_ptr(), which, None); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        print("   %-48s %.3f ms  (%.0f GB/s of 4 N^2 bytes)" % (name, min(ts), 4.0 * n * n / min(ts) / 1e6))

@@ -357,14 +357,39 @@ knn_mean_kernel(const double* __restrict__ Xq, int64_t M, const double* __restri
   }
 }
 
+// Any k (n_neighbors > 32): selection by k passes over the grid -- pass t picks the smallest (distance, index) pair
+// that is lexicographically greater than the one picked in pass t - 1.  O(k n0) per query, no per-thread list; the
+// same neighbours, the same order of summation and the same tie rule as the register-list kernel.
+__global__ void __launch_bounds__(256)
+knn_mean_passes_kernel(const double* __restrict__ Xq, int64_t M, const double* __restrict__ X0,
+                       const double* __restrict__ y0, int64_t n0, int ndim, int k, double* __restrict__ out) {
+  const int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (m >= M) return;
+  const double qx = Xq[m * ndim];
+  const double qy = (ndim == 2) ? Xq[m * 2 + 1] : 0.0;
+  double pd = -1.0, s = 0.0;
+  int64_t pi = -1;
+  for (int t = 0; t < k; ++t) {
+    double bd = INFINITY;
+    int64_t bi = -1;
+    for (int64_t n = 0; n < n0; ++n) {
+      const double dx = X0[n * ndim] - qx, dy = ((ndim == 2) ? X0[n * 2 + 1] : 0.0) - qy;
+      const double d = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+      const bool after_prev = (d > pd) || (d == pd && n > pi);
+      if (after_prev && d < bd) { bd = d; bi = n; }   // first index wins among equal distances
+    }
+    if (bi < 0) break;
+    s += y0[bi];
+    pd = bd;
+    pi = bi;
+  }
+  out[m] = s / (double)k;
+}
+
 extern "C" int tgp_knn_mean(const double* Xq, int64_t M, const double* X0, const double* y0, int64_t n0,
                             int32_t ndim, int32_t k, double* out, void* stream) {
   TGP_CHECK_ARG(M >= 0 && n0 >= 1 && (ndim == 1 || ndim == 2), "M/n0/ndim");
   TGP_CHECK_ARG(k >= 1 && k <= n0, "need 1 <= n_neighbors <= number of grid points");
-  if (k > 16) {
-    tgp_set_error("tgp_knn_mean: n_neighbors > 16 is not supported");
-    return TGP_ERR_UNSUPPORTED;
-  }
   if (M == 0) return TGP_OK;
   TGP_CHECK_ARG(Xq && X0 && y0 && out, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
@@ -372,7 +397,9 @@ extern "C" int tgp_knn_mean(const double* Xq, int64_t M, const double* X0, const
   // K = list length compiled in (entries beyond k stay +inf and are never summed... they are: cap by j < k)
   if (k <= 4) knn_mean_kernel<4><<<grid, 256, 0, st>>>(Xq, M, X0, y0, n0, ndim, k, out);
   else if (k <= 8) knn_mean_kernel<8><<<grid, 256, 0, st>>>(Xq, M, X0, y0, n0, ndim, k, out);
-  else knn_mean_kernel<16><<<grid, 256, 0, st>>>(Xq, M, X0, y0, n0, ndim, k, out);
+  else if (k <= 16) knn_mean_kernel<16><<<grid, 256, 0, st>>>(Xq, M, X0, y0, n0, ndim, k, out);
+  else if (k <= 32) knn_mean_kernel<32><<<grid, 256, 0, st>>>(Xq, M, X0, y0, n0, ndim, k, out);
+  else knn_mean_passes_kernel<<<grid, 256, 0, st>>>(Xq, M, X0, y0, n0, ndim, k, out);
   TGP_LAUNCH_CHECK();
   return TGP_OK;
 }

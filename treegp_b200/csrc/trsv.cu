@@ -8,11 +8,11 @@
 //  * the triangle is cut into 64 x 64 tiles; block row k ("slab") is owned by CTA k mod G, which keeps the slab's
 //    64 partial sums in shared memory and accumulates them in a FIXED order (column blocks ascending): the
 //    result is deterministic, bit-identical from run to run;
-//  * a CTA walks the column blocks j = 0, 1, ... and, for each, its slabs k >= j + 2.  The tiles of this sequence
-//    are streamed into a 4-stage shared-memory ring by bulk async copies (cp.async.bulk, one 512-byte row segment
-//    per thread, completion on an mbarrier) issued 3 tiles ahead: the tile data do not depend on the unknowns, so
-//    HBM keeps streaming while a CTA waits for a dependency.  The unknowns are fetched in windows of up to four
-//    column blocks, so the per-column bookkeeping (wait, two barriers, one L2 read) is paid once per window;
+//  * a CTA walks the column blocks in windows of up to four (256 unknowns, fetched with one wait) and applies each
+//    window to all of its unsolved slabs.  The matrix is streamed straight from global memory into registers, GEMV
+//    style: every warp owns eight rows of each slab and reads up to 2 KB contiguous per row with 16-byte loads (32
+//    independent loads in flight per lane), so there is no per-tile barrier and no shared-memory staging on the
+//    streaming path; the warps of a CTA only meet when a new window of unknowns is fetched;
 //  * the serial chain.  For every diagonal block a pre-pass (trsv_prep_kernel) computes D_k = L_kk^-1 and the
 //    product W_k = D_k L_{k,k-1} (forward; M_k = L_{k+1,k} D_k for the backward sweep), so that
 //        x_k = D_k (b_k - sum_{j<k-1} L_kj x_j)  -  W_k x_{k-1} :
@@ -32,11 +32,10 @@
 
 constexpr int TS = 64;                 // tile edge = diagonal block = unknowns per chain step
 constexpr int TS_P = TS + 2;           // shared-memory row pitch in doubles (528 B: 16-byte aligned rows)
-constexpr int TS_STAGES = 4;
 constexpr int TS_THREADS = 256;
 constexpr int TS_TILE_D = TS * TS_P;   // doubles per staged tile
 constexpr int TS_WIN = 4;              // column blocks of unknowns fetched per wait
-constexpr int TS_NEAR = 6;             // ... but one at a time this close to the CTA's own next chain step
+constexpr int TS_NEAR = 4;              // blocks before its own diagonal from which a slab is fed one block at a time
 
 __device__ int g_tgp_device_error = 0;
 
@@ -206,96 +205,61 @@ struct TrsvParams {
   int nb, G, aligned;
 };
 
-// position in a CTA's tile sequence: column block j (primed index), slab index m among the CTA's slabs
-struct TileIter {
-  int j, m, m0;          // m0 = first slab of this CTA with k >= j + 2
-  bool done;
-};
+__device__ __forceinline__ double2 ldg2(const double* p, bool vec) {
+  if (vec) return __ldcs(reinterpret_cast<const double2*>(p));      // streamed once: evict-first
+  return make_double2(__ldcs(p), __ldcs(p + 1));
+}
 
 template <bool FWD>
 __global__ void __launch_bounds__(TS_THREADS, 1)
 trsv_sweep_kernel(TrsvParams P) {
   extern __shared__ __align__(128) unsigned char smraw[];
-  double* ring = reinterpret_cast<double*>(smraw);                 // TS_STAGES tiles
-  double* dtile = ring + TS_STAGES * TS_TILE_D;                    // D_k of the next chain step
+  double* dtile = reinterpret_cast<double*>(smraw);                // D_k of the next chain step
   double* wtile = dtile + TS_TILE_D;                               // W_k / M_k of the next chain step
   double* xs = wtile + TS_TILE_D;                                  // window of unknowns: TS_WIN column blocks
   double* xc = xs + TS_WIN * TS;                                   // unknowns the chain step waits for
   double* vs = xc + TS;                                            // b_k - partial sums
   double* bs = vs + TS;                                            // b of the next chain step (prefetched)
-  double* red = bs + TS;                                           // 4 x 64 partials (backward)
-  uint64_t* full = reinterpret_cast<uint64_t*>(red + 4 * TS);      // TS_STAGES + 1 barriers
-  double* acc = reinterpret_cast<double*>(full + TS_STAGES + 2);   // [slabs of this CTA][64]
+  double* red = bs + TS;                                           // 4 x 64 partials (backward chain step)
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 4 * TS);      // 1 barrier (+ padding)
+  double* acc = reinterpret_cast<double*>(full + 2);               // forward [slab][64]; backward [slab][warp][64]
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c = blockIdx.x, G = P.G, nb = P.nb;
   const int M = (nb - c + G - 1) / G;                              // slabs owned: k = c + m G (primed indices)
   const int64_t ld = P.ld, N = P.N;
+  const bool vec = P.aligned != 0;
+  constexpr int ACC_PER_SLAB = FWD ? TS : 8 * TS;
 
   // primed block index -> first row / column of the block in the matrix, and its height
   auto blk0 = [&](int kp) -> int64_t { return (int64_t)(FWD ? kp : nb - 1 - kp) * TS; };
   auto blkw = [&](int kp) -> int { const int64_t r0 = blk0(kp); return (int)((N - r0 < TS) ? (N - r0) : TS); };
-  // tile of slab kp against column block jp (jp < kp): forward L[blk kp, blk jp]; backward L[blk jp', blk kp']
-  auto tile_src = [&](int kp, int jp) -> const double* {
-    return FWD ? P.L + blk0(kp) * ld + blk0(jp) : P.L + blk0(jp) * ld + blk0(kp);
-  };
-  auto tile_rows = [&](int kp, int jp) -> int { return FWD ? blkw(kp) : blkw(jp); };
 
   if (tid == 0) {
-    for (int s = 0; s <= TS_STAGES; ++s) mbar_init(&full[s], 1);
+    mbar_init(&full[0], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = tid; i < M * TS; i += TS_THREADS) acc[i] = 0.0;
+  for (int i = tid; i < M * ACC_PER_SLAB; i += TS_THREADS) acc[i] = 0.0;
   __syncthreads();
 
-  // streamed tiles of slab k: column blocks 0 .. k-2 (block k-1 enters through W_k in the chain step)
-  auto settle = [&](TileIter& it) {
-    while (it.m0 < M && c + it.m0 * G < it.j + 2) ++it.m0;
-    it.m = it.m0;
-    if (it.m0 >= M) it.done = true;
-  };
-  auto advance = [&](TileIter& it) {
-    if (it.done) return;
-    ++it.m;
-    if (it.m >= M) {
-      ++it.j;
-      settle(it);
-    }
-  };
-  auto start = [&]() {
-    TileIter it;
-    it.j = 0;
-    it.m0 = 0;
-    it.done = false;
-    settle(it);
-    return it;
-  };
-  // issue the bulk copies of one tile into ring stage `s` (threads 0..63: one row each)
-  auto issue = [&](const TileIter& it, int s) {
-    if (!P.aligned) return;
-    const int kp = c + it.m * G;
-    const int rows = tile_rows(kp, it.j);
-    if (tid == 0) mbar_expect_tx(&full[s], (uint32_t)rows * TS * 8);
-    if (tid < rows) bulk_g2s(ring + s * TS_TILE_D + tid * TS_P, tile_src(kp, it.j) + (int64_t)tid * ld, TS * 8, &full[s]);
-  };
-  // prefetch what the next chain step (slab index ms) needs: D_k, W_k (bulk) and its right-hand side
+  // prefetch what the next chain step (slab index ms) needs: D_k, W_k (bulk async copies) and its right-hand side
   auto prefetch_solve = [&](int ms) {
     if (ms >= M) return;
     const int kp = c + ms * G;
     const int64_t r0 = blk0(kp);
     const int w = blkw(kp);
     const int64_t blk = (int64_t)(FWD ? kp : nb - 1 - kp) * TS * TS;
-    if (tid == 0) mbar_expect_tx(&full[TS_STAGES], (kp >= 1 ? 2u : 1u) * TS * TS * 8);
+    if (tid == 0) mbar_expect_tx(&full[0], (kp >= 1 ? 2u : 1u) * TS * TS * 8);
     if (tid < TS) {
-      bulk_g2s(dtile + tid * TS_P, P.dinv + blk + tid * TS, TS * 8, &full[TS_STAGES]);
-      if (kp >= 1) bulk_g2s(wtile + tid * TS_P, P.wmat + blk + tid * TS, TS * 8, &full[TS_STAGES]);
+      bulk_g2s(dtile + tid * TS_P, P.dinv + blk + tid * TS, TS * 8, &full[0]);
+      if (kp >= 1) bulk_g2s(wtile + tid * TS_P, P.wmat + blk + tid * TS, TS * 8, &full[0]);
       bs[tid] = (tid < w) ? P.b[r0 + tid] : 0.0;
     }
   };
 
-  // Product of the staged 64 x 64 tile `T` (pitch TS_P) with `xvec`: forward sum_c T[r][c] x[c] for row r, backward
-  // sum_r T[r][c] x[r] for column c.  The result is returned in the register of the element's OWNER thread
-  // (forward: the q == 0 lane of row r = tid / 4; backward: thread tid < 64 for column tid); `owner`/`idx` say which.
+  // Product of a staged 64 x 64 block `T` (pitch TS_P) with `xvec` in the chain step: forward sum_c T[r][c] x[c] for
+  // row r, backward sum_r T[r][c] x[r] for column c.  The result is returned in the register of the element's
+  // OWNER thread (forward: the q == 0 lane of row r = tid / 4; backward: thread tid < 64 for column tid).
   const bool owner = FWD ? ((tid & 3) == 0) : (tid < TS);
   const int idx = FWD ? (tid >> 2) : tid;
   auto matvec = [&](const double* T, const double* xvec, int rows_valid) -> double {
@@ -343,8 +307,18 @@ trsv_sweep_kernel(TrsvParams P) {
     const int kp = c + ms * G;
     const int64_t r0 = blk0(kp);
     const int w = blkw(kp);
-    if (owner) vs[idx] = (idx < w) ? bs[idx] - acc[ms * TS + idx] : 0.0;
-    mbar_wait(&full[TS_STAGES], dphase);
+    __syncthreads();                               // every warp has booked its part of acc
+    if (owner) {
+      double a;
+      if (FWD) {
+        a = acc[ms * TS + idx];
+      } else {                                     // the eight warps' partial sums, in a fixed order
+        const double* p = acc + ms * 8 * TS + idx;
+        a = ((p[0] + p[TS]) + (p[2 * TS] + p[3 * TS])) + ((p[4 * TS] + p[5 * TS]) + (p[6 * TS] + p[7 * TS]));
+      }
+      vs[idx] = (idx < w) ? bs[idx] - a : 0.0;
+    }
+    mbar_wait(&full[0], dphase);
     dphase ^= 1;
     __syncthreads();
     double xv = matvec(dtile, vs, TS);
@@ -361,7 +335,7 @@ trsv_sweep_kernel(TrsvParams P) {
       }
       __syncthreads();
       TRSV_STAMP(kp, 0);
-      xv -= matvec(wtile, xc, tile_rows(kp, kp - 1));
+      xv -= matvec(wtile, xc, FWD ? TS : blkw(kp - 1));
     }
     if (owner) {
       if (unpublished(xv)) xv = __longlong_as_double(0x7ff8000000000000ll);   // never publish the sentinel
@@ -373,38 +347,102 @@ trsv_sweep_kernel(TrsvParams P) {
     prefetch_solve(ms + 1);
   };
 
-  // ---- prologue: prefetch the first chain step's inputs and the first tiles --------------------------
-  prefetch_solve(0);
-  TileIter pf = start();
-  int pf_stage = 0;
-  for (int s = 0; s < TS_STAGES - 1; ++s) {
-    if (!pf.done) {
-      issue(pf, pf_stage);
-      advance(pf);
-      pf_stage = (pf_stage + 1) % TS_STAGES;
+  // ---- streaming part: one (slab, window) visit per warp, straight from global memory into registers ----------
+  // Forward: the warp owns rows 8 warp .. 8 warp + 7 of every slab; a lane reads the 16-byte column pair 2 lane,
+  // 2 lane + 1 of each 64-column block of the window (512 contiguous bytes per instruction, up to 2 KB per row)
+  // and the eight row sums are completed with shuffles.  Backward (transposed product): the warp owns every
+  // eighth row of the window's blocks, a lane accumulates the two columns 2 lane, 2 lane + 1 of the slab -- no
+  // shuffles; the eight warps' partial sums stay separate in shared memory until the chain step.
+  auto visit_fwd = [&](int m, int j0, int cnt) {
+    const int kp = c + m * G;
+    const int64_t r0 = blk0(kp) + warp * 8;
+    const double* base = P.L + r0 * ld + (int64_t)j0 * TS + 2 * lane;
+    double2 v[8][TS_WIN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int g = 0; g < TS_WIN; ++g)
+        v[i][g] = (g < cnt && r0 + i < N) ? ldg2(base + (int64_t)i * ld + g * TS, vec) : make_double2(0.0, 0.0);
+    double s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int g = 0; g < TS_WIN; ++g) {
+        if (g < cnt) {
+          a0 = fma(v[i][g].x, xs[g * TS + 2 * lane], a0);
+          a1 = fma(v[i][g].y, xs[g * TS + 2 * lane + 1], a1);
+        }
+      }
+      s[i] = a0 + a1;
     }
-  }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+    if (lane < 8) {
+      double sv = s[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) sv = (lane == i) ? s[i] : sv;
+      acc[m * TS + warp * 8 + lane] += sv;
+    }
+  };
+  auto visit_bwd = [&](int m, int j0, int cnt) {
+    const int kp = c + m * G;
+    const int64_t c0 = blk0(kp) + 2 * lane;          // the slab's columns
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    for (int g = 0; g < cnt; ++g) {
+      const int64_t rb = blk0(j0 + g);               // rows of window block g (primed j0 + g)
+      const int rows = blkw(j0 + g);
+      double2 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = warp * 8 + i;
+        v[i] = (r < rows) ? ldg2(P.L + (rb + r) * ld + c0, vec) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i += 2) {
+        const double x0 = xs[g * TS + warp * 8 + i], x1 = xs[g * TS + warp * 8 + i + 1];
+        a0 = fma(v[i].x, x0, a0);
+        a1 = fma(v[i].y, x0, a1);
+        b0 = fma(v[i + 1].x, x1, b0);
+        b1 = fma(v[i + 1].y, x1, b1);
+      }
+    }
+    double* p = acc + (m * 8 + warp) * TS + 2 * lane;
+    p[0] += a0 + b0;
+    p[1] += a1 + b1;
+  };
+
+  prefetch_solve(0);
   __syncthreads();
 
-  TileIter it = start();
-  int ms_next = 0;                                 // next slab (index) whose chain step this CTA owes
-  int stage = 0;
-  uint32_t phase = 0;                              // parity of ring stage 0's current fill
-  int win0 = 0, wincnt = 0;                        // column blocks currently held in xs
-  for (;;) {
-    const int k_next = (ms_next < M) ? c + ms_next * G : 0x7fffffff;
-    if (ms_next < M && (it.done || it.j >= k_next - 1)) {
-      chain_step(ms_next);
-      ++ms_next;
-      continue;
+  // L2 prefetch of the 64-row tiles of slab index ms against column blocks j0 .. j0 + cnt - 1: near the chain front
+  // a tile is needed the moment its unknowns appear, and an HBM round trip would then sit on the serial chain
+  auto prefetch_l2 = [&](int ms, int j0, int cnt) {
+    const int kp = c + ms * G;
+    if (FWD) {
+      const int rows = blkw(kp);
+      const int lines = cnt * 4;                   // 128-byte lines per row
+      for (int i = tid; i < rows * lines; i += TS_THREADS) {
+        const double* p = P.L + (blk0(kp) + i / lines) * ld + (int64_t)j0 * TS + (i % lines) * 16;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+      }
+    } else {
+      for (int i = tid; i < cnt * TS * 4; i += TS_THREADS) {
+        const int g = i / (TS * 4), r = (i / 4) % TS;
+        if (r < blkw(j0 + g)) {
+          const double* p = P.L + (blk0(j0 + g) + r) * ld + blk0(kp) + (i % 4) * 16;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        }
+      }
     }
-    if (it.done) break;
-    if (it.j < win0 || it.j >= win0 + wincnt) {
-      // ---- fetch a new window of unknowns: column blocks it.j .. it.j + cnt - 1 (all needed before k_next - 1) ----
-      int cnt = k_next - 1 - it.j;                 // >= 1 here
-      cnt = (cnt <= TS_NEAR) ? 1 : (cnt < TS_WIN ? cnt : TS_WIN);
-      __syncthreads();                             // everyone is done with the previous window
-      const double* src = P.xpub + (int64_t)it.j * TS;
+  };
+  // fetch the unknowns of column blocks j0 .. j0 + cnt - 1 into xs (urgent: all 64 threads poll from the start)
+  auto fetch_window = [&](int j0, int cnt, bool urgent) {
+    __syncthreads();                               // everyone is done with the previous window
+    const double* src = P.xpub + (int64_t)j0 * TS;
+    if (!urgent) {
       if (tid == 0) {                              // blocks are published in order: wait for the last one, lazily
         unsigned spins = 0;
         while (unpublished(ld_relaxed_f64(src + (cnt - 1) * TS))) {
@@ -413,56 +451,67 @@ trsv_sweep_kernel(TrsvParams P) {
         }
       }
       __syncthreads();
-      if (tid < cnt * TS) {
-        double v = ld_relaxed_f64(src + tid);
-        unsigned spins = 0;
-        while (unpublished(v)) {
-          if (++spins > (1u << 25)) { atomicExch(&g_tgp_device_error, 1); break; }
-          v = ld_relaxed_f64(src + tid);
-        }
-        xs[tid] = v;
+    }
+    if (tid < cnt * TS) {
+      double v = ld_relaxed_f64(src + tid);
+      unsigned spins = 0;
+      while (unpublished(v)) {
+        if (++spins > (1u << 25)) { atomicExch(&g_tgp_device_error, 1); break; }
+        v = ld_relaxed_f64(src + tid);
       }
-      win0 = it.j;
-      wincnt = cnt;
-      __syncthreads();
+      if (!FWD && (tid & 63) >= blkw(j0 + (tid >> 6))) v = 0.0;    // padding rows of a short block
+      xs[tid] = v;
     }
-    const int kp = c + it.m * G;
-    const int rows = tile_rows(kp, it.j);
-    const double* T = ring + stage * TS_TILE_D;
-    if (P.aligned) {
-      mbar_wait(&full[stage], phase);
-    } else {
-      // unaligned matrix (odd ld / base): plain loads, no prefetch
-      const double* src = tile_src(kp, it.j);
-      for (int i2 = tid; i2 < TS * TS; i2 += TS_THREADS) {
-        const int r = i2 >> 6, cc = i2 & 63;
-        ring[stage * TS_TILE_D + r * TS_P + cc] = (r < rows) ? src[(int64_t)r * ld + cc] : 0.0;
-      }
-      __syncthreads();
+    __syncthreads();
+  };
+
+  prefetch_solve(0);
+  __syncthreads();
+
+  // Progress: column blocks < j_rest are applied to every unsolved slab; the slab whose chain step comes next
+  // ("urgent", index ms_next) may be ahead, at j_urg >= j_rest: within TS_NEAR blocks of its own diagonal it is fed
+  // one block at a time, as soon as that block's unknowns exist and before the CTA's other slabs, so that it is
+  // already waiting when the unknowns of the last block before its diagonal are published.
+  int ms_next = 0;
+  int j_rest = 0, j_urg = 0;
+  for (;;) {
+    if (ms_next >= M) break;
+    const int k_next = c + ms_next * G;
+    if (j_urg >= k_next - 1) {                     // blocks 0 .. k_next - 2 are in: the slab's chain step is due
+      chain_step(ms_next);
+      ++ms_next;
+      j_urg = j_rest;
+      continue;
     }
-    const double sv = matvec(T, xs + (it.j - win0) * TS, rows);
-    if (owner) acc[it.m * TS + idx] += sv;
-    __syncthreads();                               // the ring stage is free again
-    if (!pf.done) {                                // refill the ring, TS_STAGES - 1 tiles ahead
-      issue(pf, pf_stage);
-      advance(pf);
-      pf_stage = (pf_stage + 1) % TS_STAGES;
+    const int left = k_next - 1 - j_urg;           // blocks still to apply to the urgent slab, >= 1
+    if (left <= TS_NEAR) {
+      if (left == TS_NEAR || j_urg == j_rest) prefetch_l2(ms_next, j_urg, left);
+      fetch_window(j_urg, 1, true);
+      if (FWD) visit_fwd(ms_next, j_urg, 1); else visit_bwd(ms_next, j_urg, 1);
+      ++j_urg;
+      continue;
     }
-    stage = (stage + 1) % TS_STAGES;
-    if (stage == 0) phase ^= 1;
-    advance(it);
+    // far from any diagonal of ours: a window of up to TS_WIN blocks for all unsolved slabs
+    int cnt = left - TS_NEAR;
+    cnt = cnt < TS_WIN ? cnt : TS_WIN;
+    fetch_window(j_rest, cnt, false);
+    for (int m = ms_next; m < M; ++m) {
+      if (FWD) visit_fwd(m, j_rest, cnt); else visit_bwd(m, j_rest, cnt);
+    }
+    j_rest += cnt;
+    j_urg = j_rest;
   }
 }
 
-static size_t trsv_smem_bytes(int slabs_per_cta) {
-  return (size_t)(TS_STAGES + 2) * TS_TILE_D * 8 + (size_t)(TS_WIN * TS + 3 * TS + 4 * TS) * 8 + (TS_STAGES + 2) * 8 +
-         (size_t)slabs_per_cta * TS * 8;
+static size_t trsv_smem_bytes(bool fwd, int slabs_per_cta) {
+  return (size_t)2 * TS_TILE_D * 8 + (size_t)(TS_WIN * TS + 3 * TS + 4 * TS) * 8 + 2 * 8 +
+         (size_t)slabs_per_cta * TS * 8 * (fwd ? 1 : 8);
 }
 
 template <bool FWD>
 static int trsv_launch(const TrsvParams& P0, cudaStream_t st) {
   TrsvParams P = P0;
-  const size_t smem = trsv_smem_bytes((P.nb + P.G - 1) / P.G);
+  const size_t smem = trsv_smem_bytes(FWD, (P.nb + P.G - 1) / P.G);
   static TgpPerDeviceOnce once;
   if (tgp_first_use_on_device(once))
     TGP_CUDA(cudaFuncSetAttribute(trsv_sweep_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -518,7 +567,12 @@ int tgp_trsv_sweeps(const double* L, int64_t N, int64_t ld, double* b, int which
   double* xpub = wb + blk_d;
   int rc = TGP_OK;
   do {
+#ifdef TGP_TRSV_TIMING
+    // which & 4 (debug): pretend every block is already published -> no dependency waits, pure streaming rate
+    if (cudaMemsetAsync(xpub, (which & 4) ? 0 : 0xFF, pub_d * sizeof(double), st) != cudaSuccess) { rc = TGP_ERR_CUDA; break; }
+#else
     if (cudaMemsetAsync(xpub, 0xFF, pub_d * sizeof(double), st) != cudaSuccess) { rc = TGP_ERR_CUDA; break; }
+#endif
     static TgpPerDeviceOnce prep_once;
     if (tgp_first_use_on_device(prep_once) &&
         cudaFuncSetAttribute(trsv_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM) != cudaSuccess) {

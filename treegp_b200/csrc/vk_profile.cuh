@@ -11,7 +11,7 @@
 //   z >= 1 : f = C_INF * exp(-z) * psi(z), psi = z^(1/3) phi(z) tabulated per binade of z as a
 //            polynomial in the mantissa (no cube root, no division, no iteration).
 // Tables come from tools/gen_vk_tables.py (mpmath, 60 digits).  Measured error vs mpmath: see
-// tests/test_vk_profile.py (a few ulp relative over the whole range).
+// tests/test_cpu_host.py::test_vk_profile_against_mpmath (a few ulp relative over the whole range).
 //
 // The header is host+device so the CPU test-suite can exercise exactly this code with gcc/nvcc host
 // compilation; the product only ever calls it from device code.
