@@ -414,9 +414,6 @@ trsv_sweep_kernel(TrsvParams P) {
     p[1] += a1 + b1;
   };
 
-  prefetch_solve(0);
-  __syncthreads();
-
   // L2 prefetch of the 64-row tiles of slab index ms against column blocks j0 .. j0 + cnt - 1: near the chain front
   // a tile is needed the moment its unknowns appear, and an HBM round trip would then sit on the serial chain
   auto prefetch_l2 = [&](int ms, int j0, int cnt) {
