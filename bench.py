@@ -751,9 +751,15 @@ def run_cfg5(args, treegp, backend, ctx):
     X = rng.uniform(-Lf / 2, Lf / 2, size=(n, 2))
     size, g1, g2, sigma, noise = 8.0, 0.2, 0.1, 1.0, 0.05
     inv = np.linalg.inv(get_correlation_length_matrix(size, g1, g2))
-    mean_fn = 0.5 * np.sin(X[:, 0] / 70.0) * np.cos(X[:, 1] / 90.0)
-    y = rff_field(X, inv, sigma) + mean_fn + rng.normal(scale=noise, size=n)
+    mean_of = lambda P_: 0.5 * np.sin(P_[:, 0] / 70.0) * np.cos(P_[:, 1] / 90.0)
+    y = rff_field(X, inv, sigma) + mean_of(X) + rng.normal(scale=noise, size=n)
     y_err = np.full(n, noise)
+    # the mean function is what survives the average over many exposures: five more realisations of the random
+    # field (other positions, other phases) enter the meanify grid next to the field that is fitted
+    others = []
+    for s_ in range(5):
+        Xo = rng.uniform(-Lf / 2, Lf / 2, size=(n, 2))
+        others.append((Xo, rff_field(Xo, inv, sigma, seed=100 + s_) + mean_of(Xo) + rng.normal(scale=noise, size=n)))
     kstr = "1.0 * AnisotropicRBF(invLam=array([[%.17g, %.17g], [%.17g, %.17g]]))" % (inv[0, 0], inv[0, 1], inv[1, 0], inv[1, 1])
     tmp = os.path.join(tempfile.mkdtemp(prefix="tgp_bench_"), "mean_gp.fits")
     max_sep, B = 30.0, 100
@@ -763,6 +769,8 @@ def run_cfg5(args, treegp, backend, ctx):
         t0 = time.perf_counter()
         mf = treegp.meanify(bin_spacing=Lf / 50.0, statistics="mean")
         mf.add_field(X, y)
+        for Xo, yo in others:
+            mf.add_field(Xo, yo)
         mf.meanify()
         mf.save_results(name_output=tmp)
         t["meanify_s"] = time.perf_counter() - t0
@@ -799,6 +807,14 @@ def run_cfg5(args, treegp, backend, ctx):
     out["cfg5_truth_sigma_size_g1_g2"] = [sigma, size, g1, g2]
     pairs = n * (n - 1) / 2
     out["cfg5_bootstrap_resample_pairs_per_s"] = B * pairs / t["bootstrap_%d_s" % B]
+    # the round-1 bootstrap record, for comparison: iid field, default max_sep (half the diagonal), 100 resamples
+    tq = treegp.two_pcf(X, rng.normal(size=n), np.zeros(n), 0.0, np.sqrt(2.0) * Lf / 2.0, nbins=21, anisotropic=True)
+    tq.comp_xi_covariance(n_bootstrap=2, mask=None, seed=1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tq.comp_xi_covariance(n_bootstrap=B, mask=None, seed=610639139)
+    torch.cuda.synchronize()
+    out["cfg5_bootstrap100_default_maxsep_s"] = time.perf_counter() - t0
     # the public path: solve() = pair count + 444 resamples (fsolve, two_pcf.py:375-383) + robust fit
     torch.cuda.synchronize()
     t0 = time.perf_counter()
