@@ -198,6 +198,12 @@ int64_t tgp_pairbin_work_doubles(int64_t total_points, int32_t ncat);
 int tgp_hilbert_keys(const double* x, const double* y, int64_t n, double xmin, double ymin, double extent,
                      int32_t order, int64_t* keys, void* stream);
 
+/* The same keys with the bounding square (xmin, ymin, extent = max side * (1 + 1e-9)) found on the device, so that
+ * the caller does not have to read the extrema back in the middle of a call.  scratch32: device scratch of 32 bytes
+ * (8-byte aligned). */
+int tgp_hilbert_keys_auto(const double* x, const double* y, int64_t n, int32_t order, void* scratch32,
+                          int64_t* keys, void* stream);
+
 /* HOST function (no device work): multiplicities of `b` bootstrap resamples of n points, bit-identical to
  * b successive numpy `Generator(PCG64).integers(0, n-1, size=n)` calls -- the draws of resample_bootstrap
  * (two_pcf.py:266,269-281; index n-1 is never drawn).

@@ -228,3 +228,29 @@ def test_pairbin_log_one_bin_blocks_match_oracle(gpu_ready, weighted):
             _check(_gpu_pairbin(x, y, k, w, mn, mx, nb, "Log", hilbert=True), ref)
         finally:
             backend.set_option("pairbin_block_sums", 1)
+
+
+def test_hilbert_keys_auto_equal_keys_from_host_bounds(gpu_ready):
+    """tgp_hilbert_keys_auto (bounding square found on the device, no read-back) gives exactly the keys of
+    tgp_hilbert_keys with the extrema taken on the host."""
+    import ctypes
+    import torch
+    from treegp_b200 import _cabi, backend
+
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 1000, 300_001):
+        x = backend.to_device(rng.uniform(-7.0, 13.0, n))
+        y = backend.to_device(rng.uniform(100.0, 103.0, n))
+        xmin, xmax, ymin, ymax = float(x.min()), float(x.max()), float(y.min()), float(y.max())
+        extent = max(xmax - xmin, ymax - ymin)
+        extent = extent * (1.0 + 1e-9) if extent > 0 else 1.0
+        order = int(min(16, max(1, np.ceil(np.log2(max(np.sqrt(n), 2.0))) + 1)))
+        k1 = torch.empty(n, dtype=torch.int64, device=x.device)
+        k2 = torch.empty(n, dtype=torch.int64, device=x.device)
+        scratch = torch.empty(4, dtype=torch.int64, device=x.device)
+        lib = _cabi.load()
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _cabi.check(lib.tgp_hilbert_keys(p(x), p(y), n, xmin, ymin, extent, order, p(k1), st), "keys")
+        _cabi.check(lib.tgp_hilbert_keys_auto(p(x), p(y), n, order, p(scratch), p(k2), st), "keys_auto")
+        assert torch.equal(k1, k2)

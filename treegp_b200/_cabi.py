@@ -53,6 +53,7 @@ SIGNATURES = {
                     _vp, _vp, _vp, _vp, _vp, _vp],
     "tgp_pairbin_work_doubles": [_i64, _i32],
     "tgp_hilbert_keys": [_vp, _vp, _i64, _f64, _f64, _f64, _i32, _vp, _vp],
+    "tgp_hilbert_keys_auto": [_vp, _vp, _i64, _i32, _vp, _vp, _vp],
     "tgp_bootstrap_multiplicities": [_vp, _i64, _i64, _vp, _vp],
     "tgp_device_error": [_i32],
     "tgp_vcorr": [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _vp, _i32, _vp, _vp],

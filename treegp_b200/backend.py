@@ -306,14 +306,13 @@ def hilbert_order(px, py):
     n = int(px.numel())
     if n == 0:
         return torch.zeros(0, dtype=torch.int64, device=px.device)
-    # two reductions and one device->host transfer for the four extrema
-    xmin, xmax, ymin, ymax = torch.stack(torch.aminmax(px) + torch.aminmax(py)).tolist()
-    extent = max(xmax - xmin, ymax - ymin)
-    extent = extent * (1.0 + 1e-9) if extent > 0 else 1.0
+    # the bounding square is found on the device (tgp_hilbert_keys_auto): nothing is read back, so the host keeps
+    # enqueueing while the uploads and the sort run
     order = int(min(16, max(1, np.ceil(np.log2(max(np.sqrt(n), 2.0))) + 1)))
     keys = torch.empty(n, dtype=torch.int64, device=px.device)
-    check(_cabi.load().tgp_hilbert_keys(_p(px), _p(py), n, xmin, ymin, extent, order, _p(keys), _stream()),
-          "tgp_hilbert_keys")
+    scratch = torch.empty(4, dtype=torch.int64, device=px.device)
+    check(_cabi.load().tgp_hilbert_keys_auto(_p(px), _p(py), n, order, _p(scratch), _p(keys), _stream()),
+          "tgp_hilbert_keys_auto")
     return torch.argsort(keys)
 
 

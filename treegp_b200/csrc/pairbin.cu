@@ -1547,6 +1547,76 @@ __global__ void hilbert_keys_kernel(const double* __restrict__ x, const double* 
   keys[i] = (int64_t)d;
 }
 
+// ---- the same keys with the bounding square found on the device: no host round trip in the middle of a call ----
+__device__ __forceinline__ unsigned long long hb_key(double v) {   // order-preserving map double -> uint64
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double hb_unkey(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+__global__ void hilbert_bounds_init_kernel(unsigned long long* b4) {
+  if (threadIdx.x < 4) b4[threadIdx.x] = (threadIdx.x & 1) ? 0ull : ~0ull;   // {min x, max x, min y, max y}
+}
+__global__ void __launch_bounds__(256)
+hilbert_bounds_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n, unsigned long long* b4) {
+  double xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double a = x[i], b = y[i];
+    xmin = fmin(xmin, a); xmax = fmax(xmax, a);
+    ymin = fmin(ymin, b); ymax = fmax(ymax, b);
+  }
+  xmin = warp_min(xmin); xmax = warp_max(xmax);
+  ymin = warp_min(ymin); ymax = warp_max(ymax);
+  if ((threadIdx.x & 31) == 0 && xmin <= xmax) {
+    atomicMin(b4 + 0, hb_key(xmin)); atomicMax(b4 + 1, hb_key(xmax));
+    atomicMin(b4 + 2, hb_key(ymin)); atomicMax(b4 + 3, hb_key(ymax));
+  }
+}
+__global__ void hilbert_keys_auto_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
+                                         const unsigned long long* __restrict__ b4, int order,
+                                         int64_t* __restrict__ keys) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x0 = hb_unkey(b4[0]), x1 = hb_unkey(b4[1]), y0 = hb_unkey(b4[2]), y1 = hb_unkey(b4[3]);
+  // the formula of treegp_b200.backend.hilbert_order (same IEEE operations, so the same keys as tgp_hilbert_keys)
+  double extent = fmax(__dsub_rn(x1, x0), __dsub_rn(y1, y0));
+  extent = extent > 0.0 ? __dmul_rn(extent, 1.0 + 1e-9) : 1.0;
+  const double inv_cell = __ddiv_rn((double)(1u << order), extent);
+  const unsigned side = 1u << order;
+  long long cx = (long long)floor(__dmul_rn(__dsub_rn(x[i], x0), inv_cell));
+  long long cy = (long long)floor(__dmul_rn(__dsub_rn(y[i], y0), inv_cell));
+  unsigned ux = (unsigned)(cx < 0 ? 0 : (cx >= (long long)side ? side - 1 : cx));
+  unsigned uy = (unsigned)(cy < 0 ? 0 : (cy >= (long long)side ? side - 1 : cy));
+  unsigned long long d = 0;
+  for (unsigned s = side >> 1; s > 0; s >>= 1) {
+    const unsigned rx = (ux & s) ? 1u : 0u, ry = (uy & s) ? 1u : 0u;
+    d += (unsigned long long)s * s * ((3u * rx) ^ ry);
+    if (ry == 0) {
+      if (rx == 1) { ux = side - 1 - ux; uy = side - 1 - uy; }
+      const unsigned t = ux; ux = uy; uy = t;
+    }
+  }
+  keys[i] = (int64_t)d;
+}
+
+extern "C" int tgp_hilbert_keys_auto(const double* x, const double* y, int64_t n, int32_t order, void* scratch32,
+                                     int64_t* keys, void* stream) {
+  TGP_CHECK_ARG(n >= 0 && order >= 1 && order <= 30, "n/order");
+  if (n == 0) return TGP_OK;
+  TGP_CHECK_ARG(x && y && keys && scratch32 && ((uintptr_t)scratch32 % 8) == 0, "null / unaligned pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* b4 = reinterpret_cast<unsigned long long*>(scratch32);
+  hilbert_bounds_init_kernel<<<1, 32, 0, st>>>(b4);
+  int64_t blocks = tgp_cdiv(n, 256 * 8);
+  if (blocks > 4 * tgp_num_sms()) blocks = 4 * tgp_num_sms();
+  hilbert_bounds_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, y, n, b4);
+  hilbert_keys_auto_kernel<<<(unsigned)tgp_cdiv(n, 256), 256, 0, st>>>(x, y, n, b4, order, keys);
+  TGP_LAUNCH_CHECK();
+  return TGP_OK;
+}
+
 extern "C" int tgp_hilbert_keys(const double* x, const double* y, int64_t n, double xmin, double ymin,
                                 double extent, int32_t order, int64_t* keys, void* stream) {
   TGP_CHECK_ARG(n >= 0 && order >= 1 && order <= 30 && extent > 0.0, "n/order/extent");
