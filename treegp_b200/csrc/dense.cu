@@ -199,7 +199,9 @@ static int gemm_nt_sub_launch(double* C, int64_t M, int64_t Nc, int64_t ldc, con
 
 extern "C" int tgp_pairbin_set_block_sums(int on);
 extern "C" int tgp_pairbin_set_fast_paths(int bits);
+extern "C" int tgp_trsv_set_cluster(int v);
 extern "C" int tgp_set_option(const char* name, int value) {
+  if (name && !strcmp(name, "trsv_cluster")) return tgp_trsv_set_cluster(value);
   if (name && !strcmp(name, "gemm_config")) { g_gemm_config = value; return TGP_OK; }
   if (name && !strcmp(name, "potrf_lookahead")) { g_lookahead = value; return TGP_OK; }
   if (name && !strcmp(name, "potrf_fused")) { g_fused_panel = value; return TGP_OK; }

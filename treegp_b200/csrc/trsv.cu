@@ -129,17 +129,29 @@ trsv_prep_kernel(const double* __restrict__ L, int64_t ld, int64_t N, int nb, do
     Z[r][c] = 0.0;
   }
   __syncthreads();
-  // Z = Lk^-1 row by row: Z[r][c] = (delta_rc - sum_{m<r} Lk[r][m] Z[m][c]) / Lk[r][r]; 4 adjacent lanes share a column
+  // Z = Lk^-1, column by column: Z[r][c] = (delta_rc - sum_{c<=m<r} Lk[r][m] Z[m][c]) / Lk[r][r].  The four lanes that
+  // share column c sit in one warp and nobody else touches that column, so the rows are separated by __syncwarp only.
   {
+    double* rdiag = &T[0][0];                      // T is not in use yet
+    if (tid < TS) rdiag[tid] = 1.0 / Lk[tid][tid];
+    __syncthreads();
     const int c = tid >> 2, part = tid & 3;
+    const int m0 = c + ((part - c) & 3);           // first m >= c with m = part (mod 4)
     for (int r = 0; r < TS; ++r) {
-      double s = 0.0;
-      for (int m = part; m < r; m += 4) s = fma(Lk[r][m], Z[m][c], s);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (part == 0 && c <= r) Z[r][c] = (((r == c) ? 1.0 : 0.0) - s) / Lk[r][r];
-      __syncthreads();
+      double s0 = 0.0, s1 = 0.0;
+      int m = m0;
+      for (; m + 4 < r; m += 8) {
+        s0 = fma(Lk[r][m], Z[m][c], s0);
+        s1 = fma(Lk[r][m + 4], Z[m + 4][c], s1);
+      }
+      if (m < r) s0 = fma(Lk[r][m], Z[m][c], s0);
+      double sv = s0 + s1;
+      sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+      sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+      if (part == 0 && c <= r) Z[r][c] = (((r == c) ? 1.0 : 0.0) - sv) * rdiag[r];
+      __syncwarp();
     }
+    __syncthreads();
   }
   double* out = dinv + (int64_t)k * TS * TS;
   for (int i = tid; i < TS * TS; i += 256) out[i] = Z[i >> 6][i & 63];
@@ -203,7 +215,36 @@ struct TrsvParams {
   const double* wmat;    // nb blocks of 64 x 64: W_k (forward) or M_k (backward)
   double* xpub;          // nb * 64 words, all-ones on entry: block kp's unknowns are published at xpub + 64 kp
   int nb, G, aligned;
+  int CS;                // thread-block cluster size (1: none).  G is a multiple of CS
 };
+
+// ---- cluster primitives: the chain hop between CTAs of one cluster goes through distributed shared memory ----
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta_rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(cta_rank));
+  return r;
+}
+__device__ __forceinline__ void st_remote_f64(uint32_t cluster_addr, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(cluster_addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  unsigned tries = 0;
+  while (!ok) {
+    if (++tries > (1u << 24)) { atomicExch(&g_tgp_device_error, 2); break; }   // never hang the GPU
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ double2 ldg2(const double* p, bool vec) {
   if (vec) return __ldcs(reinterpret_cast<const double2*>(p));      // streamed once: evict-first
@@ -221,7 +262,7 @@ trsv_sweep_kernel(TrsvParams P) {
   double* vs = xc + TS;                                            // b_k - partial sums
   double* bs = vs + TS;                                            // b of the next chain step (prefetched)
   double* red = bs + TS;                                           // 4 x 64 partials (backward chain step)
-  uint64_t* full = reinterpret_cast<uint64_t*>(red + 4 * TS);      // 1 barrier (+ padding)
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 4 * TS);      // [0] D/W tiles landed, [1] xc filled by a cluster peer
   double* acc = reinterpret_cast<double*>(full + 2);               // forward [slab][64]; backward [slab][warp][64]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -229,6 +270,7 @@ trsv_sweep_kernel(TrsvParams P) {
   const int M = (nb - c + G - 1) / G;                              // slabs owned: k = c + m G (primed indices)
   const int64_t ld = P.ld, N = P.N;
   const bool vec = P.aligned != 0;
+  const int CS = P.CS;
   constexpr int ACC_PER_SLAB = FWD ? TS : 8 * TS;
 
   // primed block index -> first row / column of the block in the matrix, and its height
@@ -237,10 +279,19 @@ trsv_sweep_kernel(TrsvParams P) {
 
   if (tid == 0) {
     mbar_init(&full[0], 1);
+    mbar_init(&full[1], TS);                       // one arrival per unknown stored by the previous slab's owner
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < M * ACC_PER_SLAB; i += TS_THREADS) acc[i] = 0.0;
   __syncthreads();
+  if (CS > 1) cluster_sync_all();                  // every peer's barriers exist before anyone arrives on them
+  // The owner of slab k + 1 is CTA (c + 1) mod G, that of slab k - 1 CTA (c - 1) mod G: inside one cluster the
+  // unknowns are handed over through distributed shared memory (store into the peer's xc + arrive on its barrier,
+  // ~0.2 us) instead of the L2 round trip of the global publication (~1 us), which stays for everybody else.
+  const int next_cta = (c + 1) % G, prev_cta = (c + G - 1) % G;
+  const bool feed_next_local = CS > 1 && G >= 2 && (next_cta / CS == c / CS);
+  const bool fed_by_prev_local = CS > 1 && G >= 2 && (prev_cta / CS == c / CS);
+  uint32_t xphase = 0;
 
   // prefetch what the next chain step (slab index ms) needs: D_k, W_k (bulk async copies) and its right-hand side
   auto prefetch_solve = [&](int ms) {
@@ -323,15 +374,20 @@ trsv_sweep_kernel(TrsvParams P) {
     __syncthreads();
     double xv = matvec(dtile, vs, TS);
     if (kp >= 1) {
-      const double* src = P.xpub + (int64_t)(kp - 1) * TS;
-      if (tid < TS) {
-        double v = ld_relaxed_f64(src + tid);
-        unsigned spins = 0;
-        while (unpublished(v)) {
-          if (++spins > (1u << 25)) { atomicExch(&g_tgp_device_error, 1); break; }
-          v = ld_relaxed_f64(src + tid);
+      if (fed_by_prev_local) {
+        mbar_wait_cluster(&full[1], xphase);       // the peer has stored all 64 unknowns into xc
+        xphase ^= 1;
+      } else {
+        const double* src = P.xpub + (int64_t)(kp - 1) * TS;
+        if (tid < TS) {
+          double v = ld_relaxed_f64(src + tid);
+          unsigned spins = 0;
+          while (unpublished(v)) {
+            if (++spins > (1u << 25)) { atomicExch(&g_tgp_device_error, 1); break; }
+            v = ld_relaxed_f64(src + tid);
+          }
+          xc[tid] = v;
         }
-        xc[tid] = v;
       }
       __syncthreads();
       TRSV_STAMP(kp, 0);
@@ -339,6 +395,11 @@ trsv_sweep_kernel(TrsvParams P) {
     }
     if (owner) {
       if (unpublished(xv)) xv = __longlong_as_double(0x7ff8000000000000ll);   // never publish the sentinel
+      if (feed_next_local && kp + 1 < nb) {        // first the hop that is on the serial chain
+        const uint32_t peer = (uint32_t)(next_cta % CS);
+        st_remote_f64(map_to_cta(smem_addr(xc + idx), peer), xv);
+        mbar_arrive_remote(map_to_cta(smem_addr(&full[1]), peer));
+      }
       st_relaxed_f64(P.xpub + (int64_t)kp * TS + idx, xv);
       if (idx < w) P.b[r0 + idx] = xv;
     }
@@ -498,6 +559,7 @@ trsv_sweep_kernel(TrsvParams P) {
     j_rest += cnt;
     j_urg = j_rest;
   }
+  if (CS > 1) cluster_sync_all();                  // shared memory of a CTA stays valid while peers may still write
 }
 
 static size_t trsv_smem_bytes(bool fwd, int slabs_per_cta) {
@@ -505,16 +567,82 @@ static size_t trsv_smem_bytes(bool fwd, int slabs_per_cta) {
          (size_t)slabs_per_cta * TS * 8 * (fwd ? 1 : 8);
 }
 
+static int g_trsv_cluster = -1;   // option "trsv_cluster": -1 automatic, 1 no clusters, 2 / 4 / 8 cluster size
+extern "C" int tgp_trsv_set_cluster(int v) { g_trsv_cluster = v; return TGP_OK; }
+
+// CTAs of one cooperative launch: as many as are co-resident (one per SM: the kernel takes most of the shared
+// memory), in clusters of CS when a cluster size is in use.
+template <bool FWD>
+static int trsv_grid(int nb, int cs, size_t smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)cs);
+  cfg.blockDim = dim3(TS_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cs;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int nclusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&nclusters, trsv_sweep_kernel<FWD>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  int g = nclusters * cs;
+  const int want = (nb / cs) * cs;
+  return g < want ? g : want;
+}
+
 template <bool FWD>
 static int trsv_launch(const TrsvParams& P0, cudaStream_t st) {
   TrsvParams P = P0;
-  const size_t smem = trsv_smem_bytes(FWD, (P.nb + P.G - 1) / P.G);
   static TgpPerDeviceOnce once;
   if (tgp_first_use_on_device(once))
     TGP_CUDA(cudaFuncSetAttribute(trsv_sweep_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  // cluster size: the largest of 8 / 4 / 2 that still keeps (nearly) all SMs busy; none for tiny matrices
+  int cs = 1, G = P.G;
+  const size_t smem1 = trsv_smem_bytes(FWD, (P.nb + P.G - 1) / P.G);
+  if (g_trsv_cluster != 1 && P.nb >= 4) {
+    const int tries[3] = {8, 4, 2};
+    for (int t = 0; t < 3; ++t) {
+      const int c2 = tries[t];
+      if (g_trsv_cluster > 1 && c2 != g_trsv_cluster) continue;
+      if (P.nb < c2) continue;
+      const int g = trsv_grid<FWD>(P.nb, c2, smem1 + 4096);
+      if (g >= c2 && (g_trsv_cluster > 1 || 10 * g >= 9 * (P.nb < P.G ? (P.nb / c2) * c2 : P.G))) {
+        cs = c2;
+        G = g;
+        break;
+      }
+    }
+  }
+  P.CS = cs;
+  P.G = G;
+  const size_t smem = trsv_smem_bytes(FWD, (P.nb + P.G - 1) / P.G);
   TGP_CHECK_ARG(smem <= 227 * 1024, "matrix too large for the sweep kernel's per-CTA accumulators");
-  void* args[] = {(void*)&P};
-  TGP_CUDA(cudaLaunchCooperativeKernel((void*)trsv_sweep_kernel<FWD>, dim3((unsigned)P.G), dim3(TS_THREADS), args, smem, st));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)P.G);
+  cfg.blockDim = dim3(TS_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = (unsigned)cs;
+  at[1].val.clusterDim.y = 1;
+  at[1].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = cs > 1 ? 2 : 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, trsv_sweep_kernel<FWD>, P);
+  if (e != cudaSuccess && cs > 1) {                // clusters + cooperative launch refused: go on without clusters
+    cudaGetLastError();
+    g_trsv_cluster = 1;
+    return trsv_launch<FWD>(P0, st);
+  }
+  TGP_CUDA(e);
   return TGP_OK;
 }
 
@@ -548,6 +676,7 @@ int tgp_trsv_sweeps(const double* L, int64_t N, int64_t ld, double* b, int which
   TrsvParams P;
   P.L = L; P.ld = ld; P.N = N; P.b = b; P.nb = nb;
   P.G = nb < sms ? nb : sms;
+  P.CS = 1;
   P.aligned = ((ld & 1) == 0) && ((((uintptr_t)L) & 15) == 0);
   const size_t blk_d = (size_t)nb * TS * TS;
   const size_t pub_d = (size_t)2 * nb * TS;
