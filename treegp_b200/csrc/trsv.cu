@@ -35,6 +35,10 @@ constexpr int TS_P = TS + 2;           // shared-memory row pitch in doubles (52
 constexpr int TS_THREADS = 256;
 constexpr int TS_TILE_D = TS * TS_P;   // doubles per staged tile
 constexpr int TS_WIN = 4;              // column blocks of unknowns fetched per wait
+constexpr int TS_HAND = 1;             // distances (blocks before a slab's diagonal) handed over through distributed shared
+                                       // memory inside a cluster.  1 = the chain step only.  Measured with 5 (the near blocks
+                                       // too): hop 0.37 us instead of 0.9 us, but five remote stores per unknown cost the
+                                       // publisher as much again -- no gain, so the near blocks keep the global path
 constexpr int TS_NEAR = 4;              // blocks before its own diagonal from which a slab is fed one block at a time
 
 __device__ int g_tgp_device_error = 0;
@@ -225,22 +229,12 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_
   return r;
 }
 __device__ __forceinline__ void st_remote_f64(uint32_t cluster_addr, double v) {
-  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(cluster_addr), "d"(v) : "memory");
+  asm volatile("st.relaxed.cluster.shared::cluster.f64 [%0], %1;" ::"r"(cluster_addr), "d"(v) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok = 0;
-  unsigned tries = 0;
-  while (!ok) {
-    if (++tries > (1u << 24)) { atomicExch(&g_tgp_device_error, 2); break; }   // never hang the GPU
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_addr(bar)), "r"(parity)
-        : "memory");
-  }
+__device__ __forceinline__ double ld_shared_relaxed_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.cluster.shared::cta.f64 %0, [%1];" : "=d"(v) : "r"(smem_addr(p)) : "memory");
+  return v;
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -258,8 +252,8 @@ trsv_sweep_kernel(TrsvParams P) {
   double* dtile = reinterpret_cast<double*>(smraw);                // D_k of the next chain step
   double* wtile = dtile + TS_TILE_D;                               // W_k / M_k of the next chain step
   double* xs = wtile + TS_TILE_D;                                  // window of unknowns: TS_WIN column blocks
-  double* xc = xs + TS_WIN * TS;                                   // unknowns the chain step waits for
-  double* vs = xc + TS;                                            // b_k - partial sums
+  double* xh = xs + TS_WIN * TS;                                   // hand-over buffers [slab parity][distance 1..TS_HAND][64]:
+  double* vs = xh + 2 * TS_HAND * TS;                              // unknowns of the TS_NEAR blocks before a slab's diagonal; vs = b_k - partial sums
   double* bs = vs + TS;                                            // b of the next chain step (prefetched)
   double* red = bs + TS;                                           // 4 x 64 partials (backward chain step)
   uint64_t* full = reinterpret_cast<uint64_t*>(red + 4 * TS);      // [0] D/W tiles landed, [1] xc filled by a cluster peer
@@ -279,19 +273,23 @@ trsv_sweep_kernel(TrsvParams P) {
 
   if (tid == 0) {
     mbar_init(&full[0], 1);
-    mbar_init(&full[1], TS);                       // one arrival per unknown stored by the previous slab's owner
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < M * ACC_PER_SLAB; i += TS_THREADS) acc[i] = 0.0;
+  for (int i = tid; i < 2 * TS_HAND * TS; i += TS_THREADS) xh[i] = __longlong_as_double(-1ll);   // "nothing handed over yet"
   __syncthreads();
-  if (CS > 1) cluster_sync_all();                  // every peer's barriers exist before anyone arrives on them
+  if (CS > 1) cluster_sync_all();                  // every peer's xc is initialised before anyone stores into it
   // The owner of slab k + 1 is CTA (c + 1) mod G, that of slab k - 1 CTA (c - 1) mod G: inside one cluster the
-  // unknowns are handed over through distributed shared memory (store into the peer's xc + arrive on its barrier,
-  // ~0.2 us) instead of the L2 round trip of the global publication (~1 us), which stays for everybody else.
-  const int next_cta = (c + 1) % G, prev_cta = (c + G - 1) % G;
-  const bool feed_next_local = CS > 1 && G >= 2 && (next_cta / CS == c / CS);
-  const bool fed_by_prev_local = CS > 1 && G >= 2 && (prev_cta / CS == c / CS);
-  uint32_t xphase = 0;
+  // unknowns are handed over through distributed shared memory -- stored straight into the peer's xc, which the peer
+  // polls word by word, the same payload-is-the-flag protocol as the global publication but without the L2 round
+  // trip (~1 us); the global publication stays for everybody else.
+  // The same hand-over serves the TS_NEAR blocks before a slab's diagonal (distance d = 1 is the chain step itself,
+  // d = 2 .. TS_NEAR the block-by-block feeding of the urgent slab): the owner of slab k pushes its unknowns to the
+  // owners of slabs k + 1 .. k + TS_NEAR that sit in its cluster.  local_from(d): is the owner of (my slab - d) a peer?
+  auto peer_ahead = [&](int d) -> int { return (c + d) % G; };
+  auto local_to = [&](int d) -> bool { return CS > 1 && G >= 2 * TS_HAND && (peer_ahead(d) / CS == c / CS); };
+  auto local_from = [&](int d) -> bool { return CS > 1 && G >= 2 * TS_HAND && (((c + G - d) % G) / CS == c / CS); };
+  const bool fed_by_prev_local = local_from(1);
 
   // prefetch what the next chain step (slab index ms) needs: D_k, W_k (bulk async copies) and its right-hand side
   auto prefetch_solve = [&](int ms) {
@@ -373,10 +371,15 @@ trsv_sweep_kernel(TrsvParams P) {
     dphase ^= 1;
     __syncthreads();
     double xv = matvec(dtile, vs, TS);
+    double* xc = xh + ((ms & 1) * TS_HAND + 0) * TS;   // hand-over buffer of this slab, distance 1
     if (kp >= 1) {
       if (fed_by_prev_local) {
-        mbar_wait_cluster(&full[1], xphase);       // the peer has stored all 64 unknowns into xc
-        xphase ^= 1;
+        if (tid < TS) {                            // the peer stores the 64 unknowns straight into xc
+          unsigned spins = 0;
+          while (unpublished(ld_shared_relaxed_f64(xc + tid))) {
+            if (++spins > (1u << 26)) { atomicExch(&g_tgp_device_error, 2); break; }
+          }
+        }
       } else {
         const double* src = P.xpub + (int64_t)(kp - 1) * TS;
         if (tid < TS) {
@@ -395,16 +398,25 @@ trsv_sweep_kernel(TrsvParams P) {
     }
     if (owner) {
       if (unpublished(xv)) xv = __longlong_as_double(0x7ff8000000000000ll);   // never publish the sentinel
-      if (feed_next_local && kp + 1 < nb) {        // first the hop that is on the serial chain
-        const uint32_t peer = (uint32_t)(next_cta % CS);
-        st_remote_f64(map_to_cta(smem_addr(xc + idx), peer), xv);
-        mbar_arrive_remote(map_to_cta(smem_addr(&full[1]), peer));
+#pragma unroll
+      for (int d = 1; d <= TS_HAND; ++d) {         // first the hops that are on (or next to) the serial chain
+        if (local_to(d) && kp + d < nb) {
+          // the peer's slab kp + d is its slab number (kp + d) / G: that parity selects its buffer set
+          double* dst = xh + ((((kp + d) / G) & 1) * TS_HAND + (d - 1)) * TS + idx;
+          st_remote_f64(map_to_cta(smem_addr(dst), (uint32_t)(peer_ahead(d) % CS)), xv);
+        }
       }
       st_relaxed_f64(P.xpub + (int64_t)kp * TS + idx, xv);
       if (idx < w) P.b[r0 + idx] = xv;
     }
     TRSV_STAMP(kp, 2);
     __syncthreads();                               // dtile, wtile, bs, vs, xc are free again
+    // re-arm this slab's hand-over buffer: the next store into it (slab ms + 2) causally follows the publication of
+    // slab ms + 1 by this CTA, which follows this line in program order
+    if (CS > 1) {
+      double* mine = xh + (ms & 1) * TS_HAND * TS;
+      for (int i = tid; i < TS_HAND * TS; i += TS_THREADS) mine[i] = __longlong_as_double(-1ll);
+    }
     prefetch_solve(ms + 1);
   };
 
@@ -523,6 +535,22 @@ trsv_sweep_kernel(TrsvParams P) {
     __syncthreads();
   };
 
+  // the unknowns of the block at distance d before slab index ms's diagonal, handed over by a cluster peer
+  auto fetch_handover = [&](int ms, int d) {
+    __syncthreads();                               // everyone is done with the previous window
+    const double* src = xh + ((ms & 1) * TS_HAND + (d - 1)) * TS;
+    if (tid < TS) {
+      unsigned spins = 0;
+      double v = ld_shared_relaxed_f64(src + tid);
+      while (unpublished(v)) {
+        if (++spins > (1u << 26)) { atomicExch(&g_tgp_device_error, 2); break; }
+        v = ld_shared_relaxed_f64(src + tid);
+      }
+      xs[tid] = v;                                 // (a short block's padding rows are published as zeros)
+    }
+    __syncthreads();
+  };
+
   prefetch_solve(0);
   __syncthreads();
 
@@ -544,7 +572,11 @@ trsv_sweep_kernel(TrsvParams P) {
     const int left = k_next - 1 - j_urg;           // blocks still to apply to the urgent slab, >= 1
     if (left <= TS_NEAR) {
       if (left == TS_NEAR || j_urg == j_rest) prefetch_l2(ms_next, j_urg, left);
-      fetch_window(j_urg, 1, true);
+      if (left + 1 <= TS_HAND && local_from(left + 1)) {   // block j_urg sits left + 1 blocks before the slab's diagonal
+        fetch_handover(ms_next, left + 1);
+      } else {
+        fetch_window(j_urg, 1, true);
+      }
       if (FWD) visit_fwd(ms_next, j_urg, 1); else visit_bwd(ms_next, j_urg, 1);
       ++j_urg;
       continue;
@@ -563,7 +595,7 @@ trsv_sweep_kernel(TrsvParams P) {
 }
 
 static size_t trsv_smem_bytes(bool fwd, int slabs_per_cta) {
-  return (size_t)2 * TS_TILE_D * 8 + (size_t)(TS_WIN * TS + 3 * TS + 4 * TS) * 8 + 2 * 8 +
+  return (size_t)2 * TS_TILE_D * 8 + (size_t)(TS_WIN * TS + 2 * TS_HAND * TS + 2 * TS + 4 * TS) * 8 + 2 * 8 +
          (size_t)slabs_per_cta * TS * 8 * (fwd ? 1 : 8);
 }
 
