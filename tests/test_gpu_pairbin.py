@@ -254,3 +254,27 @@ def test_hilbert_keys_auto_equal_keys_from_host_bounds(gpu_ready):
         _cabi.check(lib.tgp_hilbert_keys(p(x), p(y), n, xmin, ymin, extent, order, p(k1), st), "keys")
         _cabi.check(lib.tgp_hilbert_keys_auto(p(x), p(y), n, order, p(scratch), p(k2), st), "keys_auto")
         assert torch.equal(k1, k2)
+
+
+def test_pairbin_block_forms_match_oracle_at_benchmark_density(gpu_ready):
+    """N = 300 000 points at the benchmark's density and binning (field 548, nbins = 21, default max_sep = half the
+    diagonal): the closed-form / rank-query / two-query block forms and their short cuts against the INDEPENDENT
+    checker (the OpenMP oracle, 4.5e10 pairs, ~25 s on 16 cores) -- at this size most pairs no longer go through the
+    pair-by-pair loop, so this is the comparison that exercises the block forms the way bench.py does."""
+    import os
+
+    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count()))
+    n = 300_000
+    L = 1000.0 * np.sqrt(n / 1e6)
+    rng = np.random.default_rng(2026)
+    x, y = rng.uniform(-L / 2, L / 2, n), rng.uniform(-L / 2, L / 2, n)
+    k = rng.normal(size=n)
+    mx = np.sqrt(2.0) * L / 2.0
+    ref = po.pairbin(x, y, k, None, 0.0, mx, 21, "TwoD")
+    res = _gpu_pairbin(x, y, k, None, 0.0, mx, 21, "TwoD", hilbert=True)
+    _check(res, ref)
+    from treegp_b200 import backend
+
+    st = backend.pairbin_stats(reset=True)
+    tot = max(1, sum(st.values()))
+    assert st["closed_form"] / tot > 0.3 and (st["one_axis_sorted"] + st["two_axis_sorted"]) / tot > 0.2
