@@ -270,11 +270,12 @@ def test_pairbin_block_forms_match_oracle_at_benchmark_density(gpu_ready):
     x, y = rng.uniform(-L / 2, L / 2, n), rng.uniform(-L / 2, L / 2, n)
     k = rng.normal(size=n)
     mx = np.sqrt(2.0) * L / 2.0
-    ref = po.pairbin(x, y, k, None, 0.0, mx, 21, "TwoD")
-    res = _gpu_pairbin(x, y, k, None, 0.0, mx, 21, "TwoD", hilbert=True)
-    _check(res, ref)
     from treegp_b200 import backend
 
+    ref = po.pairbin(x, y, k, None, 0.0, mx, 21, "TwoD")
+    backend.pairbin_stats(reset=True)
+    res = _gpu_pairbin(x, y, k, None, 0.0, mx, 21, "TwoD", hilbert=True)
+    _check(res, ref)
     st = backend.pairbin_stats(reset=True)
     tot = max(1, sum(st.values()))
     assert st["closed_form"] / tot > 0.3 and (st["one_axis_sorted"] + st["two_axis_sorted"]) / tot > 0.2
