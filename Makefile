@@ -6,7 +6,7 @@ NVFLAGS   := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-Wno-unknow
 CSRC      := treegp_b200/csrc
 OBJDIR    := build
 LIB       := treegp_b200/libtreegp_b200.so
-SRCS      := kmat.cu dense.cu trsv.cu predict.cu pairbin.cu microbench.cu hostrng.cu vcorr.cu
+SRCS      := kmat.cu dense.cu trsv.cu predict.cu pairbin.cu microbench.cu hostrng.cu vcorr.cu collective.cu
 OBJS      := $(SRCS:%.cu=$(OBJDIR)/%.o)
 HDRS      := $(wildcard $(CSRC)/*.cuh) $(CSRC)/vk_tables.h include/treegp_b200.h
 
@@ -17,7 +17,7 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; exit 1)
 
 $(LIB): $(OBJS)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -Xlinker -soname,libtreegp_b200.so
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -Xlinker -soname,libtreegp_b200.so -ldl
 
 oracle:
 	$(MAKE) -C oracle

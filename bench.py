@@ -324,6 +324,22 @@ def run_ours(args):
     off = backend.to_device(np.array([0, n]), torch.int64)
     edges = backend.to_device(binning.twod_thresholds(mx, NBINS))
     launches = 0
+    # the exchange step behind the C ABI (tgp_allreduce_bins: NCCL bound by the library at run time); torch.distributed's
+    # all-reduce if that communicator cannot be made
+    comm, collective = None, "none"
+    if world > 1:
+        try:
+            comm = dist.CabiComm(rank, world)
+            collective = "tgp_allreduce_bins (C ABI, NCCL via dlopen)"
+        except Exception as exc:      # noqa: BLE001
+            collective = "torch.distributed all_reduce (CabiComm failed: %s)" % (exc,)
+
+    def reduce_bins(res):
+        if comm is not None:
+            return comm.allreduce_packed_bins(res)          # plane 0 stays int64 words
+        return dist.allreduce_packed_bins(dist.WORLD, res)  # plane 0 becomes FP64 values
+
+    counts_are_words = world == 1 or comm is not None
 
     def count(sep, ed):
         """one device-resident step: pair count of this rank's tiles (+ ONE all-reduce of the packed bin sums)"""
@@ -341,7 +357,7 @@ def run_ours(args):
             res = count(sep, ed)
             e1.record()
             if world > 1:
-                res = dist.allreduce_packed_bins(dist.WORLD, res)
+                res = reduce_bins(res)
             e2.record()
             barrier()
             step_ms.append(max_over_ranks(e0.elapsed_time(e2)))
@@ -349,7 +365,7 @@ def run_ours(args):
         return res, step_ms, kern_ms
 
     def total_count(res):
-        return int(res[0].sum().item()) if world > 1 else int(res[0].view(torch.int64).sum().item())
+        return int(res[0].view(torch.int64).sum().item()) if counts_are_words else int(res[0].sum().item())
 
     # per-pair mode first (block forms off: every pair of every in-range block goes through the compare /
     # masked-FMA loop): this is the kernel the FP64-issue roofline of 10 ops per pair applies to
@@ -372,7 +388,7 @@ def run_ours(args):
     counted = total_count(res)
     total_ms = float(np.sum(step_ms))
     value = npairs_total * args.steps / (total_ms * 1e-3)
-    as_int = (lambda t: t[0]) if world > 1 else (lambda t: t[0].view(torch.int64))
+    as_int = (lambda t: t[0].view(torch.int64)) if counts_are_words else (lambda t: t[0])
     same_counts = bool(total_count(res_pp) == counted and torch.equal(as_int(res_pp), as_int(res)))
 
     # ---------------- 2PCF: end to end through the public API (host buffers) ----------------
@@ -387,7 +403,7 @@ def run_ours(args):
     Xp, yp, yerrp = pinned(np.ascontiguousarray(X)), pinned(y), pinned(y_err)
     e2e_ms = []
     tp = treegp.two_pcf(Xp, yp, yerrp, mn, mx, nbins=NBINS, anisotropic=True)
-    tp.group = dist.WORLD if world > 1 else False
+    tp.group = (comm if comm is not None else dist.WORLD) if world > 1 else False
     for i in range(2 + args.steps):
         barrier()
         t0 = time.perf_counter()
@@ -444,9 +460,11 @@ def run_ours(args):
                                "diagonal (configs[3])" % n,
                    "pairs_per_step": npairs_total, "pairs_in_range_x2": counted,
                    "sharding": "pair tiles over %d rank(s) + ONE NCCL allreduce of the packed bin sums" % world,
+                   "collective": collective,
                    "l2": "256 MB buffer written between timed iterations (L2 flush)"},
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_call": float(np.mean(e2e_ms)),
+                "collective": collective,
                 "api": "treegp_b200.two_pcf(...).comp_2pcf(X, y, y_err) with host numpy inputs (page-locked)"},
         "gpu_launches": launches,
         "clocks": clocks,

@@ -233,6 +233,21 @@ int tgp_vcorr(const double* x, const double* y, const double* vx, const double* 
               const double* edges, int32_t nbins, int64_t* counts, double* sums, int64_t* amb_pairs,
               int32_t amb_cap, int32_t* amb_count, void* stream);
 
+/* ---- the exchange step of the sharded pair binning ----------------------------------
+ * NCCL bound at run time (dlopen); TGP_ERR_UNSUPPORTED if no libnccl can be found.
+ *  tgp_comm_unique_id : rank 0 fills 128 bytes that every rank must pass to tgp_comm_init_rank (ship them by any means).
+ *  tgp_comm_init_rank : collective over the `nranks` processes (one GPU each, the current device); *comm receives an
+ *                       opaque handle.
+ *  tgp_allreduce_bins : in-place sum over the ranks of the packed bin buffer that tgp_pairbin filled on each rank:
+ *                       `planes` x `per_plane` doubles (plane 0 = the int64 pair counts as raw 8-byte words, then sumw,
+ *                       sumwkk[, sumwr], per_plane = ncat * nb).  Plane 0 is reduced as FP64 VALUES (exact below 2^53)
+ *                       and converted back, so on return it holds int64 counts again -- identical for any number of
+ *                       ranks.  Asynchronous on `stream`. */
+int tgp_comm_unique_id(void* id128 /*host, 128 bytes*/);
+int tgp_comm_init_rank(const void* id128 /*host*/, int32_t rank, int32_t nranks, void** comm /*host*/);
+int tgp_comm_destroy(void* comm);
+int tgp_allreduce_bins(void* comm, double* packed, int64_t planes, int64_t per_plane, void* stream);
+
 /* Sticky device-side error word: set (never cleared by the kernels) when an inter-CTA flag wait inside
  * tgp_potrs_vec / tgp_loglike(want_alpha) timed out -- which cannot happen with the cooperative launch those
  * sweeps use, but would otherwise leave unknowns unsolved without any other sign.  Synchronises the device and

@@ -281,3 +281,29 @@ def test_eb_pair_sums_and_api_on_the_device(gpu_ready):
     xie2, xib2, logr2 = treegp.comp_eb_treecorr(x, y, dx, dy, rmin=rmin, rmax=rmax, dlogr=dlogr)
     assert xie.shape == xib.shape == logr.shape == xie2.shape == (bins,)
     np.testing.assert_allclose((xie + xib)[ok], xp[ok], atol=1e-12)
+
+
+def test_cabi_collective_single_rank(gpu_ready):
+    """tgp_comm_* / tgp_allreduce_bins (NCCL bound by the library at run time) with a one-rank communicator: the
+    packed bin buffer comes back unchanged, plane 0 still holding int64 counts; two_pcf accepts the communicator as
+    its group.  (The two- and eight-rank exchange runs in bench.py under torchrun.)"""
+    import torch
+    import treegp_b200 as treegp
+    from treegp_b200 import dist
+
+    comm = dist.CabiComm(0, 1)
+    packed = torch.zeros((3, 2, 9), dtype=torch.float64, device="cuda")
+    counts = torch.arange(18, dtype=torch.int64, device="cuda").reshape(2, 9) * 1234567891
+    packed[0] = counts.view(torch.float64)
+    packed[1:] = torch.randn((2, 2, 9), dtype=torch.float64, device="cuda")
+    before = packed.clone()
+    comm.allreduce_packed_bins(packed)
+    torch.cuda.synchronize()
+    assert torch.equal(packed[0].view(torch.int64), counts) and torch.equal(packed[1:], before[1:])
+    rng = np.random.default_rng(0)
+    X, y = rng.uniform(-5, 5, size=(500, 2)), rng.normal(size=500)
+    t = treegp.two_pcf(X, y, np.full(500, 0.1), 0.0, 3.0, nbins=9, anisotropic=True)
+    xi0 = t.comp_2pcf(X, y, np.full(500, 0.1))[0]
+    t.group = comm
+    np.testing.assert_array_equal(t.comp_2pcf(X, y, np.full(500, 0.1))[0], xi0)
+    comm.close()

@@ -23,9 +23,11 @@ def _pg(group):
 
 def rank_world(group=None):
     """(rank, world) of `group`.  False: explicitly single-process -> (0, 1).  None / WORLD: the default process
-    group, or (0, 1) when torch.distributed is not initialised.  Otherwise a ProcessGroup."""
+    group, or (0, 1) when torch.distributed is not initialised.  A CabiComm carries its own.  Otherwise a ProcessGroup."""
     if group is False:
         return 0, 1
+    if isinstance(group, CabiComm):
+        return group.rank, group.world
     if group in (None, WORLD) and not (tdist.is_available() and tdist.is_initialized()):
         return 0, 1
     return tdist.get_rank(_pg(group)), tdist.get_world_size(_pg(group))
@@ -46,6 +48,51 @@ def allreduce_packed_bins(group, packed):
     packed[0] = packed[0].view(torch.int64).to(torch.float64)
     tdist.all_reduce(packed, op=tdist.ReduceOp.SUM, group=_pg(group))
     return packed
+
+
+class CabiComm(object):
+    """The all-reduce of the bin sums behind the C ABI (tgp_comm_* / tgp_allreduce_bins: NCCL bound by the library at run
+    time), for callers that shard the pair tiles without torch.distributed collectives on the data path.  Construction
+    is collective: `exchange(buf)` must return rank 0's 128-byte id on every rank -- by default a torch.distributed
+    broadcast (plumbing only; any transport will do).  Usable as `two_pcf.group`."""
+
+    def __init__(self, rank, world, exchange=None):
+        import ctypes
+        from . import _cabi
+
+        self.rank, self.world = int(rank), int(world)
+        lib = _cabi.load()
+        ident = (ctypes.c_ubyte * 128)()
+        if self.rank == 0:
+            _cabi.check(lib.tgp_comm_unique_id(ident), "tgp_comm_unique_id")
+        if self.world > 1:
+            if exchange is None:
+                t = torch.tensor(list(ident), dtype=torch.uint8, device="cuda")
+                tdist.broadcast(t, src=0)
+                raw = bytes(t.cpu().tolist())
+            else:
+                raw = exchange(bytes(ident))
+            ident = (ctypes.c_ubyte * 128).from_buffer_copy(raw)
+        self._handle = ctypes.c_void_p(0)
+        _cabi.check(lib.tgp_comm_init_rank(ident, self.rank, self.world, ctypes.byref(self._handle)), "tgp_comm_init_rank")
+
+    def allreduce_packed_bins(self, packed):
+        """In-place sum of the packed bin buffer over the ranks; plane 0 holds int64 counts (raw words) before and after."""
+        import ctypes
+        from . import _cabi
+
+        planes, per_plane = int(packed.shape[0]), int(packed[0].numel())
+        _cabi.check(_cabi.load().tgp_allreduce_bins(self._handle, ctypes.c_void_p(packed.data_ptr()), planes, per_plane,
+                                                    ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                    "tgp_allreduce_bins")
+        return packed
+
+    def close(self):
+        from . import _cabi
+
+        if self._handle:
+            _cabi.load().tgp_comm_destroy(self._handle)
+            self._handle = None
 
 
 def slab(n, rank, world):

@@ -226,11 +226,16 @@ class two_pcf(object):
         packed = backend.pairbin_packed(
             px, py, pk, pw, offsets, max_len, bt, self._device_edges(edges), self.nbins,
             self.min_sep, self.max_sep, rank=rank, nranks=world)
-        if world > 1:
-            packed = dist.allreduce_packed_bins(self.group, packed)   # ONE collective for all bin arrays
+        values = False
+        if world > 1:                                                 # ONE collective for all bin arrays
+            if isinstance(self.group, dist.CabiComm):
+                packed = self.group.allreduce_packed_bins(packed)     # behind the C ABI; counts stay int64 words
+            else:
+                packed = dist.allreduce_packed_bins(self.group, packed)
+                values = True
         host = packed.cpu().numpy()                                   # ONE device->host transfer
-        # plane 0: pair counts -- raw int64 words from the kernel, FP64 values after an all-reduce
-        counts = host[0].astype(np.int64) if world > 1 else np.ascontiguousarray(host[0]).view(np.int64)
+        # plane 0: pair counts -- raw int64 words from the kernel, FP64 values after a torch all-reduce
+        counts = host[0].astype(np.int64) if values else np.ascontiguousarray(host[0]).view(np.int64)
         sw, swkk = host[1], host[2]
         has_wr = host.shape[0] == 4
         with np.errstate(invalid="ignore", divide="ignore"):
