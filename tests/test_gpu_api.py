@@ -304,6 +304,9 @@ def test_cabi_collective_single_rank(gpu_ready):
     X, y = rng.uniform(-5, 5, size=(500, 2)), rng.normal(size=500)
     t = treegp.two_pcf(X, y, np.full(500, 0.1), 0.0, 3.0, nbins=9, anisotropic=True)
     xi0 = t.comp_2pcf(X, y, np.full(500, 0.1))[0]
+    n0 = t._last_npairs.copy()
     t.group = comm
-    np.testing.assert_array_equal(t.comp_2pcf(X, y, np.full(500, 0.1))[0], xi0)
+    xi1 = t.comp_2pcf(X, y, np.full(500, 0.1))[0]
+    np.testing.assert_array_equal(t._last_npairs, n0)
+    np.testing.assert_allclose(xi1, xi0, rtol=0, atol=1e-13 * np.abs(xi0).max())   # FP64 sums: atomic order
     comm.close()
