@@ -233,6 +233,15 @@ int tgp_vcorr(const double* x, const double* y, const double* vx, const double* 
               const double* edges, int32_t nbins, int64_t* counts, double* sums, int64_t* amb_pairs,
               int32_t amb_cap, int32_t* amb_count, void* stream);
 
+/* Batched chi-square of the robust anisotropic fit: for each of `nsets` parameter triples (size, g1, g2) the objective
+ * robust_2dfit.chi2 (two_pcf.py:115-148) -- model profile of `family` (TGP_FAM_RBF | TGP_FAM_VONKARMAN) at the P masked
+ * bin lags for the correlation-length matrix of (size, g1, g2) (two_pcf.py:12-31), analytic amplitude and offset,
+ * chi2 = r^T W r; +inf outside |g| <= 1 or for non-finite parameters.
+ *  coord : device double[2 P] (dx, dy) of the masked pixels;  y : device double[P] masked xi;  W : device double[P * P];
+ *  params: device double[3 nsets];  out : device double[4 nsets] = {chi2, |amplitude|, offset, 1 if evaluated}. */
+int tgp_robust_chi2_batch(const double* coord, const double* y, const double* W, int32_t P, int32_t family,
+                          const double* params, int32_t nsets, double* out, void* stream);
+
 /* ---- the exchange step of the sharded pair binning ----------------------------------
  * NCCL bound at run time (dlopen); TGP_ERR_UNSUPPORTED if no libnccl can be found.
  *  tgp_comm_unique_id : rank 0 fills 128 bytes that every rank must pass to tgp_comm_init_rank (ship them by any means).

@@ -143,6 +143,30 @@ def install():
 
     backend.pairbin_packed = pairbin_packed
 
+    def robust_chi2_batch(coord_d, y_d, W_d, family, params):
+        """numpy restatement of two_pcf.py:12-31,96-148 (the objective of the robust fit) for the stand-in."""
+        coord, yv, W = _np(coord_d), _np(y_d), _np(W_d)
+        out = np.zeros((len(params), 4))
+        for i, (size, g1, g2) in enumerate(np.asarray(params, dtype=float).reshape(-1, 3)):
+            if not np.isfinite(size + g1 + g2) or abs(g1) > 1 or abs(g2) > 1:
+                out[i, 0] = np.inf
+                continue
+            e = np.sqrt(g1 ** 2 + g2 ** 2)
+            q = (1 - e) / (1 + e)
+            phi = 0.5 * np.arctan2(g2, g1)
+            rot = np.array([[np.cos(phi), np.sin(phi)], [-np.sin(phi), np.cos(phi)]])
+            Lm = rot.T @ np.diag([size ** 2, (size * q) ** 2]) @ rot
+            model = go.kmat(_FAM[family], coord, np.zeros((1, 2)), amp=1.0, invLam=np.linalg.inv(Lm))[:, 0]
+            F = np.array([model, np.ones_like(model)]).T
+            FtW = F.T @ W
+            alpha = np.linalg.inv(FtW @ F) @ (FtW @ yv)
+            alpha[0] = abs(alpha[0])
+            r = yv - (alpha[0] * model + alpha[1])
+            out[i] = [r @ W @ r, alpha[0], alpha[1], 1.0]
+        return out
+
+    backend.robust_chi2_batch = robust_chi2_batch
+
     def knn_mean(X0, y0, Xq, k):
         from sklearn.neighbors import KNeighborsRegressor   # what the reference itself calls (gp_interp.py:236-238)
 

@@ -56,6 +56,7 @@ SIGNATURES = {
     "tgp_hilbert_keys_auto": [_vp, _vp, _i64, _i32, _vp, _vp, _vp],
     "tgp_bootstrap_multiplicities": [_vp, _i64, _i64, _vp, _vp],
     "tgp_device_error": [_i32],
+    "tgp_robust_chi2_batch": [_vp, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp],
     "tgp_comm_unique_id": [_vp],
     "tgp_comm_init_rank": [_vp, _i32, _i32, _vp],
     "tgp_comm_destroy": [_vp],

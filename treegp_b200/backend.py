@@ -300,6 +300,18 @@ def vcorr_sums(x, y, dx, dy, logrmin, dlogr, bins):
     return (c, s[0], s[1], s[2] + 1j * s[3], s[4] + 1j * s[5])
 
 
+def robust_chi2_batch(coord_d, y_d, W_d, family, params):
+    """chi2, |amplitude|, offset of robust_2dfit.chi2 (two_pcf.py:115-148) for every row (size, g1, g2) of `params`
+    in ONE launch (tgp_robust_chi2_batch).  coord_d (P, 2), y_d (P,), W_d (P, P): device tensors of the masked pixels.
+    Returns a (len(params), 4) numpy array; chi2 = inf where the reference returns inf."""
+    params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 3)
+    pd = to_device(params)
+    out = torch.empty((params.shape[0], 4), dtype=F64, device=coord_d.device)
+    check(_cabi.load().tgp_robust_chi2_batch(_p(coord_d), _p(y_d), _p(W_d), int(y_d.numel()), int(family), _p(pd),
+                                             int(params.shape[0]), _p(out), _stream()), "tgp_robust_chi2_batch")
+    return out.cpu().numpy()
+
+
 def hilbert_order(px, py):
     """Permutation (device int64) that sorts the points along a Hilbert curve; makes tgp_pairbin's
     register path applicable.  The argsort is torch plumbing; the keys come from the C ABI."""

@@ -19,8 +19,9 @@ import numpy as np
 
 
 class Migrad(object):
-    def __init__(self, fcn, start, errordef=1.0, tol=0.1, max_calls=4000):
+    def __init__(self, fcn, start, errordef=1.0, tol=0.1, max_calls=4000, fcn_batch=None):
         self.fcn = fcn
+        self.fcn_batch = fcn_batch          # optional: values of several points at once (one device launch)
         self.values = np.array(start, dtype=float)
         self.errordef = float(errordef)
         self.tol = float(tol)
@@ -39,6 +40,14 @@ class Migrad(object):
         v = float(v)
         return v if np.isfinite(v) else np.inf
 
+    def _fmany(self, xs):
+        """Values at several points: one call of fcn_batch if there is one, else point by point."""
+        if self.fcn_batch is None or len(xs) < 2:
+            return [self._f(x) for x in xs]
+        self.nfcn += len(xs)
+        vals = np.asarray(self.fcn_batch(np.asarray(xs, dtype=float)), dtype=float)
+        return [float(v) if np.isfinite(v) else np.inf for v in vals]
+
     def _steps(self, x):
         # like Minuit's default initial errors: 1 % of the value, 0.01 for parameters at zero
         return np.where(x != 0.0, 1e-2 * np.abs(x), 1e-2)
@@ -46,8 +55,22 @@ class Migrad(object):
     def _gradient(self, x, f0, h):
         n = len(x)
         g, g2 = np.zeros(n), np.zeros(n)
+        first = None
+        if self.fcn_batch is not None:      # the 2 n probes of the first attempt in one launch
+            pts = []
+            for i in range(n):
+                xp, xm = x.copy(), x.copy()
+                xp[i] += h[i]
+                xm[i] -= h[i]
+                pts += [xp, xm]
+            first = self._fmany(pts)
         for i in range(n):
             hi = h[i]
+            if first is not None and np.isfinite(first[2 * i]) and np.isfinite(first[2 * i + 1]):
+                fp, fm = first[2 * i], first[2 * i + 1]
+                g[i] = (fp - fm) / (2.0 * hi)
+                g2[i] = (fp + fm - 2.0 * f0) / (hi * hi)
+                continue
             for _ in range(8):  # shrink until both probes are finite
                 xp, xm = x.copy(), x.copy()
                 xp[i] += hi
@@ -65,18 +88,26 @@ class Migrad(object):
     def _hessian(self, x, f0, h):
         n = len(x)
         H = np.zeros((n, n))
-        fp, fm = np.zeros(n), np.zeros(n)
+        # all 2 n + n (n - 1) / 2 probes first (one launch with fcn_batch), in the order they are used below
+        pts = []
         for i in range(n):
             e = np.zeros(n)
             e[i] = h[i]
-            fp[i], fm[i] = self._f(x + e), self._f(x - e)
-            H[i, i] = (fp[i] + fm[i] - 2.0 * f0) / (h[i] * h[i])
+            pts += [x + e, x - e]
         for i in range(n):
             for j in range(i):
                 e = np.zeros(n)
                 e[i], e[j] = h[i], h[j]
-                fpp = self._f(x + e)
-                H[i, j] = H[j, i] = (fpp - fp[i] - fp[j] + f0) / (h[i] * h[j])
+                pts.append(x + e)
+        vals = self._fmany(pts)
+        fp, fm = np.array(vals[0:2 * n:2]), np.array(vals[1:2 * n:2])
+        for i in range(n):
+            H[i, i] = (fp[i] + fm[i] - 2.0 * f0) / (h[i] * h[i])
+        k = 2 * n
+        for i in range(n):
+            for j in range(i):
+                H[i, j] = H[j, i] = (vals[k] - fp[i] - fp[j] + f0) / (h[i] * h[j])
+                k += 1
         return H
 
     def _line_search(self, x, f0, p, slope):

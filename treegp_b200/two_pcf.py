@@ -117,11 +117,23 @@ class robust_2dfit(object):
         self.chi2_value = self.residuals.dot(self.W).dot(self.residuals.reshape((len(model), 1)))
         return self.chi2_value[0]
 
+    def chi2_batch(self, params):
+        """chi2 of several parameter sets [size, g1, g2] in one device launch (the probes of a numerical gradient or
+        Hessian): same objective as `chi2`, without its side effects (alpha, residuals, kernel_fit)."""
+        if getattr(self, "_dev", None) is None:
+            fam = _cabi.FAM_VONKARMAN if self.kernel_class is kernels.AnisotropicVonKarman else _cabi.FAM_RBF
+            self._dev = (backend.to_device(np.ascontiguousarray(self.coord[self.mask])),
+                         backend.to_device(np.ascontiguousarray(self.flat_data[self.mask])),
+                         backend.to_device(np.ascontiguousarray(self.W)), fam)
+        coord_d, y_d, W_d, fam = self._dev
+        return backend.robust_chi2_batch(coord_d, y_d, W_d, fam, params)[:, 0]
+
     def _minimize_minuit(self, p0=[3000.0, 0.2, 0.2]):
         """One variable-metric minimisation started at p0 = [size, g1, g2]."""
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            self.m = Migrad(self.chi2, p0)
+            batch = self.chi2_batch if 2 <= int(np.sum(self.mask)) <= 1024 else None
+            self.m = Migrad(self.chi2, p0, fcn_batch=batch)
             self.m.migrad()
             results = list(self.m.values)
             self._fit_ok = self.m.accurate
