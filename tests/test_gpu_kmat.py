@@ -93,3 +93,18 @@ def test_unsupported_kernel_raises(gpu_ready):
 
     with pytest.raises(TgpError):
         lower_kernel(RBF(1.0) + WhiteKernel(0.1), 2)
+
+
+def test_coordinate_width_must_match_the_kernel(gpu_ready):
+    """A 2-D kernel on (N, 1) coordinates, or X / Y of different widths, is an error (the reference raises from
+    pdist / cdist); the device kernels would otherwise read past the coordinate buffers."""
+    import treegp_b200 as treegp
+
+    k2 = treegp.eval_kernel("2.0 * AnisotropicRBF(invLam=array([[0.5, 0.1], [0.1, 0.4]]))")
+    X1 = np.random.default_rng(0).uniform(-1, 1, size=(10, 1))
+    X2 = np.random.default_rng(1).uniform(-1, 1, size=(10, 2))
+    with pytest.raises(ValueError):
+        k2(X1)
+    with pytest.raises(ValueError):
+        k2(X2, Y=X1)
+    assert k2(X2).shape == (10, 10)

@@ -104,7 +104,10 @@ kmat_sym_kernel(const double* __restrict__ X, int64_t N, KDesc kd, const double*
   const bool diag_tile = (I == J);
   const bool mirror = !diag_tile && !lower_only;
 
-#pragma unroll
+  // von Karman: the profile (series / per-binade polynomial, sqrt, cbrt, exp) is ~350 instructions per evaluation;
+  // unrolled 8 x 2 times the kernel was 94 KB of SASS and stalled on instruction fetch (no_instruction 4.4 per
+  // issue, profiles/r2_start_kmat_vk.ncu.txt) -- two rows per trip keep it inside the instruction cache
+#pragma unroll(FAM == TGP_FAM_VONKARMAN ? 2 : KT / 8)
   for (int rr = 0; rr < KT / 8; ++rr) {
     const int rl = warp + 8 * rr;
     const int64_t rg = r0 + rl;
@@ -182,7 +185,7 @@ kmat_cross_kernel(const double* __restrict__ Xs, int64_t M, const double* __rest
   const int cl = 2 * lane;
   const double cx0 = xc[cl], cy0 = yc[cl], cx1 = xc[cl + 1], cy1 = yc[cl + 1];
   const int64_t cg = c0 + cl;
-#pragma unroll
+#pragma unroll(FAM == TGP_FAM_VONKARMAN ? 2 : KT / 8)
   for (int rr = 0; rr < KT / 8; ++rr) {
     const int rl = warp + 8 * rr;
     const int64_t rg = r0 + rl;
