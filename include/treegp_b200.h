@@ -214,6 +214,37 @@ int tgp_hilbert_keys_auto(const double* x, const double* y, int64_t n, int32_t o
  *  mult  : host uint8[b * n], overwritten.  More than 255 draws of one point -> TGP_ERR_UNSUPPORTED. */
 int tgp_bootstrap_multiplicities(uint64_t* state, int64_t n, int64_t b, const int64_t* pos, uint8_t* mult);
 
+/* Bootstrap batch of the TwoD two-point function with the pair geometry shared by all resamples (replaces the loop
+ * of two_pcf.py:342-362: n_bootstrap x [resample_bootstrap :269-281 + comp_2pcf :283-328]).  A resample is the BASE
+ * catalogue with integer multiplicities; TreeCorr skips the zero-distance pairs between copies of a point, so with
+ * a_b[i] = mult[b][i] * w_i and c_b[i] = a_b[i] * z_i the sums over the pairs (i < j) of the base catalogue in a bin
+ *     S0 = sum a_i a_j,  S1 = sum (c_i a_j + a_i c_j),  S2 = sum c_i c_j
+ * give sumw = S0 and, with delta_b = sum_i mult[b][i] z_i / n (the mean of the resampled values, np.mean(y) of
+ * two_pcf.py:297), sumwkk = S2 - delta_b S1 + delta_b^2 S0.
+ *  px, py, pz, pw : device double[n], the base catalogue (Hilbert order recommended, see tgp_hilbert_keys); pz the
+ *                   field minus ANY fixed constant (e.g. its mean); pw the weights or NULL (unit weights).
+ *  mult           : device uint8[nboot * n], resample-major (the layout tgp_bootstrap_multiplicities writes).
+ *  edges, nbins, min_sep2, max_sep : as for tgp_pairbin with TGP_BIN_TWOD (same thresholds, same pair rule).
+ *  tile_rank, tile_nranks : multi-GPU sharding of the work items; the per-rank `sums` add up.
+ *  sums           : device double[tgp_bootbin_sums_doubles(nbins, nboot)] = [2][3][nbins^2][bpad], bpad = nboot
+ *                   rounded up to a multiple of 32; OVERWRITTEN: forward-entry sums S0, S1, S2 per bin and resample,
+ *                   then corrections for pairs whose mirrored bin is not the mirror image of the forward bin.
+ *  delta          : device double[bpad], overwritten (identical on every rank).
+ *  work           : device scratch of tgp_bootbin_work_bytes(n, nboot) bytes, 256-byte aligned.
+ * tgp_bootbin_xi turns (all-reduced) sums into xi[nboot][nbins^2] = sumwkk / sumw (0 where sumw == 0) and, if
+ * sumw_out != NULL, sumw[nboot][nbins^2]. */
+int tgp_bootbin_twod(const double* px, const double* py, const double* pz, const double* pw, int64_t n,
+                     const uint8_t* mult, int32_t nboot, const double* edges, int32_t nbins, double min_sep2,
+                     double max_sep, int32_t tile_rank, int32_t tile_nranks, double* sums, double* delta,
+                     void* work, void* stream);
+int tgp_bootbin_xi(const double* sums, const double* delta, int32_t nbins, int32_t nboot, double* xi,
+                   double* sumw_out, void* stream);
+int64_t tgp_bootbin_work_bytes(int64_t n, int32_t nboot);
+int64_t tgp_bootbin_sums_doubles(int32_t nbins, int32_t nboot);
+/* Diagnostics: blocks per path of all tgp_bootbin_twod launches since the last reset: [0] booked whole, [1] axis
+ * sweeps, [2] pair-by-pair blocks, [3] exact per-pair blocks, [4] window flushes, [5] sweeps handed back. */
+int tgp_bootbin_stats(unsigned long long* host8 /*host*/, int reset);
+
 /* Pair sums of a VECTOR field's 2-point functions in log-radius bins (E/B diagnostics; replaces the all-pairs numpy
  * loop of utils.py:5-74 and TreeCorr's VVCorrelation of utils.py:110-155 in the bin_slop -> 0 limit).
  *  x, y, vx, vy : n points and the vector field there.
@@ -281,7 +312,9 @@ int tgp_pairbin_stats(unsigned long long* host8 /*host*/, int reset);
  * "pairbin_fast_paths": bit mask, default all on; bit 0 = short-cut dispatch of one-axis blocks that fit the open
  * bin window, bit 1 = 2 x 2-window blocks take their marginal sums from rank queries, bit 2 = the pair-by-pair kernel
  * ("pairbin_block_sums" 0) skips the per-pair mirrored-bin check in blocks whose bounding boxes prove it
- * (0 = the general paths only; results are identical either way). */
+ * (0 = the general paths only; results are identical either way); "bootbin_paths": bit mask of tgp_bootbin_twod,
+ * default all on; bit 0 = blocks in one bin booked from chunk sums, bit 1 = window paths (0: every block through the
+ * exact per-pair path), bit 2 = axis sweeps. */
 int tgp_set_option(const char* name, int value);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */

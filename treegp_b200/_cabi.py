@@ -55,6 +55,11 @@ SIGNATURES = {
     "tgp_hilbert_keys": [_vp, _vp, _i64, _f64, _f64, _f64, _i32, _vp, _vp],
     "tgp_hilbert_keys_auto": [_vp, _vp, _i64, _i32, _vp, _vp, _vp],
     "tgp_bootstrap_multiplicities": [_vp, _i64, _i64, _vp, _vp],
+    "tgp_bootbin_twod": [_vp, _vp, _vp, _vp, _i64, _vp, _i32, _vp, _i32, _f64, _f64, _i32, _i32, _vp, _vp, _vp, _vp],
+    "tgp_bootbin_xi": [_vp, _vp, _i32, _i32, _vp, _vp, _vp],
+    "tgp_bootbin_work_bytes": [_i64, _i32],
+    "tgp_bootbin_sums_doubles": [_i32, _i32],
+    "tgp_bootbin_stats": [_vp, ctypes.c_int],
     "tgp_device_error": [_i32],
     "tgp_robust_chi2_batch": [_vp, _vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp],
     "tgp_comm_unique_id": [_vp],
@@ -68,7 +73,8 @@ SIGNATURES = {
     "tgp_microbench_fp64": [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)],
 }
 _RESTYPES = {"tgp_last_error": ctypes.c_char_p, "tgp_pairbin_work_doubles": ctypes.c_int64,
-             "tgp_predict_work_doubles": ctypes.c_int64, "tgp_profile_qcut": ctypes.c_double}
+             "tgp_predict_work_doubles": ctypes.c_int64,
+             "tgp_bootbin_work_bytes": ctypes.c_int64, "tgp_bootbin_sums_doubles": ctypes.c_int64, "tgp_profile_qcut": ctypes.c_double}
 
 _lib = None
 

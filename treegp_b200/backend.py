@@ -255,6 +255,43 @@ def pairbin(px, py, pk, pw, cat_off, max_cat_len, bin_type, edges, nbins, min_se
     return out[0].view(torch.int64), out[1], out[2], (out[3] if out.shape[0] == 4 else None)
 
 
+def bootbin_sums(px, py, pz, pw, mult, edges, nbins, min_sep, max_sep, rank=0, nranks=1):
+    """Pair sums of a bootstrap batch with shared geometry (tgp_bootbin_twod).  px, py, pz, pw|None: the base
+    catalogue on the device (Hilbert order); mult: (nboot, n) uint8 device tensor of multiplicities.  Returns
+    (sums, delta): the packed (6 * nb * bpad) forward / correction sums of this rank and the resample means."""
+    n = int(px.numel())
+    nboot = int(mult.shape[0])
+    dev = px.device
+    lib = _cabi.load()
+    bpad = (nboot + 31) // 32 * 32
+    sums = torch.empty(int(lib.tgp_bootbin_sums_doubles(int(nbins), nboot)), dtype=F64, device=dev)
+    delta = torch.empty(bpad, dtype=F64, device=dev)
+    nbytes = int(lib.tgp_bootbin_work_bytes(n, nboot))
+    work = _pairbin_scratch(dev, nbytes // 8 + 64)
+    off = (-work.data_ptr()) % 256          # torch allocations are 512-byte aligned; kept general
+    check(lib.tgp_bootbin_twod(_p(px), _p(py), _p(pz), _p(pw), n, _p(mult), nboot, _p(edges), int(nbins),
+                               float(min_sep) ** 2, float(max_sep), int(rank), int(nranks), _p(sums), _p(delta),
+                               ctypes.c_void_p(work.data_ptr() + off), _stream()), "tgp_bootbin_twod")
+    return sums, delta
+
+
+def bootbin_xi(sums, delta, nbins, nboot, want_sumw=False):
+    """xi (nboot, nbins^2) [and sumw] from the (all-reduced) sums of bootbin_sums."""
+    xi = torch.empty((int(nboot), int(nbins) ** 2), dtype=F64, device=sums.device)
+    sw = torch.empty_like(xi) if want_sumw else None
+    check(_cabi.load().tgp_bootbin_xi(_p(sums), _p(delta), int(nbins), int(nboot), _p(xi), _p(sw), _stream()),
+          "tgp_bootbin_xi")
+    return (xi, sw) if want_sumw else xi
+
+
+def bootbin_stats(reset=True):
+    """Blocks per path of tgp_bootbin_twod since the last reset; synchronises the device."""
+    buf = (ctypes.c_ulonglong * 8)()
+    check(_cabi.load().tgp_bootbin_stats(buf, int(bool(reset))), "tgp_bootbin_stats")
+    keys = ("closed_form", "sweeps", "pairwise", "exact_per_pair", "flushes", "sweeps_handed_back")
+    return {k: int(buf[i]) for i, k in enumerate(keys)}
+
+
 def vcorr_sums(x, y, dx, dy, logrmin, dlogr, bins):
     """Pair sums of the vector-field correlation functions (utils.py:5-74) as numpy arrays:
     counts, sum ln r, sum Re(v1 conj v2), sum v1 v2 (complex), sum v1 v2 conj(d)^2/|d|^2 (complex).

@@ -259,6 +259,7 @@ class two_pcf(object):
                 rnom = np.exp(np.log(self.min_sep) + (np.arange(self.nbins) + 0.5) * bs)
                 meanr = np.where(sw != 0, host[3] / sw, rnom[None, :])
         self._last_npairs = counts
+        self._last_sumw = sw
         return xi, meanr
 
     def _device_edges(self, edges):
@@ -346,8 +347,14 @@ class two_pcf(object):
             raise _cabi.TgpError("a point was drawn more than 255 times in one resample")
         return torch.as_tensor(cnt.astype(np.uint8))
 
+    # Bootstrap batches share the pair geometry across resamples (tgp_bootbin_twod); False: every resample is an
+    # independent weighted catalogue of one tgp_pairbin launch (the round-1 batch, kept as the cross-check).
+    SHARED_BOOTSTRAP = True
+
     def _bootstrap_xi(self, n_bootstrap, batch_points=1 << 26):
         """xi of `n_bootstrap` resamples, shape (n_bootstrap, nb)."""
+        from . import dist
+
         n = len(self.y)
         dev = backend.require_cuda()
         x = backend.to_device(np.asarray(self.X[:, 0], dtype=np.float64))
@@ -357,9 +364,6 @@ class two_pcf(object):
         err_d = backend.to_device(err)
         # Hilbert-sort the base catalogue once: every resample is a sub-multiset in the same order
         order = backend.hilbert_order(x, yy) if self.anisotropic else None
-        out = []
-        per_batch = max(1, int(batch_points // max(n, 1)))
-        done = 0
         if order is not None:
             x, yy, val, err_d = x[order], yy[order], val[order], err_d[order]
         # storage position of every original point (identity without the Hilbert sort)
@@ -367,6 +371,47 @@ class two_pcf(object):
         if order is not None:
             pos = np.empty(n, dtype=np.int64)
             pos[order.cpu().numpy()] = np.arange(n, dtype=np.int64)
+        # The reference drops the weights of a resample iff its errors sum to 0 (two_pcf.py:291-294): with all
+        # errors zero every resample is unweighted, with all errors positive none is -- the two cases the shared
+        # kernel covers; mixed inputs keep the per-catalogue batch.
+        all_zero, all_pos = bool(np.all(err == 0)), bool(np.all(err > 0))
+        if (self.anisotropic and self.SHARED_BOOTSTRAP and n >= 2 and (all_zero or all_pos)
+                and not isinstance(self.group, dist.CabiComm)):
+            return self._bootstrap_xi_shared(n_bootstrap, x, yy, val, None if all_zero else 1.0 / (err_d * err_d), pos)
+        return self._bootstrap_xi_catalogues(n_bootstrap, x, yy, val, err_d, pos, batch_points)
+
+    def _bootstrap_xi_shared(self, n_bootstrap, x, yy, val, w, pos, batch_bytes=1 << 31):
+        """All resamples of a batch in ONE pass over the pairs of the base catalogue (tgp_bootbin_twod): the bin of a
+        pair does not depend on the resample, only its weight m_b[i] m_b[j] does."""
+        from . import dist
+
+        n = int(x.numel())
+        dev = x.device
+        _, edges = self._bin_geometry()
+        edges_d = self._device_edges(edges)
+        rank, world = dist.rank_world(self.group)
+        z = (val - val.mean()).contiguous()       # any fixed centring; the resample means are applied after the sums
+        per_batch = max(32, min(int(n_bootstrap), int(batch_bytes // max(n, 1)) // 32 * 32))
+        out, done = [], 0
+        while done < n_bootstrap:
+            b = min(per_batch, n_bootstrap - done)
+            mult = self._draw_multiplicities(b, n, pos).to(dev, non_blocking=True)
+            sums, delta = backend.bootbin_sums(x, yy, z, w, mult, edges_d, self.nbins, self.min_sep, self.max_sep,
+                                               rank=rank, nranks=world)
+            if world > 1:
+                dist.allreduce_bins(self.group, sums)
+            out.append(backend.bootbin_xi(sums, delta, self.nbins, b).cpu().numpy())
+            done += b
+        return np.concatenate(out, axis=0)
+
+    def _bootstrap_xi_catalogues(self, n_bootstrap, x, yy, val, err_d, pos, batch_points=1 << 26):
+        """Every resample as its own weighted catalogue (points with multiplicity > 0, weight m w) of one batched
+        tgp_pairbin launch."""
+        n = int(x.numel())
+        dev = x.device
+        out = []
+        per_batch = max(1, int(batch_points // max(n, 1)))
+        done = 0
         while done < n_bootstrap:
             b = min(per_batch, n_bootstrap - done)
             # multiplicities of `b` successive resample_bootstrap() draws, in storage order
