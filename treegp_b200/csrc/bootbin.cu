@@ -19,14 +19,18 @@
 //   * (row block, column chunk) pairs are classified from bounding boxes exactly like tgp_pairbin (same thresholds,
 //     same exactness argument: FP subtraction is monotone);
 //   * a block that falls into ONE bin is booked from the per-resample chunk sums of the pre-pass (4 FMAs per lane);
-//   * a block with two bins along an axis takes that axis' "upper bin" sums from a merged sweep over the chunk sorted
-//     along the axis and the rows sorted along the axis: the split position of every row is found by its lane
-//     (bisection on fl(x_j - x_i) >= t), the suffix sums of a_b, c_b run in the resample lanes: 32 column steps +
-//     32 row steps instead of 1024 pair steps; the exact mirrored bits are checked at the two neighbours of the split;
+//   * a block with two bins along an axis takes that axis' "upper bin" sums from a sweep: a column (coordinate s,
+//     columns in ascending order along the axis) pairs in the upper bin with the rows whose coordinate is small
+//     enough, fl(s - r) >= t, i.e. with the first nle rows in ascending order; nle is found by bisection in the
+//     column's lane, and the column's share is (a, c) times the prefix sums of the rows' (a, c) in ascending order --
+//     tables built once per work item in shared memory (lanes = resamples), so a sweep is 32 independent steps of
+//     6 FMAs instead of 1024 pair steps; the exact mirrored bits are checked at the two neighbours of the split;
 //   * what is left (the "both bits" quadrant of 2 x 2-window blocks, blocks that need the range test per pair, the
 //     diagonal block) goes pair by pair: per-row 32-bit masks from ballots in the geometry phase, then per resample
-//     lane predicated adds over the chunk's columns held in registers;
-//   * multiplicities travel as bytes (four copies: row-major for rows, chunk-packed in natural / x-sorted / y-sorted
+//     lane masked FMAs over the chunk's 32 columns held in registers (the 0.0 / 1.0 factors of four columns come
+//     from a 16-entry table indexed by a nibble of the mask; bytes of the mask without a bit are skipped: columns
+//     are kept in ascending x, so the zeros of a quadrant mask are contiguous);
+//   * multiplicities travel as bytes (three copies: row-major for rows, chunk-packed in ascending-x and ascending-y
 //     column order) and become doubles by the 2^52 trick inside one FMA: a = fma(2^52 + m, w, -2^52 w) = m w exactly.
 //
 // Window registers hold the sums in inclusion-exclusion form {all, x-bit, y-bit, both} for an open 2 x 2 bin window
@@ -41,16 +45,15 @@
 #include "tgp_common.cuh"
 
 constexpr int BB_CHUNK = 32;
-constexpr int BB_WARPS = 4;
+constexpr int BB_WARPS = 4;   // warps per CTA
 constexpr int BB_GEO = 80;   // doubles per chunk record: box[4], xs[32], ys[32], permx[32] u8, permy[32] u8, pad
-constexpr int BB_CG = 16;    // columns held in registers at a time by the pair-by-pair accumulation
 
 struct BBParams {
   const double *px, *py;
   const double4* pt;          // per point {w, -2^52 w, w z, -2^52 w z}, padded to whole chunks with zeros
   const double* geo;          // per chunk record (BB_GEO doubles)
   const uint8_t *m_row;       // [nblk*32][bpad]
-  const uint8_t *m_nat, *m_sx, *m_sy;   // [nblk][bpad][32]: column multiplicities in natural / x-sorted / y-sorted order
+  const uint8_t *m_sx, *m_sy;   // [nblk][bpad][32]: column multiplicities in ascending-x / ascending-y column order
   const double* csum;         // [nblk][3][bpad]: per chunk and resample sum a, sum c, sum m z
   const double* edges;
   double* hist;               // [2][3][nb][bpad]: forward-only sums, then corrections
@@ -124,45 +127,45 @@ __device__ __forceinline__ int bb_classify(double iminx, double imaxx, double im
   return cls | ((ex & 1) << 2) | ((ey & 1) << 3) | (x0 << 8) | (y0 << 20);
 }
 
-// sum of a[j], c[j] over the set bits of W (uniform across the warp): the bit becomes a 0.0 / 1.0 factor inside an
-// FMA (ptxas turns a predicated FP64 add into add + two selects: the mask form is shorter); two chains each
-__device__ __forceinline__ void bb_masked_sum(const double (&a)[BB_CG], const double (&c)[BB_CG], unsigned W,
-                                              double& sa, double& sc) {
-  double sa0 = 0.0, sa1 = 0.0, sc0 = 0.0, sc1 = 0.0;
-#pragma unroll
-  for (int j = 0; j < BB_CG; j += 2) {
-    const double m0 = __hiloint2double((W & (1u << j)) ? 0x3ff00000 : 0, 0);
-    const double m1 = __hiloint2double((W & (2u << j)) ? 0x3ff00000 : 0, 0);
-    sa0 = fma(a[j], m0, sa0);
-    sc0 = fma(c[j], m0, sc0);
-    sa1 = fma(a[j + 1], m1, sa1);
-    sc1 = fma(c[j + 1], m1, sc1);
-  }
-  sa = sa0 + sa1;
-  sc = sc0 + sc1;
+__device__ __forceinline__ void bb_prefetch_l1(const void* p) {
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(__cvta_generic_to_global(p)));
 }
 
-__global__ void __launch_bounds__(BB_WARPS * 32, 3)
+// CTAs per SM: 2 (248 registers, no spills: 251 ms for 100 resamples at N = 200k) measured faster than 3 (168
+// registers, 300 bytes of spills: 268 ms)
+#ifndef BB_MIN_CTAS
+#define BB_MIN_CTAS 2
+#endif
+constexpr int BB_WARP_SMEM = 2 * 1024 + 512;   // per warp: scx, scy, msk
+
+// A CTA (4 warps) owns one work item = (group of 32 resamples, row block of 32 points) x all column chunks from the
+// row block on; what depends only on the item -- the row constants and multiplicities, the two row-prefix tables --
+// is built once in shared memory, and the warps pull rounds of 32 column chunks from a shared counter.
+__global__ void __launch_bounds__(BB_WARPS * 32, BB_MIN_CTAS)
 bootbin_kernel(BBParams P) {
   extern __shared__ __align__(16) unsigned char bb_smem[];
   const int nbins = P.nbins, nb = P.nb, bpad = P.bpad;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  double* ed = reinterpret_cast<double*>(bb_smem);                           // nbins + 1, padded to even
-  unsigned char* wbase = bb_smem + (size_t)((nbins + 2) & ~1) * 8 + (size_t)warp * 4864;
-  double4* colc = reinterpret_cast<double4*>(wbase);            // [32] constants of the staged chunk's points
-  double4* scol = colc + 32;                                    // [32] the same in sorted order (sweeps)
-  double4* rowc = scol + 32;                                    // [32] constants of the row points
+  double* ed = reinterpret_cast<double*>(bb_smem);              // nbins + 1 thresholds, padded to even
+  double* mtab = ed + ((nbins + 2) & ~1);                       // [16][4]: the bits of a nibble as 0.0 / 1.0
+  double2* tab = reinterpret_cast<double2*>(mtab + 64);         // [2 axes][33][32 lanes] row-prefix sums {a, c}
+  double4* rowc = reinterpret_cast<double4*>(tab + 2 * 33 * 32);       // [32] constants of the row points
   unsigned char* rowm = reinterpret_cast<unsigned char*>(rowc + 32);   // [32 rows][32 resample lanes]
-  double* sxs = reinterpret_cast<double*>(rowm + 1024);         // [32] sorted coordinates of the staged chunk
-  unsigned* msk = reinterpret_cast<unsigned*>(sxs + 32);        // [32 rows][4]: in range, & x bit, & y bit, & both
+  double* rs = reinterpret_cast<double*>(rowm + 1024);          // [2][32] row coordinates in ascending order
+  double2* rxy = reinterpret_cast<double2*>(rs + 64);           // [32] row coordinates, storage order
+  long long* ctl = reinterpret_cast<long long*>(rxy + 32);      // [0] item of the CTA, [1] round counter
+  unsigned char* wbase = reinterpret_cast<unsigned char*>(ctl + 2) + (size_t)warp * BB_WARP_SMEM;
+  double4* scx = reinterpret_cast<double4*>(wbase);             // [32] constants of the chunk's points, x-sorted
+  double4* scy = scx + 32;                                      // [32] the same, y-sorted
+  unsigned* msk = reinterpret_cast<unsigned*>(scy + 32);        // [32 rows][4]: in range, & x bit, & y bit, & both
 
   for (int i = tid; i <= nbins; i += blockDim.x) ed[i] = P.edges[i];
-  __syncthreads();
+  for (int e = tid; e < 64; e += blockDim.x) mtab[e] = (((e >> 2) >> (e & 3)) & 1) ? 1.0 : 0.0;
 
   const double M = P.hi, lo2 = P.lo2;
   const double NaN = __longlong_as_double(0x7ff8000000000000ll);
-  const int R = P.run;
   const int G = P.ngroups;
+  const int64_t n = P.n, nblk = P.nblk;
   unsigned st_closed = 0, st_sweep = 0, st_pair = 0, st_slow = 0, st_flush = 0, st_back = 0;
 
   // window registers: element u = ux + 2 uy holds the sums over pairs with (x bit >= ux) and (y bit >= uy)
@@ -173,60 +176,66 @@ bootbin_kernel(BBParams P) {
   unsigned touched = 0u;   // window bins that received something
 
   while (true) {
-    unsigned long long q = 0;
-    if (lane == 0) q = atomicAdd(P.counter, 1ull);
-    q = __shfl_sync(0xffffffffu, q, 0);
-    if ((int64_t)q >= P.my_items) break;
-    const int64_t item = (int64_t)q * P.nranks + P.rank;
+    __syncthreads();   // everybody is done with the previous item's shared data
+    if (tid == 0) {
+      ctl[0] = (long long)atomicAdd(P.counter, 1ull);
+      ctl[1] = 0;
+    }
+    __syncthreads();
+    const int64_t q = ctl[0];
+    if (q >= P.my_items) break;
+    const int64_t item = q * P.nranks + P.rank;   // largest items (small ib) first
     const int g = (int)(item % G);
-    const int64_t lq = item / G;
-    if (lq >= P.items_per_group) break;
+    const int64_t ib = item / G;
+    if (ib >= nblk) break;
     const int gb = g * 32 + lane;              // this lane's resample
-    const int64_t n = P.n, nblk = P.nblk;
-    const int64_t nruns = (nblk + R - 1) / R;
-    // decode lq -> (row block ib, run r): rows of group gg = ib / R pair with runs gg .. nruns-1
-    const double tn = 2.0 * (double)nruns + 1.0;
-    const double disc = tn * tn - 8.0 * (double)lq / (double)R;
-    int64_t gg = (int64_t)((tn - sqrt(disc > 0.0 ? disc : 0.0)) * 0.5);
-    if (gg < 0) gg = 0;
-    if (gg >= nruns) gg = nruns - 1;
-    while (gg > 0 && (int64_t)R * (gg * nruns - gg * (gg - 1) / 2) > lq) --gg;
-    while (gg + 1 < nruns && (int64_t)R * ((gg + 1) * nruns - (gg + 1) * gg / 2) <= lq) ++gg;
-    const int64_t rem = lq - (int64_t)R * (gg * nruns - gg * (gg - 1) / 2);
-    const int64_t per_row = nruns - gg;
-    const int64_t row_in_g = rem / per_row;
-    const int64_t ib = gg * R + row_in_g;
-    const int64_t r = gg + rem % per_row;
-    if (row_in_g >= R || ib >= nblk) continue;
-    const int64_t c_lo = (r * R > ib) ? r * R : ib;
-    const int64_t c_hi = ((r + 1) * R < nblk) ? (r + 1) * R : nblk;
-    if (c_lo >= c_hi) continue;
+    const int64_t c_lo = ib, c_hi = nblk;
 
-    // ---- this warp's row points (lanes = rows) and their per-resample values (lanes = resamples) ----
+    // ---- the item's row points (lanes = rows) and their per-resample values (lanes = resamples) ----
     const int64_t ig = ib * BB_CHUNK + lane;
     const bool live = ig < n;
     const double xi = live ? P.px[ig] : NaN, yi = live ? P.py[ig] : NaN;
-    __syncwarp();
-    rowc[lane] = P.pt[ig];
+    const double* rrec = P.geo + (size_t)ib * BB_GEO;
+    if (warp == 0) {
+      rowc[lane] = P.pt[ig];
+      rxy[lane] = make_double2(xi, yi);
+      rs[lane] = rrec[4 + lane];          // ascending x of the row block (+inf for absent points)
+      rs[32 + lane] = rrec[36 + lane];    // ascending y
+    }
     {
       const uint8_t* mr = P.m_row + (size_t)ib * BB_CHUNK * bpad + gb;
-#pragma unroll 8
-      for (int i = 0; i < 32; ++i) rowm[i * 32 + lane] = mr[(size_t)i * bpad];
+#pragma unroll
+      for (int i = warp * 8; i < warp * 8 + 8; ++i) rowm[i * 32 + lane] = mr[(size_t)i * bpad];
     }
-    __syncwarp();
-    double RA = 0.0, RC = 0.0;
-#pragma unroll 4
-    for (int i = 0; i < 32; ++i) {
+    __syncthreads();
+    auto row_vals = [&](int i, double& ai, double& ci) {
       const double Mi = bb_magic(rowm[i * 32 + lane]);
       const double4 rc = rowc[i];
-      RA += fma(Mi, rc.x, rc.y);
-      RC += fma(Mi, rc.z, rc.w);
+      ai = fma(Mi, rc.x, rc.y);
+      ci = fma(Mi, rc.z, rc.w);
+    };
+    // prefix sums of a, c over the rows in ascending x (warp 0) / y (warp 1): tab[axis][e] = sum of the first e rows
+    if (warp < 2) {
+      const int axis = warp;
+      const int prk = reinterpret_cast<const unsigned char*>(rrec + 68)[32 * axis + lane];
+      double2* tb = tab + axis * 33 * 32 + lane;
+      double pa = 0.0, pc = 0.0;
+      tb[0] = make_double2(0.0, 0.0);
+#pragma unroll 4
+      for (int k = 0; k < 32; ++k) {
+        const int i = __shfl_sync(0xffffffffu, prk, k);
+        double ai, ci;
+        row_vals(i, ai, ci);
+        pa += ai;
+        pc += ci;
+        tb[(k + 1) * 32] = make_double2(pa, pc);
+      }
     }
     const double iminx = bb_warp_min(live ? xi : INFINITY), imaxx = bb_warp_max(live ? xi : -INFINITY);
     const double iminy = bb_warp_min(live ? yi : INFINITY), imaxy = bb_warp_max(live ? yi : -INFINITY);
     const int nlive = __popc(__ballot_sync(0xffffffffu, live));
-    const unsigned char* rperm = reinterpret_cast<const unsigned char*>(P.geo + (size_t)ib * BB_GEO + 68);
-    const int permr_x = rperm[lane], permr_y = rperm[32 + lane];   // rows in ascending x / y order
+    __syncthreads();
+    const double RA = tab[32 * 32 + lane].x, RC = tab[32 * 32 + lane].y;   // sums over all rows
 
     // ---- helpers -------------------------------------------------------------------------------------
     auto flush = [&]() {
@@ -255,20 +264,18 @@ bootbin_kernel(BBParams P) {
       touched = 0u;
       fx0 = -1;
     };
-    auto row_vals = [&](int i, double& ai, double& ci) {
-      const double Mi = bb_magic(rowm[i * 32 + lane]);
-      const double4 rc = rowc[i];
-      ai = fma(Mi, rc.x, rc.y);
-      ci = fma(Mi, rc.z, rc.w);
-    };
-    // exact per-pair path: forward and mirrored bin of every pair from the thresholds, straight into the histograms
-    auto slow_block = [&](int64_t c, bool diag, double xj, double yj, bool clive) {
+    // exact per-pair path (lanes = columns in storage order): forward and mirrored bin of every pair from the
+    // thresholds, straight into the histograms
+    auto slow_block = [&](int64_t c, bool diag) {
       ++st_slow;
+      const int64_t jg = c * BB_CHUNK + lane;
+      const bool clive = jg < n;
+      const double xj = clive ? P.px[jg] : NaN, yj = clive ? P.py[jg] : NaN;
       double* hf = P.hist;
       double* hc = P.hist + (size_t)3 * nb * bpad;
       for (int i = 0; i < nlive; ++i) {
-        const double xiu = __shfl_sync(0xffffffffu, xi, i), yiu = __shfl_sync(0xffffffffu, yi, i);
-        const double dx = xj - xiu, dy = yj - yiu;
+        const double2 ri = rxy[i];
+        const double dx = xj - ri.x, dy = yj - ri.y;
         const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
         const bool inr = clive && r2 >= lo2 && fabs(dx) < M && fabs(dy) < M && (!diag || lane > i);
         int b1 = -1, b2 = -1;
@@ -285,7 +292,7 @@ bootbin_kernel(BBParams P) {
           mask &= mask - 1;
           const int bb1 = __shfl_sync(0xffffffffu, b1, j), bb2 = __shfl_sync(0xffffffffu, b2, j);
           const double Mj = bb_magic(P.m_row[((size_t)c * BB_CHUNK + j) * bpad + gb]);
-          const double4 k4 = colc[j];
+          const double4 k4 = P.pt[c * BB_CHUNK + j];
           const double aj = fma(Mj, k4.x, k4.y), cj = fma(Mj, k4.z, k4.w);
           const double v0 = ai * aj, v1 = ci * aj + ai * cj, v2 = ci * cj;
           const size_t s = (size_t)nb * bpad;
@@ -300,67 +307,85 @@ bootbin_kernel(BBParams P) {
         }
       }
     };
-    // merged sweep along one axis: sums over the pairs whose bit along that axis is set (upper bin), all resamples
-    // of this group.  false: the exact mirrored split differs somewhere (caller goes pair by pair).
-    auto sweep = [&](int axis, int64_t c, int v0, double& h0, double& h1, double& h2) -> bool {
-      __syncwarp();
-      const double* grec = P.geo + (size_t)c * BB_GEO;
-      sxs[lane] = grec[4 + 32 * axis + lane];
-      const int pc = reinterpret_cast<const unsigned char*>(grec + 68)[32 * axis + lane];
-      scol[lane] = colc[pc];
-      __syncwarp();
+    // Sweep along one axis: the sums over the pairs whose bit along that axis is set (upper bin), for the 32
+    // resamples of this group.  Column p (ascending along the axis, coordinate s) pairs with the rows whose
+    // coordinate is small enough, fl(s - r_k) >= t: the first nle rows in ascending order, so its share is its own
+    // (a, c) times the row-prefix sums tab[axis][nle] -- found by bisection in the column's lane, no dependence
+    // between columns.  false: the exact mirrored split differs somewhere (the caller goes pair by pair).
+    auto sweep = [&](int axis, int v0, double s, int cnt, const unsigned (&wb)[8], const double4* sc, double& h0,
+                     double& h1, double& h2) -> bool {
       const double t = ed[v0 + 1], rt = ed[nbins - 1 - v0];
-      const double ci_ = axis ? yi : xi;
-      int lo = 0, hi = 32;   // pos = number of columns with fl(s_p - c_i) < t
+      const double* rsa = rs + 32 * axis;
+      int lo = 0, hi = 32;   // nle = number of rows with fl(s - r_k) >= t (true for the small r_k)
 #pragma unroll
-      for (int s = 0; s < 6; ++s) {
+      for (int it = 0; it < 6; ++it) {
         if (lo < hi) {
           const int mid = (lo + hi) >> 1;
-          if ((sxs[mid] - ci_) < t) lo = mid + 1; else hi = mid;
+          if ((s - rsa[mid]) >= t) lo = mid + 1; else hi = mid;
         }
       }
-      const int pos = lo;
-      // exact mirrored bits: columns below the split must be in the upper mirrored bin, columns from it on in the
-      // lower one; in ascending order only the two neighbours of the split can fail
-      const bool ok = (pos == 0 || (ci_ - sxs[pos - 1]) >= rt) && (pos == 32 || (ci_ - sxs[pos]) < rt);
+      const int nle = lo;
+      // exact mirrored bits: rows in the upper forward bin must sit in the lower mirrored bin, fl(r_k - s) < rt,
+      // the others in the upper one; in ascending order only the two neighbours of the split can fail
+      const bool ok = lane >= cnt || ((nle == 0 || (rsa[nle - 1] - s) < rt) &&
+                                      (nle >= nlive || (rsa[nle] - s) >= rt));
       if (!__all_sync(0xffffffffu, ok)) return false;
-      const int prk = axis ? permr_y : permr_x;
-      const int Pk = __shfl_sync(0xffffffffu, pos, prk);   // split positions in ascending row-coordinate order
-      const uint4* mp = reinterpret_cast<const uint4*>((axis ? P.m_sy : P.m_sx) + ((size_t)c * bpad + gb) * 32);
-      const uint4 u0 = mp[0], u1 = mp[1];
-      const unsigned wb[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-      double sufA = 0.0, sufC = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
-      int k = 31;
-      while (k >= 0 && __shfl_sync(0xffffffffu, Pk, k) == 32) --k;
+      const double2* tb = tab + axis * 33 * 32 + lane;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
 #pragma unroll
-      for (int wq = 7; wq >= 0; --wq) {
-        const unsigned word = wb[wq];
-#pragma unroll 1
-        for (int bq = 3; bq >= 0; --bq) {
-          const int p = wq * 4 + bq;
-          const double Mj = bb_magic((word >> (8 * bq)) & 0xffu);
-          const double4 k4 = scol[p];
-          sufA += fma(Mj, k4.x, k4.y);
-          sufC += fma(Mj, k4.z, k4.w);
-          while (k >= 0 && __shfl_sync(0xffffffffu, Pk, k) == p) {
-            const int i = __shfl_sync(0xffffffffu, prk, k);
-            double ai, ci;
-            row_vals(i, ai, ci);
-            a0 = fma(ai, sufA, a0);
-            a1 = fma(ci, sufA, fma(ai, sufC, a1));
-            a2 = fma(ci, sufC, a2);
-            --k;
-          }
+      for (int p = 0; p < 32; p += 2) {
+        {
+          const int e = __shfl_sync(0xffffffffu, nle, p);
+          const double Mj = bb_magic((wb[p >> 2] >> (8 * (p & 3))) & 0xffu);
+          const double4 k4 = sc[p];
+          const double2 T = tb[e * 32];
+          const double A = fma(Mj, k4.x, k4.y), C = fma(Mj, k4.z, k4.w);
+          a0 = fma(A, T.x, a0);
+          a1 = fma(C, T.x, fma(A, T.y, a1));
+          a2 = fma(C, T.y, a2);
+        }
+        {
+          const int e = __shfl_sync(0xffffffffu, nle, p + 1);
+          const double Mj = bb_magic((wb[(p + 1) >> 2] >> (8 * ((p + 1) & 3))) & 0xffu);
+          const double4 k4 = sc[p + 1];
+          const double2 T = tb[e * 32];
+          const double A = fma(Mj, k4.x, k4.y), C = fma(Mj, k4.z, k4.w);
+          b0 = fma(A, T.x, b0);
+          b1 = fma(C, T.x, fma(A, T.y, b1));
+          b2 = fma(C, T.y, b2);
         }
       }
-      if (k >= 0) return false;   // cannot happen (split positions are monotone in the row coordinate)
-      h0 = a0; h1 = a1; h2 = a2;
+      h0 = a0 + b0; h1 = a1 + b1; h2 = a2 + b2;
       return true;
     };
+    // lines the next block will read, into L1 (the loads of a block are otherwise one exposed L2 round trip each)
+    auto prefetch_block = [&](int64_t c, int d) {
+      const bool closed = (d & 3) == BB_REG_FULL && !(d & 12) && (P.paths & 1);
+      const char* cs = reinterpret_cast<const char*>(P.csum + (size_t)c * 3 * bpad + g * 32);
+      if (closed || (d & 3) == BB_GENERIC) {
+        if (lane < 4) bb_prefetch_l1(cs + (lane >> 1) * (size_t)bpad * 8 + (lane & 1) * 128);
+        return;
+      }
+      const char* a;
+      const size_t mo = ((size_t)c * bpad + g * 32) * 32;
+      if (lane < 8) a = reinterpret_cast<const char*>(P.m_sx) + mo + lane * 128;
+      else if (lane < 16) a = reinterpret_cast<const char*>(P.m_sy) + mo + (lane - 8) * 128;
+      else if (lane < 24) a = reinterpret_cast<const char*>(P.pt + c * BB_CHUNK) + (lane - 16) * 128;
+      else if (lane < 26) a = reinterpret_cast<const char*>(P.py + (c * BB_CHUNK + 16 * (lane - 24) < n ? c * BB_CHUNK : 0)) + (lane - 24) * 128;
+      else if (lane < 31) a = reinterpret_cast<const char*>(P.geo + (size_t)c * BB_GEO) + (lane - 26) * 128;
+      else a = cs;
+      bb_prefetch_l1(a);
+      if (lane < 3) bb_prefetch_l1(cs + (lane == 0 ? 128 : (size_t)bpad * 8 + (lane - 1) * 128));
+    };
 
-    for (int64_t sc = c_lo; sc < c_hi; sc += 32) {
-      // ---- lane l classifies column chunk sc + l ----
-      const int64_t mychunk = sc + lane;
+    while (true) {
+      long long rd = 0;
+      if (lane == 0) rd = (long long)atomicAdd(reinterpret_cast<unsigned long long*>(ctl + 1), 1ull);
+      rd = __shfl_sync(0xffffffffu, rd, 0);
+      const int64_t sc0 = c_lo + rd * 32;
+      if (sc0 >= c_hi) break;
+      // ---- lane l classifies column chunk sc0 + l ----
+      const int64_t mychunk = sc0 + lane;
       int desc = 0;
       if (mychunk < c_hi) {
         const double4 bb = *reinterpret_cast<const double4*>(P.geo + (size_t)mychunk * BB_GEO);
@@ -371,21 +396,17 @@ bootbin_kernel(BBParams P) {
         }
       }
       unsigned todo = __ballot_sync(0xffffffffu, desc != 0);
+      if (todo) prefetch_block(sc0 + __ffs(todo) - 1, __shfl_sync(0xffffffffu, desc, __ffs(todo) - 1));
       while (todo) {
         const int tl = __ffs(todo) - 1;
         todo &= todo - 1;
         const int d = __shfl_sync(0xffffffffu, desc, tl);
-        const int64_t c = sc + tl;
+        const int64_t c = sc0 + tl;
+        if (todo) prefetch_block(sc0 + __ffs(todo) - 1, __shfl_sync(0xffffffffu, desc, __ffs(todo) - 1));
         const int cls = d & 3, ex = (d >> 2) & 1, ey = (d >> 3) & 1, x0 = (d >> 8) & 0xfff, y0 = (d >> 20) & 0xfff;
         const bool diag = (d >> 4) & 1;
-        const int64_t jg = c * BB_CHUNK + lane;
-        const bool clive = jg < n;
         if (cls == BB_GENERIC || !(P.paths & 2)) {
-          const double xj = clive ? P.px[jg] : NaN, yj = clive ? P.py[jg] : NaN;
-          __syncwarp();
-          colc[lane] = P.pt[jg];
-          __syncwarp();
-          slow_block(c, diag, xj, yj, clive);
+          slow_block(c, diag);
           continue;
         }
         const bool full = cls == BB_REG_FULL;
@@ -413,85 +434,145 @@ bootbin_kernel(BBParams P) {
           if (!ex && !ey && (P.paths & 1)) { ++st_closed; booked = true; }
         }
         if (!booked) {
-          // ---- stage the chunk (lanes = columns) ----
-          const double xj = clive ? P.px[jg] : NaN, yj = clive ? P.py[jg] : NaN;
+          // ---- the chunk in ascending x (and y) order: coordinates in the lanes, constants staged ----
+          const double* grec = P.geo + (size_t)c * BB_GEO;
+          const unsigned char* cperm = reinterpret_cast<const unsigned char*>(grec + 68);
+          const int cnt = (int)((n - c * BB_CHUNK < BB_CHUNK) ? (n - c * BB_CHUNK) : BB_CHUNK);
+          const bool clive = lane < cnt;           // absent points sort last (+inf) and carry zero multiplicities
+          const double sx = grec[4 + lane], sy = grec[36 + lane];
+          const int pcx = cperm[lane], pcy = cperm[32 + lane];
+          const uint4* mpx = reinterpret_cast<const uint4*>(P.m_sx + ((size_t)c * bpad + gb) * 32);
+          const uint4 ux0 = mpx[0], ux1 = mpx[1];
+          const unsigned wbx[8] = {ux0.x, ux0.y, ux0.z, ux0.w, ux1.x, ux1.y, ux1.z, ux1.w};
+          const double yjx = clive ? P.py[c * BB_CHUNK + pcx] : NaN;   // y of the x-sorted columns
           __syncwarp();
-          colc[lane] = P.pt[jg];
+          scx[lane] = P.pt[c * BB_CHUNK + pcx];
+          scy[lane] = P.pt[c * BB_CHUNK + pcy];
           __syncwarp();
           bool done_x = false, done_y = false;
-          if (full && (P.paths & 4) && nlive == 32 && (c + 1) * BB_CHUNK <= n) {
-            if (ex) { done_x = sweep(0, c, x0, L[1][0], L[1][1], L[1][2]); if (done_x) ++st_sweep; else ++st_back; }
-            if (ey) { done_y = sweep(1, c, y0, L[2][0], L[2][1], L[2][2]); if (done_y) ++st_sweep; else ++st_back; }
+          if (full && (P.paths & 4)) {
+            if (ex) {
+              done_x = sweep(0, x0, sx, cnt, wbx, scx, L[1][0], L[1][1], L[1][2]);
+              if (done_x) ++st_sweep; else ++st_back;
+            }
+            if (ey) {
+              const uint4* mpy = reinterpret_cast<const uint4*>(P.m_sy + ((size_t)c * bpad + gb) * 32);
+              const uint4 uy0 = mpy[0], uy1 = mpy[1];
+              const unsigned wby[8] = {uy0.x, uy0.y, uy0.z, uy0.w, uy1.x, uy1.y, uy1.z, uy1.w};
+              done_y = sweep(1, y0, sy, cnt, wby, scy, L[2][0], L[2][1], L[2][2]);
+              if (done_y) ++st_sweep; else ++st_back;
+            }
           }
           const bool need_t = !full || !(P.paths & 1 || ex || ey);
           const bool need_x = ex && !done_x, need_y = ey && !done_y, need_xy = ex && ey;
           if (need_t || need_x || need_y || need_xy) {
             ++st_pair;
-            // ---- geometry (lanes = columns): per-row masks of the pairs in range and of their window bits ----
+            // ---- geometry (lanes = columns in ascending x): per-row masks of the pairs in range and their bits ----
             const double tx = ed[x0 + 1], rtx = ed[nbins - 1 - x0], ty = ed[y0 + 1], rty = ed[nbins - 1 - y0];
+            uint2* msk2 = reinterpret_cast<uint2*>(msk);   // [half of the columns][row]: {t | x << 16, y | xy << 16}
             unsigned bad = 0u;
-#pragma unroll 2
-            for (int i = 0; i < 32; ++i) {
-              const double xiu = __shfl_sync(0xffffffffu, xi, i), yiu = __shfl_sync(0xffffffffu, yi, i);
-              const double dx = xj - xiu, dy = yj - yiu;
-              bool inr = true;
-              if (!full) {
-                const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-                inr = r2 >= lo2 && fabs(dx) < M && fabs(dy) < M && (!diag || lane > i);
+            if (!need_t && !need_x && !need_y) {
+              // both axes came from sweeps (which also settled the mirrored bits): only the "both bits" quadrant is left
+#pragma unroll 4
+              for (int i = 0; i < 32; ++i) {
+                const double2 ri = rxy[i];
+                const unsigned wxy = __ballot_sync(0xffffffffu, (sx - ri.x) >= tx && (yjx - ri.y) >= ty);
+                if (lane < 2) msk2[lane * 32 + i] = make_uint2(0u, (lane ? wxy >> 16 : wxy & 0xffffu) << 16);
               }
-              const bool bx = ex && dx >= tx, by = ey && dy >= ty;
-              const bool qx = (-dx) >= rtx, qy = (-dy) >= rty;
-              const bool wrong = inr && clive && i < nlive && ((ex && bx == qx) || (ey && by == qy));
-              const unsigned wt = __ballot_sync(0xffffffffu, inr), wx = __ballot_sync(0xffffffffu, inr && bx);
-              const unsigned wy = __ballot_sync(0xffffffffu, inr && by);
-              bad |= __ballot_sync(0xffffffffu, wrong);
-              if (lane == 0) *reinterpret_cast<uint4*>(msk + 4 * i) = make_uint4(wt, wx, wy, wx & wy);
+            } else {
+              const unsigned kt = need_t ? 0xffffu : 0u, kx = need_x ? 0xffffu : 0u, ky = need_y ? 0xffffu : 0u;
+              const unsigned kxy = need_xy ? 0xffffu : 0u;
+#pragma unroll 2
+              for (int i = 0; i < 32; ++i) {
+                const double2 ri = rxy[i];
+                const double dx = sx - ri.x, dy = yjx - ri.y;
+                bool inr = true;
+                if (!full) {
+                  const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+                  inr = r2 >= lo2 && fabs(dx) < M && fabs(dy) < M && (!diag || pcx > i);
+                }
+                const bool bx = ex && dx >= tx, by = ey && dy >= ty;
+                const bool qx = (-dx) >= rtx, qy = (-dy) >= rty;
+                const bool wrong = inr && clive && i < nlive && ((ex && bx == qx) || (ey && by == qy));
+                const unsigned wt = __ballot_sync(0xffffffffu, inr), wx = __ballot_sync(0xffffffffu, inr && bx);
+                const unsigned wy = __ballot_sync(0xffffffffu, inr && by);
+                const unsigned wxy = __ballot_sync(0xffffffffu, inr && bx && by);
+                bad |= __ballot_sync(0xffffffffu, wrong);
+                if (lane < 2) {
+                  const int sh = 16 * lane;
+                  msk2[lane * 32 + i] = make_uint2(((wt >> sh) & kt) | (((wx >> sh) & kx) << 16),
+                                                   ((wy >> sh) & ky) | (((wxy >> sh) & kxy) << 16));
+                }
+              }
             }
             __syncwarp();
             if (bad) {   // some displacement sits on a bin edge: exact per-pair path for the whole block
               --st_pair;
-              slow_block(c, diag, xj, yj, clive);
+              slow_block(c, diag);
               continue;
             }
-            // ---- accumulation (lanes = resamples) ----
+            // ---- accumulation (lanes = resamples): 16 columns at a time in registers ----
             if (need_t) L[0][0] = L[0][1] = L[0][2] = 0.0;
-            const uint4* mp = reinterpret_cast<const uint4*>(P.m_nat + ((size_t)c * bpad + gb) * 32);
-            const uint4 u0 = mp[0], u1 = mp[1];
+            const double4* mt4 = reinterpret_cast<const double4*>(mtab);
 #pragma unroll 1
-            for (int h = 0; h < 32 / BB_CG; ++h) {
-              const unsigned w4[4] = {h ? u1.x : u0.x, h ? u1.y : u0.y, h ? u1.z : u0.z, h ? u1.w : u0.w};
-              double a[BB_CG], cc[BB_CG];
+            for (int h = 0; h < 2; ++h) {
+              const unsigned w4[4] = {h ? wbx[4] : wbx[0], h ? wbx[5] : wbx[1], h ? wbx[6] : wbx[2], h ? wbx[7] : wbx[3]};
+              double a[16], cc[16];
 #pragma unroll
-              for (int jj = 0; jj < BB_CG; ++jj) {
+              for (int jj = 0; jj < 16; ++jj) {
                 const double Mj = bb_magic((w4[jj >> 2] >> (8 * (jj & 3))) & 0xffu);
-                const double4 k4 = colc[h * BB_CG + jj];
+                const double4 k4 = scx[h * 16 + jj];
                 a[jj] = fma(Mj, k4.x, k4.y);
                 cc[jj] = fma(Mj, k4.z, k4.w);
               }
+              // sum of a[j], c[j] over the set bits of the 16-bit W: each nibble fetches four 0.0 / 1.0 factors from
+              // the table (a predicated FP64 add costs ptxas an add + two selects; the factor inside an FMA nothing);
+              // four independent chains of eight FMAs
+              auto masked = [&](unsigned W, double& sa, double& sc) {
+                const double4 m0 = mt4[W & 15u], m1 = mt4[(W >> 4) & 15u], m2 = mt4[(W >> 8) & 15u], m3 = mt4[W >> 12];
+                double sa0 = a[0] * m0.x, sa1 = a[1] * m0.y, sc0 = cc[0] * m0.x, sc1 = cc[1] * m0.y;
+                sa0 = fma(a[2], m0.z, sa0);  sa1 = fma(a[3], m0.w, sa1);  sc0 = fma(cc[2], m0.z, sc0);  sc1 = fma(cc[3], m0.w, sc1);
+                sa0 = fma(a[4], m1.x, sa0);  sa1 = fma(a[5], m1.y, sa1);  sc0 = fma(cc[4], m1.x, sc0);  sc1 = fma(cc[5], m1.y, sc1);
+                sa0 = fma(a[6], m1.z, sa0);  sa1 = fma(a[7], m1.w, sa1);  sc0 = fma(cc[6], m1.z, sc0);  sc1 = fma(cc[7], m1.w, sc1);
+                sa0 = fma(a[8], m2.x, sa0);  sa1 = fma(a[9], m2.y, sa1);  sc0 = fma(cc[8], m2.x, sc0);  sc1 = fma(cc[9], m2.y, sc1);
+                sa0 = fma(a[10], m2.z, sa0); sa1 = fma(a[11], m2.w, sa1); sc0 = fma(cc[10], m2.z, sc0); sc1 = fma(cc[11], m2.w, sc1);
+                sa0 = fma(a[12], m3.x, sa0); sa1 = fma(a[13], m3.y, sa1); sc0 = fma(cc[12], m3.x, sc0); sc1 = fma(cc[13], m3.y, sc1);
+                sa0 = fma(a[14], m3.z, sa0); sa1 = fma(a[15], m3.w, sa1); sc0 = fma(cc[14], m3.z, sc0); sc1 = fma(cc[15], m3.w, sc1);
+                sa = sa0 + sa1;
+                sc = sc0 + sc1;
+              };
+              // the row loop is software-pipelined: row i+1's mask words and values are fetched while row i is summed
+              uint2 mk_n = msk2[h * 32];
+              unsigned mb_n = rowm[lane];
+              double4 rc_n = rowc[0];
 #pragma unroll 1
               for (int i = 0; i < 32; ++i) {
-                const uint4 mk = *reinterpret_cast<const uint4*>(msk + 4 * i);
-                const unsigned Wt = need_t ? (mk.x >> (BB_CG * h)) & 0xffffu : 0u;
-                const unsigned Wx = need_x ? (mk.y >> (BB_CG * h)) & 0xffffu : 0u;
-                const unsigned Wy = need_y ? (mk.z >> (BB_CG * h)) & 0xffffu : 0u;
-                const unsigned Wxy = need_xy ? (mk.w >> (BB_CG * h)) & 0xffffu : 0u;
-                if (!(Wt | Wx | Wy | Wxy)) continue;
-                double ai, ci, sa, scv;
-                row_vals(i, ai, ci);
+                const uint2 mk = mk_n;
+                const unsigned mb = mb_n;
+                const double4 rc = rc_n;
+                const int i1 = (i + 1) & 31;
+                mk_n = msk2[h * 32 + i1];
+                mb_n = rowm[i1 * 32 + lane];
+                rc_n = rowc[i1];
+                if (!(mk.x | mk.y)) continue;
+                const unsigned Wt = mk.x & 0xffffu, Wx = mk.x >> 16, Wy = mk.y & 0xffffu, Wxy = mk.y >> 16;
+                const double Mi = bb_magic(mb);
+                const double ai = fma(Mi, rc.x, rc.y), ci = fma(Mi, rc.z, rc.w);
+                double sa, scv;
                 if (Wt) {
-                  bb_masked_sum(a, cc, Wt, sa, scv);
+                  masked(Wt, sa, scv);
                   L[0][0] = fma(ai, sa, L[0][0]); L[0][1] = fma(ci, sa, fma(ai, scv, L[0][1])); L[0][2] = fma(ci, scv, L[0][2]);
                 }
                 if (Wx) {
-                  bb_masked_sum(a, cc, Wx, sa, scv);
+                  masked(Wx, sa, scv);
                   L[1][0] = fma(ai, sa, L[1][0]); L[1][1] = fma(ci, sa, fma(ai, scv, L[1][1])); L[1][2] = fma(ci, scv, L[1][2]);
                 }
                 if (Wy) {
-                  bb_masked_sum(a, cc, Wy, sa, scv);
+                  masked(Wy, sa, scv);
                   L[2][0] = fma(ai, sa, L[2][0]); L[2][1] = fma(ci, sa, fma(ai, scv, L[2][1])); L[2][2] = fma(ci, scv, L[2][2]);
                 }
                 if (Wxy) {
-                  bb_masked_sum(a, cc, Wxy, sa, scv);
+                  masked(Wxy, sa, scv);
                   L[3][0] = fma(ai, sa, L[3][0]); L[3][1] = fma(ci, sa, fma(ai, scv, L[3][1])); L[3][2] = fma(ci, scv, L[3][2]);
                 }
               }
@@ -576,8 +657,8 @@ bootbin_geo_kernel(const double* __restrict__ px, const double* __restrict__ py,
 __global__ void __launch_bounds__(256)
 bootbin_mult_kernel(const uint8_t* __restrict__ mult, int64_t n, int64_t nblk, int32_t nboot, int32_t bpad,
                     const double* __restrict__ geo, const double4* __restrict__ pt, const double* __restrict__ pz,
-                    uint8_t* __restrict__ m_row, uint8_t* __restrict__ m_nat, uint8_t* __restrict__ m_sx,
-                    uint8_t* __restrict__ m_sy, double* __restrict__ csum) {
+                    uint8_t* __restrict__ m_row, uint8_t* __restrict__ m_sx, uint8_t* __restrict__ m_sy,
+                    double* __restrict__ csum) {
   __shared__ unsigned tile_all[8][32][9];   // [warp][resample][column bytes, 36 B pitch]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int G = bpad / 32;
@@ -595,10 +676,9 @@ bootbin_mult_kernel(const uint8_t* __restrict__ mult, int64_t n, int64_t nblk, i
   const unsigned char* perm = reinterpret_cast<const unsigned char*>(geo + (size_t)c * BB_GEO + 68);
   const int gb = g * 32 + lane;
   // lane = resample
-  const unsigned* trow = reinterpret_cast<const unsigned*>(tile + lane * 36);
-  unsigned nat[8], sx[8], sy[8];
+  unsigned sx[8], sy[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) { nat[k] = trow[k]; sx[k] = 0u; sy[k] = 0u; }
+  for (int k = 0; k < 8; ++k) { sx[k] = 0u; sy[k] = 0u; }
   double CA = 0.0, CC = 0.0, CZ = 0.0;
   for (int p = 0; p < 32; ++p) {
     const int jx = perm[p], jy = perm[32 + p];
@@ -617,8 +697,6 @@ bootbin_mult_kernel(const uint8_t* __restrict__ mult, int64_t n, int64_t nblk, i
     m_row[(size_t)jp * bpad + gb] = (unsigned char)m;
   }
   uint4* o;
-  o = reinterpret_cast<uint4*>(m_nat + ((size_t)c * bpad + gb) * 32);
-  o[0] = make_uint4(nat[0], nat[1], nat[2], nat[3]); o[1] = make_uint4(nat[4], nat[5], nat[6], nat[7]);
   o = reinterpret_cast<uint4*>(m_sx + ((size_t)c * bpad + gb) * 32);
   o[0] = make_uint4(sx[0], sx[1], sx[2], sx[3]); o[1] = make_uint4(sx[4], sx[5], sx[6], sx[7]);
   o = reinterpret_cast<uint4*>(m_sy + ((size_t)c * bpad + gb) * 32);
@@ -681,7 +759,7 @@ extern "C" int tgp_bootbin_stats(unsigned long long* host8, int reset) {
 
 static inline int64_t bb_align(int64_t v) { return (v + 255) & ~(int64_t)255; }
 struct BBLayout {
-  int64_t geo, pt, m_row, m_nat, m_sx, m_sy, csum, total;
+  int64_t geo, pt, m_row, m_sx, m_sy, csum, total;
 };
 static BBLayout bb_layout(int64_t n, int32_t bpad) {
   const int64_t nblk = tgp_cdiv(n, BB_CHUNK);
@@ -690,7 +768,6 @@ static BBLayout bb_layout(int64_t n, int32_t bpad) {
   L.geo = o; o = bb_align(o + nblk * BB_GEO * 8);
   L.pt = o; o = bb_align(o + nblk * BB_CHUNK * 32);
   L.m_row = o; o = bb_align(o + nblk * BB_CHUNK * (int64_t)bpad);
-  L.m_nat = o; o = bb_align(o + nblk * BB_CHUNK * (int64_t)bpad);
   L.m_sx = o; o = bb_align(o + nblk * BB_CHUNK * (int64_t)bpad);
   L.m_sy = o; o = bb_align(o + nblk * BB_CHUNK * (int64_t)bpad);
   L.csum = o; o = bb_align(o + nblk * 3 * (int64_t)bpad * 8);
@@ -734,7 +811,7 @@ extern "C" int tgp_bootbin_twod(const double* px, const double* py, const double
   P.px = px; P.py = py;
   P.pt = reinterpret_cast<const double4*>(wk + L.pt);
   P.geo = reinterpret_cast<const double*>(wk + L.geo);
-  P.m_row = wk + L.m_row; P.m_nat = wk + L.m_nat; P.m_sx = wk + L.m_sx; P.m_sy = wk + L.m_sy;
+  P.m_row = wk + L.m_row; P.m_sx = wk + L.m_sx; P.m_sy = wk + L.m_sy;
   P.csum = reinterpret_cast<const double*>(wk + L.csum);
   P.edges = edges;
   P.hist = sums;
@@ -748,30 +825,25 @@ extern "C" int tgp_bootbin_twod(const double* px, const double* py, const double
       px, py, pz, pw, n, nblk, reinterpret_cast<double*>(wk + L.geo), reinterpret_cast<double4*>(wk + L.pt));
   TGP_LAUNCH_CHECK();
   bootbin_mult_kernel<<<(unsigned)tgp_cdiv(nblk * P.ngroups, 8), 256, 0, st>>>(
-      mult, n, nblk, nboot, bpad, P.geo, P.pt, pz, wk + L.m_row, wk + L.m_nat, wk + L.m_sx, wk + L.m_sy,
+      mult, n, nblk, nboot, bpad, P.geo, P.pt, pz, wk + L.m_row, wk + L.m_sx, wk + L.m_sy,
       reinterpret_cast<double*>(wk + L.csum));
   TGP_LAUNCH_CHECK();
   bootbin_delta_kernel<<<(unsigned)P.ngroups, 256, 0, st>>>(P.csum, nblk, bpad, n, delta);
   TGP_LAUNCH_CHECK();
 
-  const size_t smem = (size_t)((nbins + 2) & ~1) * 8 + (size_t)BB_WARPS * 4864;
+  // shared memory of a CTA: thresholds, nibble masks, two row-prefix tables, row data, per-warp staging
+  const size_t smem = (size_t)((nbins + 2) & ~1) * 8 + 512 + 2 * 33 * 32 * 16 + 1024 + 1024 + 512 + 512 + 16 +
+                      (size_t)BB_WARPS * BB_WARP_SMEM;
   TGP_CHECK_ARG(smem <= 200 * 1024, "too many bins");
   const int sms = tgp_num_sms();
-  const int64_t grid_target = (int64_t)sms * 3;
-  // work decomposition: item = (resample group, 32 row points, run of column chunks)
-  const double chunk_pairs = 0.5 * (double)nblk * (double)nblk * (double)P.ngroups;
-  const double slots = (double)grid_target * BB_WARPS * tile_nranks;
-  int64_t run = (int64_t)(chunk_pairs / (slots * 32.0));
-  run = (run / 32) * 32;
-  if (run < 32) run = 32;
-  if (run > 256) run = 256;
-  P.run = (int32_t)run;
-  const int64_t nruns = tgp_cdiv(nblk, run);
-  P.items_per_group = run * (nruns * nruns - nruns * (nruns - 1) / 2);
-  const int64_t total_items = P.items_per_group * P.ngroups;
+  const int64_t grid_target = (int64_t)sms * BB_MIN_CTAS;
+  // work decomposition: item = (resample group, row block) x all column chunks from the row block on
+  P.run = 0;
+  P.items_per_group = nblk;
+  const int64_t total_items = nblk * P.ngroups;
   P.my_items = (total_items - tile_rank + tile_nranks - 1) / tile_nranks;
   if (P.my_items <= 0) return TGP_OK;
-  int64_t grid = tgp_cdiv(P.my_items, BB_WARPS);
+  int64_t grid = P.my_items;
   if (grid > grid_target) grid = grid_target;
 
   static std::atomic<unsigned> launch_seq{0};
