@@ -242,7 +242,8 @@ int tgp_bootbin_xi(const double* sums, const double* delta, int32_t nbins, int32
 int64_t tgp_bootbin_work_bytes(int64_t n, int32_t nboot);
 int64_t tgp_bootbin_sums_doubles(int32_t nbins, int32_t nboot);
 /* Diagnostics: blocks per path of all tgp_bootbin_twod launches since the last reset: [0] booked whole, [1] axis
- * sweeps, [2] pair-by-pair blocks, [3] exact per-pair blocks, [4] window flushes, [5] sweeps handed back. */
+ * sweeps, [2] pair-by-pair blocks, [3] exact per-pair blocks, [4] window flushes, [5] sweeps handed back,
+ * [6] wide-window blocks summed bin by bin. */
 int tgp_bootbin_stats(unsigned long long* host8 /*host*/, int reset);
 
 /* Pair sums of a VECTOR field's 2-point functions in log-radius bins (E/B diagnostics; replaces the all-pairs numpy
@@ -314,7 +315,7 @@ int tgp_pairbin_stats(unsigned long long* host8 /*host*/, int reset);
  * ("pairbin_block_sums" 0) skips the per-pair mirrored-bin check in blocks whose bounding boxes prove it
  * (0 = the general paths only; results are identical either way); "bootbin_paths": bit mask of tgp_bootbin_twod,
  * default all on; bit 0 = blocks in one bin booked from chunk sums, bit 1 = window paths (0: every block through the
- * exact per-pair path), bit 2 = axis sweeps. */
+ * exact per-pair path), bit 2 = axis sweeps, bit 3 = blocks spanning more than 2 x 2 bins summed bin by bin. */
 int tgp_set_option(const char* name, int value);
 
 /* ---- measurement helpers --------------------------------------------------------------------- */

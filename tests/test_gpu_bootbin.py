@@ -32,7 +32,7 @@ def _xi(tp, B, shared, paths=None):
         return tp._bootstrap_xi(B)
     finally:
         if paths is not None:
-            backend.set_option("bootbin_paths", 7)
+            backend.set_option("bootbin_paths", 15)
 
 
 def _close(a, b, scale, tol=2e-11):
@@ -56,15 +56,15 @@ def test_shared_batch_equals_catalogue_batch(weighted, nbins, max_frac):
     tp = treegp.two_pcf(X, y, err, 0.0, max_frac * np.hypot(L, L), nbins=nbins, anisotropic=True)
     ref = _xi(tp, B, shared=False)
     scale = np.var(y)
-    for paths in (0, 2, 3, 6, 7):
+    for paths in (0, 2, 3, 6, 7, 15):
         backend.bootbin_stats(reset=True)
         got = _xi(tp, B, shared=True, paths=paths)
         st = backend.bootbin_stats()
         _close(got, ref, scale)
         if paths == 0:
             assert st["closed_form"] == 0 and st["sweeps"] == 0 and st["pairwise"] == 0 and st["exact_per_pair"] > 0
-        if paths == 7:
-            assert st["closed_form"] + st["sweeps"] + st["pairwise"] > 0
+        if paths == 15:
+            assert st["closed_form"] + st["sweeps"] + st["pairwise"] + st["bin_by_bin"] > 0
 
 
 def test_unweighted_pair_weights_are_exact_integers():
@@ -109,7 +109,7 @@ def test_lattice_displacements_on_bin_edges(nbins):
     X, y = _field(n, 7, lattice=True, L=64.0)
     tp = treegp.two_pcf(X, y, np.zeros(n), 0.0, 21.0 if nbins == 21 else 20.0, nbins=nbins, anisotropic=True)
     ref = _xi(tp, B, shared=False)
-    for paths in (0, 7):
+    for paths in (0, 7, 15):
         backend.bootbin_stats(reset=True)
         got = _xi(tp, B, shared=True, paths=paths)
         _close(got, ref, np.var(y))

@@ -288,7 +288,7 @@ def bootbin_stats(reset=True):
     """Blocks per path of tgp_bootbin_twod since the last reset; synchronises the device."""
     buf = (ctypes.c_ulonglong * 8)()
     check(_cabi.load().tgp_bootbin_stats(buf, int(bool(reset))), "tgp_bootbin_stats")
-    keys = ("closed_form", "sweeps", "pairwise", "exact_per_pair", "flushes", "sweeps_handed_back")
+    keys = ("closed_form", "sweeps", "pairwise", "exact_per_pair", "flushes", "sweeps_handed_back", "bin_by_bin")
     return {k: int(buf[i]) for i, k in enumerate(keys)}
 
 

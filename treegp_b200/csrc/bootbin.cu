@@ -64,7 +64,7 @@ struct BBParams {
 };
 
 // diagnostics: [0] blocks booked whole, [1] sweeps, [2] pair-by-pair blocks, [3] exact per-pair (slow) blocks,
-// [4] window flushes, [5] sweeps handed back (mirrored split differs)
+// [4] window flushes, [5] sweeps handed back (mirrored split differs), [6] wide-window blocks summed bin by bin
 __device__ unsigned long long g_bb_stats[8];
 
 enum { BB_OUT = 0, BB_REG_FULL = 1, BB_REG_CHECK = 2, BB_GENERIC = 3 };
@@ -166,7 +166,7 @@ bootbin_kernel(BBParams P) {
   const double NaN = __longlong_as_double(0x7ff8000000000000ll);
   const int G = P.ngroups;
   const int64_t n = P.n, nblk = P.nblk;
-  unsigned st_closed = 0, st_sweep = 0, st_pair = 0, st_slow = 0, st_flush = 0, st_back = 0;
+  unsigned st_closed = 0, st_sweep = 0, st_pair = 0, st_slow = 0, st_flush = 0, st_back = 0, st_gen = 0;
 
   // window registers: element u = ux + 2 uy holds the sums over pairs with (x bit >= ux) and (y bit >= uy)
   double wacc[4][3];
@@ -307,6 +307,99 @@ bootbin_kernel(BBParams P) {
         }
       }
     };
+    // Blocks whose displacements span more than 2 x 2 bins (sparse catalogues, small bins): the local bin of every
+    // pair is found once (lanes = columns, exact thresholds); then, bin by bin of the block's window, the pairs of
+    // that bin are summed per resample lane (masked FMAs over the chunk's 32 columns in registers, nibbles without
+    // a bit skipped) into registers -- three red.global per BIN of the block instead of three per pair.
+    // false: not handled (window of more than 64 bins, or a pair whose mirrored bin is not the mirror image).
+    auto generic_block = [&](int64_t c, bool diag, int x0, int y0) -> bool {
+      const double* grec = P.geo + (size_t)c * BB_GEO;
+      const double4 bb = *reinterpret_cast<const double4*>(grec);
+      const int x1 = bb_bin_search(bb.y - iminx, nbins, ed), y1 = bb_bin_search(bb.w - iminy, nbins, ed);
+      const int wxn = x1 - x0 + 1, wyn = y1 - y0 + 1;
+      if (wxn < 1 || wyn < 1 || wxn * wyn > 64) return false;
+      const unsigned char* cperm = reinterpret_cast<const unsigned char*>(grec + 68);
+      const int cnt = (int)((n - c * BB_CHUNK < BB_CHUNK) ? (n - c * BB_CHUNK) : BB_CHUNK);
+      const bool clive = lane < cnt;
+      const double sx = grec[4 + lane];
+      const int pcx = cperm[lane];
+      const double yjx = clive ? P.py[c * BB_CHUNK + pcx] : NaN;
+      const uint4* mpx = reinterpret_cast<const uint4*>(P.m_sx + ((size_t)c * bpad + gb) * 32);
+      const uint4 ux0 = mpx[0], ux1 = mpx[1];
+      const unsigned wbx[8] = {ux0.x, ux0.y, ux0.z, ux0.w, ux1.x, ux1.y, ux1.z, ux1.w};
+      __syncwarp();
+      scx[lane] = P.pt[c * BB_CHUNK + pcx];
+      __syncwarp();
+      // local bin of every pair of this lane's column (255: not in range), four rows per word
+      unsigned lbw[8];
+      unsigned anymism = 0u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) lbw[k] = 0u;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const double2 ri = rxy[i];
+        const double dx = sx - ri.x, dy = yjx - ri.y;
+        const double r2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        const bool inr = clive && i < nlive && r2 >= lo2 && fabs(dx) < M && fabs(dy) < M && (!diag || pcx > i);
+        unsigned lb = 255u;
+        if (inr) {
+          const int bx = bb_bin_twod(dx, M, P.inv_bin, nbins, ed), by = bb_bin_twod(dy, M, P.inv_bin, nbins, ed);
+          const int mx = bb_bin_twod(-dx, M, P.inv_bin, nbins, ed), my = bb_bin_twod(-dy, M, P.inv_bin, nbins, ed);
+          if (mx != nbins - 1 - bx || my != nbins - 1 - by) anymism = 1u;
+          lb = (unsigned)((by - y0) * wxn + (bx - x0));
+        }
+        lbw[i >> 2] |= lb << (8 * (i & 3));
+      }
+      if (__any_sync(0xffffffffu, anymism != 0u)) return false;
+      double a[32], cc[32];
+#pragma unroll
+      for (int p = 0; p < 32; ++p) {
+        const double Mj = bb_magic((wbx[p >> 2] >> (8 * (p & 3))) & 0xffu);
+        const double4 k4 = scx[p];
+        a[p] = fma(Mj, k4.x, k4.y);
+        cc[p] = fma(Mj, k4.z, k4.w);
+      }
+      const double4* mt4 = reinterpret_cast<const double4*>(mtab);
+      const size_t s3 = (size_t)nb * bpad;
+#pragma unroll 1
+      for (int lb = 0; lb < wxn * wyn; ++lb) {
+        unsigned mymask = 0u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const unsigned m = __ballot_sync(0xffffffffu, ((lbw[i >> 2] >> (8 * (i & 3))) & 0xffu) == (unsigned)lb);
+          if (lane == i) mymask = m;
+        }
+        unsigned rows = __ballot_sync(0xffffffffu, mymask != 0u);
+        if (!rows) continue;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+        while (rows) {
+          const int i = __ffs(rows) - 1;
+          rows &= rows - 1;
+          const unsigned W = __shfl_sync(0xffffffffu, mymask, i);
+          double ai, ci;
+          row_vals(i, ai, ci);
+          double sa0 = 0.0, sa1 = 0.0, sc0 = 0.0, sc1 = 0.0;
+#pragma unroll
+          for (int q8 = 0; q8 < 8; ++q8) {
+            const unsigned nib = (W >> (4 * q8)) & 15u;
+            if (nib) {
+              const double4 m = mt4[nib];
+              sa0 = fma(a[4 * q8], m.x, sa0);     sc0 = fma(cc[4 * q8], m.x, sc0);
+              sa1 = fma(a[4 * q8 + 1], m.y, sa1); sc1 = fma(cc[4 * q8 + 1], m.y, sc1);
+              sa0 = fma(a[4 * q8 + 2], m.z, sa0); sc0 = fma(cc[4 * q8 + 2], m.z, sc0);
+              sa1 = fma(a[4 * q8 + 3], m.w, sa1); sc1 = fma(cc[4 * q8 + 3], m.w, sc1);
+            }
+          }
+          const double sa = sa0 + sa1, scv = sc0 + sc1;
+          v0 = fma(ai, sa, v0);
+          v1 = fma(ci, sa, fma(ai, scv, v1));
+          v2 = fma(ci, scv, v2);
+        }
+        double* h = P.hist + (size_t)((y0 + lb / wxn) * nbins + x0 + lb % wxn) * bpad + gb;
+        atomicAdd(h, v0); atomicAdd(h + s3, v1); atomicAdd(h + 2 * s3, v2);
+      }
+      return true;
+    };
     // Sweep along one axis: the sums over the pairs whose bit along that axis is set (upper bin), for the 32
     // resamples of this group.  Column p (ascending along the axis, coordinate s) pairs with the rows whose
     // coordinate is small enough, fl(s - r_k) >= t: the first nle rows in ascending order, so its share is its own
@@ -406,6 +499,10 @@ bootbin_kernel(BBParams P) {
         const int cls = d & 3, ex = (d >> 2) & 1, ey = (d >> 3) & 1, x0 = (d >> 8) & 0xfff, y0 = (d >> 20) & 0xfff;
         const bool diag = (d >> 4) & 1;
         if (cls == BB_GENERIC || !(P.paths & 2)) {
+          if (cls == BB_GENERIC && (P.paths & 2) && (P.paths & 8)) {
+            flush();
+            if (generic_block(c, diag, x0, y0)) { ++st_gen; continue; }
+          }
           slow_block(c, diag);
           continue;
         }
@@ -609,6 +706,7 @@ bootbin_kernel(BBParams P) {
     if (st_slow) atomicAdd(&g_bb_stats[3], (unsigned long long)st_slow);
     if (st_flush) atomicAdd(&g_bb_stats[4], (unsigned long long)st_flush);
     if (st_back) atomicAdd(&g_bb_stats[5], (unsigned long long)st_back);
+    if (st_gen) atomicAdd(&g_bb_stats[6], (unsigned long long)st_gen);
   }
 }
 
@@ -743,8 +841,8 @@ __global__ void bootbin_xi_kernel(const double* __restrict__ hist, const double*
   if (sumw) sumw[(size_t)b * nb + bin] = s0;
 }
 
-static int g_bb_paths = 7;   // tgp_set_option("bootbin_paths", bits): 1 whole-block bookings, 2 window paths (else
-                             // every block exact pair by pair), 4 sweeps
+static int g_bb_paths = 15;  // tgp_set_option("bootbin_paths", bits): 1 whole-block bookings, 2 window paths (else
+                             // every block exact pair by pair), 4 sweeps, 8 bin-by-bin form of wide-window blocks
 extern "C" int tgp_bootbin_set_paths(int bits) { g_bb_paths = bits; return TGP_OK; }
 
 extern "C" int tgp_bootbin_stats(unsigned long long* host8, int reset) {
