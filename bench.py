@@ -829,10 +829,21 @@ def run_cfg5(args, treegp, backend, ctx):
     tq = treegp.two_pcf(X, rng.normal(size=n), np.zeros(n), 0.0, np.sqrt(2.0) * Lf / 2.0, nbins=21, anisotropic=True)
     tq.comp_xi_covariance(n_bootstrap=2, mask=None, seed=1)
     torch.cuda.synchronize()
+    backend.bootbin_stats(reset=True)
     t0 = time.perf_counter()
     tq.comp_xi_covariance(n_bootstrap=B, mask=None, seed=610639139)
     torch.cuda.synchronize()
     out["cfg5_bootstrap100_default_maxsep_s"] = time.perf_counter() - t0
+    out["cfg5_bootstrap_paths_blocks"] = backend.bootbin_stats()
+    # the same resamples as independent weighted catalogues of one tgp_pairbin launch (the round-1 batch)
+    tq.SHARED_BOOTSTRAP = False
+    tq.comp_xi_covariance(n_bootstrap=2, mask=None, seed=1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tq.comp_xi_covariance(n_bootstrap=B, mask=None, seed=610639139)
+    torch.cuda.synchronize()
+    out["cfg5_bootstrap100_default_maxsep_per_catalogue_s"] = time.perf_counter() - t0
+    tq.SHARED_BOOTSTRAP = True
     # the public path: solve() = pair count + 444 resamples (fsolve, two_pcf.py:375-383) + robust fit
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -142,6 +142,9 @@ def install():
         return torch.stack(planes)
 
     backend.pairbin_packed = pairbin_packed
+    from . import bootbin_standin
+
+    bootbin_standin.install(backend, po)
 
     def robust_chi2_batch(coord_d, y_d, W_d, family, params):
         """numpy restatement of two_pcf.py:12-31,96-148 (the objective of the robust fit) for the stand-in."""

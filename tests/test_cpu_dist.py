@@ -46,6 +46,11 @@ def _worker(rank, world, port, ret):
             return torch.stack([c.to(torch.int64).view(torch.float64), sw, swkk] + ([] if swr is None else [swr]))
 
         backend.pairbin_packed = fake_packed
+        import sys
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from refsuite import bootbin_standin
+
+        bootbin_standin.install(backend, po, slab=dist.slab)
         assert dist.rank_world(None) == (rank, world)
         assert dist.rank_world(False) == (0, 1) and dist.rank_world(dist.WORLD) == (rank, world)
         # sharding is opt-in: by default every process counts all pairs of its own catalogue
@@ -65,6 +70,17 @@ def _worker(rank, world, port, ret):
             np.testing.assert_allclose(dist_, rdist, rtol=1e-12)
             full = po.pairbin(X[:, 0], X[:, 1], y - y.mean(), 1 / y_err ** 2, mn, mx, nb, "TwoD" if aniso else "Log")
             np.testing.assert_array_equal(t._last_npairs[0], full["npairs"])  # counts exact for any world size
+            if aniso:
+                # the bootstrap batch shards the same way: per-rank partial sums, one all-reduce, identical covariance
+                B = 5
+                cov = t.comp_xi_covariance(n_bootstrap=B, mask=mask, seed=99)
+                r = np.random.default_rng(99)
+                xis = []
+                for _ in range(B):
+                    ind = r.integers(0, n - 1, size=n)
+                    xis.append(po.comp_2pcf(X[ind], y[ind], y_err[ind], mn, mx, nb, aniso)[0][mask])
+                d = np.array(xis) - np.mean(xis, axis=0)
+                np.testing.assert_allclose(cov, d.T @ d / (B - 1.0), rtol=0, atol=1e-12)
 
         # ---- distributed forward-difference gradient of the likelihood search (opt-in) ----
         from treegp_b200 import log_likelihood as llmod
