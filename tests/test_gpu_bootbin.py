@@ -160,3 +160,23 @@ def test_large_batch_matches_catalogue_batch():
     st = backend.bootbin_stats()
     _close(got, ref, np.var(y))
     assert st["closed_form"] > 0 and st["sweeps"] > 0 and st["exact_per_pair"] < st["closed_form"]
+
+
+def test_small_remainder_goes_through_the_catalogue_path_with_the_same_stream():
+    """n_bootstrap = 32 k + (a few): the remainder is drawn from the same random stream and counted as independent
+    catalogues; the result equals the all-catalogue batch resample by resample."""
+    import treegp_b200 as treegp
+
+    n, B = 1500, 35
+    X, y = _field(n, 51)
+    tp = treegp.two_pcf(X, y, np.full(n, 0.3), 0.0, 30.0, nbins=9, anisotropic=True)
+    ref = _xi(tp, B, shared=False)
+    got = _xi(tp, B, shared=True)
+    _close(got, ref, np.var(y))
+    # and the generator ends in the same state: the next draw agrees
+    a = tp.resample_bootstrap()
+    tp.SHARED_BOOTSTRAP = False
+    tp._rng = None
+    tp._bootstrap_xi(B)
+    b = tp.resample_bootstrap()
+    assert np.array_equal(a[0], b[0])

@@ -624,7 +624,7 @@ bootbin_kernel(BBParams P) {
               }
               // sum of a[j], c[j] over the set bits of the 16-bit W: each nibble fetches four 0.0 / 1.0 factors from
               // the table (a predicated FP64 add costs ptxas an add + two selects; the factor inside an FMA nothing);
-              // four independent chains of eight FMAs
+              // four independent chains of eight FMAs (skipping the nibbles without a bit measured slower: 306 vs 267 ms)
               auto masked = [&](unsigned W, double& sa, double& sc) {
                 const double4 m0 = mt4[W & 15u], m1 = mt4[(W >> 4) & 15u], m2 = mt4[(W >> 8) & 15u], m3 = mt4[W >> 12];
                 double sa0 = a[0] * m0.x, sa1 = a[1] * m0.y, sc0 = cc[0] * m0.x, sc1 = cc[1] * m0.y;
