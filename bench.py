@@ -495,6 +495,8 @@ def run_ours(args):
         cfg.update(run_cfg2(args, treegp, backend, ctx))
         if world == 1:
             cfg.update(run_cfg5(args, treegp, backend, ctx))
+        else:
+            cfg.update(run_bootstrap_sharded(args, treegp, backend, dist, ctx))
     line["cfg"] = cfg or None
 
     # ---------------- CPU baselines (rank 0, one GPU, bounded samples) ----------------
@@ -852,6 +854,29 @@ def run_cfg5(args, treegp, backend, ctx):
     out["cfg5_solve_444_resamples_s"] = time.perf_counter() - t0
     out["cfg5_solve_result"] = [float(v) for v in gp._optimizer._results_robust]
     return out
+
+
+def run_bootstrap_sharded(args, treegp, backend, dist, ctx):
+    """N > 1: the 100-resample bootstrap of configs[4] (iid field, N = 200k, default max_sep) with the work items of
+    tgp_bootbin_twod dealt to the ranks and ONE all-reduce of the per-resample sums (torch.distributed / NCCL)."""
+    import torch
+
+    rank, world, dev, barrier, max_over_ranks = (ctx[k] for k in ("rank", "world", "dev", "barrier", "max_over_ranks"))
+    n, B = 200_000, 100
+    Lf = 1000.0 * np.sqrt(n / 1e6)
+    rng = np.random.default_rng(11)
+    X = rng.uniform(-Lf / 2, Lf / 2, size=(n, 2))
+    tq = treegp.two_pcf(X, rng.normal(size=n), np.zeros(n), 0.0, np.sqrt(2.0) * Lf / 2.0, nbins=21, anisotropic=True)
+    tq.group = dist.WORLD
+    tq.comp_xi_covariance(n_bootstrap=2, mask=None, seed=1)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    cov = tq.comp_xi_covariance(n_bootstrap=B, mask=None, seed=610639139)
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    return {"cfg5_bootstrap100_default_maxsep_s": dt, "cfg5_bootstrap_cov_trace": float(np.trace(cov)),
+            "cfg5_bootstrap_sharding": "work items of tgp_bootbin_twod over %d ranks + one all-reduce of the sums" % world}
 
 
 def main():
