@@ -397,3 +397,56 @@ def test_draw_multiplicities_continues_the_python_generator():
     ua, _, ya, _ = a.resample_bootstrap()
     ub, _, yb, _ = b.resample_bootstrap()
     assert np.array_equal(ua, ub) and np.array_equal(ya, yb)
+
+
+# ---- windowed predictive variance: host-side plan ------------------------------------------------------
+@pytest.mark.parametrize("ndim", [1, 2])
+def test_variance_window_plan_only_skips_uncorrelated_points(ndim):
+    """backend.support_cutoffs / plan_var_windows (pure host logic): every training point a chunk skips lies at
+    q = d^T M d >= q_cut from EVERY test point of the chunk, in the ascending and in the descending order; the
+    skips are multiples of 64 and leave a non-empty system; the flop counts are what the skips imply."""
+    from treegp_b200 import _cabi, backend, eval_kernel
+    from treegp_b200.kernels import lower_kernel
+
+    rng = np.random.default_rng(5 + ndim)
+    if ndim == 2:
+        Mi = np.array([[0.9, -0.35], [-0.35, 0.6]])
+        desc = lower_kernel(eval_kernel("2.0 * AnisotropicVonKarman(invLam=array([[0.9, -0.35], [-0.35, 0.6]]))"), 2)
+    else:
+        Mi = np.array([[1.0 / 0.7 ** 2]])
+        desc = lower_kernel(eval_kernel("2.0 * RBF(0.7)"), 1)
+    qcut = float(_cabi.load().tgp_profile_qcut(int(desc.family)))
+    dcut = backend.support_cutoffs(desc)
+    assert len(dcut) == ndim
+    # the per-axis cut-off is exactly the smallest |d_a| that guarantees q >= q_cut: minimise q over the other axis
+    if ndim == 2:
+        for a in (0, 1):
+            o = 1 - a
+            d = np.zeros(2)
+            d[a] = dcut[a]
+            d[o] = -Mi[a, o] * d[a] / Mi[o, o]
+            assert abs(d @ Mi @ d - qcut) < 1e-9 * qcut
+    n, m, chunk = 5000, 20000, 1500
+    field = 400.0
+    X = rng.uniform(0, field, size=(n, ndim))
+    Xs = rng.uniform(0, field, size=(m, ndim))
+    axis = int(np.argmin(np.asarray(dcut)))          # same extent on both axes
+    ot, os_ = np.argsort(X[:, axis], kind="stable"), np.argsort(Xs[:, axis], kind="stable")
+    Xt, Xss = X[ot], Xs[os_]
+    starts = np.arange(0, m, chunk)
+    ends = np.minimum(starts + chunk, m) - 1
+    sizes = ends - starts + 1
+    sa, sd, use_desc, f_win, f_full = backend.plan_var_windows(Xt[:, axis], Xss[starts, axis], Xss[ends, axis], dcut[axis], sizes)
+    assert np.all(sa % 64 == 0) and np.all(sd % 64 == 0) and np.all(sa < n) and np.all(sd < n)
+    assert use_desc.any() and (~use_desc).any() and f_win < 0.5 * f_full
+    Xdesc = Xt[::-1]
+    left = 0.0
+    for c in range(len(starts)):
+        P = Xss[starts[c]:ends[c] + 1]
+        for skipped in (Xt[:sa[c]], Xdesc[:sd[c]]):
+            if len(skipped):
+                d = P[:, None, :] - skipped[None, :, :]
+                q = np.einsum("pta,ab,ptb->pt", d, Mi, d)
+                assert q.min() >= qcut
+        left += sizes[c] * float(n - (sd[c] if use_desc[c] else sa[c])) ** 2
+    assert f_win == left and f_full == float(m) * n * n

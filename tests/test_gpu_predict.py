@@ -146,3 +146,72 @@ def test_knn_mean_ties_take_the_lower_index(gpu_ready):
     got = backend.knn_mean(X0, y0, np.array([[2.0, 2.0]]), 4).cpu().numpy()
     # nearest: index 12 (d = 0), then 7, 11, 13, 17 at d = 1 -> 7, 11, 13 by index
     np.testing.assert_allclose(got, [(12 + 7 + 11 + 13) / 4.0])
+
+
+@pytest.mark.parametrize("case", ["rbf2", "vk2", "rbf1"])
+def test_windowed_variance_equals_plain_variance(gpu_ready, case):
+    """backend.predict_var_windowed: chunks of neighbouring test points solve only the trailing sub-system of the
+    ascending / descending factorisation they can be correlated with.  Same numbers as tgp_predict_var on the
+    unsorted factor (only rounding differs: correlations below 1e-40 amp count as zero) and as the oracle."""
+    from treegp_b200 import backend, eval_kernel
+    from treegp_b200.kernels import lower_kernel
+
+    rng = np.random.default_rng(17)
+    n, m, field = 2500, 12000, 300.0
+    if case == "rbf1":
+        ndim, s, fam, kw = 1, "2.0 * RBF(0.8)", "rbf", dict(amp=2.0, invLam=np.array([[1.0 / 0.64]]))
+    else:
+        ndim = 2
+        Mi = np.array([[0.9, -0.35], [-0.35, 0.6]])
+        name, fam = ("AnisotropicRBF", "rbf") if case == "rbf2" else ("AnisotropicVonKarman", "vonkarman")
+        s, kw = "2.0 * %s(invLam=array([[0.9, -0.35], [-0.35, 0.6]]))" % name, dict(amp=2.0, invLam=Mi)
+    X = rng.uniform(0, field, size=(n, ndim))
+    Xs = rng.uniform(0, field, size=(m, ndim))
+    desc = lower_kernel(eval_kernel(s), ndim)
+    yerr2 = rng.uniform(0.005, 0.02, size=n)
+    e2 = backend.to_device(yerr2)
+    ws = backend.kmat_sym(X, desc, diag_add=e2, lower_only=True)
+    assert int(backend.potrf(ws, n).item()) == 0
+    plain = backend.predict_var(Xs, X, desc, ws).cpu().numpy()
+    stats = {}
+    win = backend.predict_var_windowed(Xs, X, desc, e2, chunk=1024, stats=stats)
+    assert win is not None and stats["used"] and stats["chunks"] == 12
+    assert 0 < stats["chunks_descending"] < stats["chunks"]
+    assert stats["flops_windowed"] + stats["flops_factors"] < 0.6 * stats["flops_full"]
+    np.testing.assert_allclose(win.cpu().numpy(), plain, rtol=0, atol=1e-11)
+    sub = rng.choice(m, 300, replace=False)
+    K = go.kmat(fam, X, **kw) + np.diag(yerr2)
+    ref = go.predictive_variance(K, go.kmat(fam, Xs[sub], X, **kw), 2.0)
+    np.testing.assert_allclose(win.cpu().numpy()[sub], ref, rtol=0, atol=1e-9)
+
+
+def test_windowed_variance_declines_when_it_does_not_pay(gpu_ready):
+    """Support as wide as the field, or too few test points for two extra factorisations: None, and
+    GPInterpolation.predict_var falls through to the plain solves with the same result."""
+    import treegp_b200 as treegp
+    from treegp_b200 import backend, eval_kernel
+    from treegp_b200.kernels import lower_kernel
+
+    rng = np.random.default_rng(3)
+    n = 1500
+    X = rng.uniform(0, 20.0, size=(n, 2))
+    e2 = backend.to_device(np.full(n, 0.01))
+    wide = lower_kernel(eval_kernel("1.0 * AnisotropicRBF(invLam=array([[0.5, 0.0], [0.0, 0.5]]))"), 2)
+    st = {}
+    assert backend.predict_var_windowed(rng.uniform(0, 20.0, size=(20000, 2)), X, wide, e2, chunk=1024, stats=st) is None
+    assert st["used"] is False
+    narrow = lower_kernel(eval_kernel("1.0 * AnisotropicRBF(invLam=array([[400.0, 0.0], [0.0, 400.0]]))"), 2)
+    assert backend.predict_var_windowed(rng.uniform(0, 20.0, size=(100, 2)), X, narrow, e2, stats=st) is None
+    # through the public class: both settings of the switch give the same variance
+    kstr = "1.0 * AnisotropicRBF(invLam=array([[30.0, 0.0], [0.0, 30.0]]))"
+    y = rng.normal(size=n)
+    Xs = rng.uniform(0, 20.0, size=(9000, 2))
+    out = []
+    for flag in (True, False):
+        gp = treegp.GPInterpolation(kernel=kstr, optimizer="none", normalize=True)
+        gp.WINDOWED_VARIANCE, gp.VAR_CHUNK = flag, 1024
+        gp.initialize(X, y, y_err=np.full(n, 0.1))
+        out.append(gp.predict_var(Xs) + (gp._var_plan.get("used", False),))
+    assert out[0][2] is True and out[1][2] is False
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(out[0][1], out[1][1], rtol=0, atol=1e-11)

@@ -125,6 +125,11 @@ class GPInterpolation(object):
             return y_interp, y_cov
         return y_interp
 
+    # predict_var: solve only the trailing sub-system that a chunk of neighbouring test points can be correlated with
+    # (backend.predict_var_windowed) whenever that is cheaper than the plain solves on the cached factor
+    WINDOWED_VARIANCE = True
+    VAR_CHUNK = None   # test points per pass (None: a workspace of about 2 GiB)
+
     def predict_var(self, X):
         """Extension (not in the reference): mean and DIAGONAL predictive variance for any number of
         test points -- what the reference's callers take from ``np.diag(y_cov)``, without the M x M
@@ -133,7 +138,12 @@ class GPInterpolation(object):
         Xd, desc, ws = self._factor
         Xs = backend.as_points(X)
         mean = backend.predict_mean(Xs, Xd, desc, self._alpha_dev)
-        var = backend.predict_var(Xs, Xd, desc, ws)
+        var, self._var_plan = None, {}
+        if self.WINDOWED_VARIANCE:
+            e2 = backend.to_device(np.asarray(self._y_err, dtype=np.float64).reshape(-1) ** 2)
+            var = backend.predict_var_windowed(Xs, Xd, desc, e2, chunk=self.VAR_CHUNK, stats=self._var_plan)
+        if var is None:
+            var = backend.predict_var(Xs, Xd, desc, ws, chunk=self.VAR_CHUNK)
         y = mean.cpu().numpy() + self._mean + self._build_average_meanify(X)
         return y, var.cpu().numpy()
 
