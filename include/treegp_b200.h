@@ -112,6 +112,32 @@ int tgp_loglike(const double* X, const double* y, const double* yerr2, int64_t N
                 const tgp_kernel* k /*host*/, double* work, int64_t ld, double* alpha, int want_alpha,
                 double* out, int32_t* info, void* stream);
 
+/* ---- (2b) envelope (variable-band) forms of the dense calls ----------------------------------------
+ * Same results as the dense calls above for a matrix that is ZERO outside an envelope -- which is what K(X, X) is,
+ * to 1e-40 of its amplitude, once the points are sorted along one axis and the kernel's support (tgp_profile_qcut)
+ * is short against the field: row i then starts at the first point within the cut-off distance of point i, and a
+ * Cholesky factor keeps the envelope of its matrix.  The reference factorises the dense matrix whatever the kernel
+ * (gp_interp.py:181, log_likelihood.py:30); these entry points skip the blocks that are zero: N bw^2 flop instead
+ * of N^3 / 3 for a band of bw rows.
+ * row_end (HOST array, one entry per block of tgp_envelope_block() = 512 columns, nblocks = ceil(N / 512)):
+ * the rows [row_end[b], N) of block column b are outside the envelope.  Entries are clamped to
+ * [end of the block, N] and made non-decreasing.  Rows outside the envelope are neither read nor written. */
+int tgp_envelope_block(void);
+
+/* tgp_potrf_rows restricted to the envelope (nrows extra right-hand-side rows below the matrix, may be 0). */
+int tgp_potrf_env(double* A, int64_t N, int64_t ld, const int64_t* row_end /*host*/, int64_t nblocks,
+                  int64_t nrows, int32_t* info, void* stream);
+
+/* tgp_trsm_rows for a factor with the envelope row_end: 2 M N bw flop instead of M N^2. */
+int tgp_trsm_rows_env(const double* L, int64_t N, int64_t ld, const int64_t* row_end /*host*/, int64_t nblocks,
+                      double* B, int64_t M, int64_t ldb, void* stream);
+
+/* tgp_loglike with the factorisation restricted to the envelope (X sorted along the envelope's axis by the
+ * caller; y, yerr2 and alpha in the same order). */
+int tgp_loglike_env(const double* X, const double* y, const double* yerr2, int64_t N,
+                    const tgp_kernel* k /*host*/, double* work, int64_t ld, double* alpha, int want_alpha,
+                    double* out, int32_t* info, const int64_t* row_end /*host*/, int64_t nblocks, void* stream);
+
 /* ---- (4) predict ----------------------------------------------------------------------------- */
 
 /* mean[m] = sum_n K(Xs_m, X_n) alpha_n without materialising K(Xs, X).
@@ -137,6 +163,11 @@ double tgp_profile_qcut(int32_t family);
 int tgp_predict_var(const double* Xs, int64_t M, const double* X, int64_t N,
                     const tgp_kernel* k /*host*/, const double* L, int64_t ld, double* work,
                     int64_t chunk, double* var, void* stream);
+
+/* tgp_predict_var on a factor with a known envelope (tgp_potrf_env / tgp_loglike_env; X in the factor's order). */
+int tgp_predict_var_env(const double* Xs, int64_t M, const double* X, int64_t N,
+                        const tgp_kernel* k /*host*/, const double* L, int64_t ld, const int64_t* row_end /*host*/,
+                        int64_t nblocks, double* work, int64_t chunk, double* var, void* stream);
 
 /* out[m] = uniform mean of y0 over the k grid points nearest to Xq_m (squared Euclidean distance, exact ties
  * towards the lower grid index, values summed in order of increasing distance).  Replaces

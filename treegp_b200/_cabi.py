@@ -43,6 +43,11 @@ SIGNATURES = {
     "tgp_gemm_nt_sub": [_vp, _i64, _i64, _i64, _vp, _i64, _vp, _i64, _i64, ctypes.c_int, _vp],
     "tgp_logdet_chi2": [_vp, _i64, _i64, _vp, _vp, _vp, _vp],
     "tgp_loglike": [_vp, _vp, _vp, _i64, _kp, _vp, _i64, _vp, ctypes.c_int, _vp, _vp, _vp],
+    "tgp_envelope_block": [],
+    "tgp_potrf_env": [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp],
+    "tgp_trsm_rows_env": [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _vp],
+    "tgp_loglike_env": [_vp, _vp, _vp, _i64, _kp, _vp, _i64, _vp, ctypes.c_int, _vp, _vp, _vp, _i64, _vp],
+    "tgp_predict_var_env": [_vp, _i64, _vp, _i64, _kp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp],
     "tgp_predict_mean": [_vp, _i64, _vp, _i64, _kp, _vp, _vp, _vp],
     "tgp_predict_mean_trunc": [_vp, _i64, _vp, _i64, _kp, _vp, _vp, _vp, _vp],
     "tgp_predict_work_doubles": [_i64],

@@ -91,11 +91,83 @@ def kmat_cross(Xs, X, kdesc, out=None):
     return out
 
 
-def potrf(A, N):
-    """In-place lower Cholesky of the leading N x N block of the workspace A.  Returns info (device int32)."""
+def potrf(A, N, row_end=None):
+    """In-place lower Cholesky of the leading N x N block of the workspace A.  Returns info (device int32).
+    row_end: restrict the factorisation to that envelope (envelope_rows; tgp_potrf_env)."""
     info = torch.zeros(1, dtype=torch.int32, device=A.device)
-    check(_cabi.load().tgp_potrf(_p(A), N, A.stride(0), _p(info), _stream()), "tgp_potrf")
+    if row_end is None:
+        check(_cabi.load().tgp_potrf(_p(A), N, A.stride(0), _p(info), _stream()), "tgp_potrf")
+    else:
+        check(_cabi.load().tgp_potrf_env(_p(A), N, A.stride(0), _host_i64(row_end), len(row_end), 0, _p(info),
+                                         _stream()), "tgp_potrf_env")
     return info
+
+
+def _host_i64(a):
+    """Pointer to a host int64 array the C side reads during the call (envelopes)."""
+    if not (isinstance(a, np.ndarray) and a.dtype == np.int64 and a.flags["C_CONTIGUOUS"]):
+        raise TypeError("envelope must be a contiguous int64 numpy array")
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+# ---- envelopes: K(X, X) of points sorted along one axis is zero (below 1e-40 amp) beyond the kernel's support ----
+def envelope_block():
+    return int(_cabi.load().tgp_envelope_block())
+
+
+def envelope_rows(x_sorted, dcut, start=0):
+    """Envelope of K for the points x_sorted[start:] (ascending coordinates along the sorting axis, host array):
+    per block of envelope_block() columns the first row that is farther than `dcut` from every point of the block
+    (and of all earlier blocks).  int64 array for the *_env entry points."""
+    x = np.asarray(x_sorted, dtype=np.float64)[int(start):]
+    n, ob = len(x), envelope_block()
+    c1 = np.minimum(np.arange(ob, n + ob, ob), n)          # one past the last column of every block
+    reach = x[c1 - 1] + dcut * (1.0 + 1e-9)                 # a hair wider: the device forms fl(x_i - x_j)
+    return np.ascontiguousarray(np.maximum(np.searchsorted(x, reach, side="left"), c1), dtype=np.int64)
+
+
+def envelope_flops(row_end, n):
+    """Flop count of tgp_potrf_env for that envelope (diagonal blocks + panel solves + trailing updates)."""
+    ob = envelope_block()
+    k = np.arange(0, n, ob, dtype=np.float64)
+    w = np.minimum(ob, n - k)
+    below = np.maximum.accumulate(np.clip(np.asarray(row_end, dtype=np.float64), k + w, n)) - (k + w)
+    return float(np.sum(w ** 3 / 3.0 + w * w * below + w * below * below))
+
+
+ENVELOPE_MIN_N = 4096      # below this the dense factorisation takes a few ms at most
+ENVELOPE_MIN_GAIN = 2.0    # use the envelope when it needs at most 1/2 of the dense flops (its GEMMs are smaller)
+
+
+def plan_envelope(X, kdesc, sorted_axes=None):
+    """Decide whether K(X, X) for this kernel is worth factorising inside its envelope.  Returns None (dense), or a
+    dict: axis, dcut, order (device index tensor: points ascending along `axis`), x (their coordinates along it, host),
+    row_end, flops, flops_dense.  sorted_axes: optional cache {axis: (order, x_host)} filled / reused across calls with
+    the same X (the likelihood search evaluates many kernels on one point set)."""
+    N = int(X.shape[0])
+    if N < ENVELOPE_MIN_N:
+        return None
+    dcut = np.asarray(support_cutoffs(kdesc), dtype=np.float64)
+    if not np.all(np.isfinite(dcut)):
+        return None
+    cache = sorted_axes if sorted_axes is not None else {}
+    if "extent" not in cache:
+        lo_hi = torch.stack([X.amin(dim=0), X.amax(dim=0)]).cpu().numpy()
+        cache["extent"] = np.maximum(lo_hi[1] - lo_hi[0], 1e-300)
+    extent = cache["extent"]
+    axis = int(np.argmin(dcut / extent))
+    if dcut[axis] >= 0.7 * extent[axis]:
+        return None
+    if axis not in cache:
+        order = torch.argsort(X[:, axis], stable=True)
+        cache[axis] = (order, X[order, axis].cpu().numpy())
+    order, x = cache[axis]
+    row_end = envelope_rows(x, dcut[axis])
+    f_env, f_dense = envelope_flops(row_end, N), float(N) ** 3 / 3.0
+    if f_env * ENVELOPE_MIN_GAIN > f_dense:
+        return None
+    return {"axis": axis, "dcut": float(dcut[axis]), "order": order, "x": x, "row_end": row_end,
+            "flops": f_env, "flops_dense": f_dense}
 
 
 def potrs_vec(L, N, b):
@@ -104,9 +176,14 @@ def potrs_vec(L, N, b):
     return b
 
 
-def trsm_rows(L, N, B, M):
-    """B[:M, :N] <- B L^-T in place."""
-    check(_cabi.load().tgp_trsm_rows(_p(L), N, L.stride(0), _p(B), M, B.stride(0), _stream()), "tgp_trsm_rows")
+def trsm_rows(L, N, B, M, row_end=None):
+    """B[:M, :N] <- B L^-T in place.  row_end: the factor's envelope (envelope_rows) -- solved blocks are only
+    propagated to the rows inside it."""
+    if row_end is None:
+        check(_cabi.load().tgp_trsm_rows(_p(L), N, L.stride(0), _p(B), M, B.stride(0), _stream()), "tgp_trsm_rows")
+    else:
+        check(_cabi.load().tgp_trsm_rows_env(_p(L), N, L.stride(0), _host_i64(row_end), len(row_end), _p(B), M,
+                                             B.stride(0), _stream()), "tgp_trsm_rows_env")
     return B
 
 
@@ -124,8 +201,10 @@ def logdet_chi2(L, N, y=None, alpha=None):
     return out
 
 
-def loglike(X, y, yerr2, kdesc, work=None, want_alpha=False):
-    """One marginal-likelihood evaluation.  Returns (out[3] = logL, chi2, logdet; info; alpha; work)."""
+def loglike(X, y, yerr2, kdesc, work=None, want_alpha=False, row_end=None):
+    """One marginal-likelihood evaluation.  Returns (out[3] = logL, chi2, logdet; info; alpha; work).
+    row_end: X (with y, yerr2) is sorted along an axis and the factorisation stays inside that envelope
+    (plan_envelope; tgp_loglike_env)."""
     X = as_points(X)
     N = X.shape[0]
     if work is None:
@@ -135,8 +214,13 @@ def loglike(X, y, yerr2, kdesc, work=None, want_alpha=False):
     alpha = torch.empty(N, dtype=F64, device=X.device)
     out = torch.zeros(3, dtype=F64, device=X.device)
     info = torch.zeros(1, dtype=torch.int32, device=X.device)
-    check(_cabi.load().tgp_loglike(_p(X), _p(y), _p(yerr2), N, ctypes.byref(kdesc), _p(work), work.stride(0),
-                                   _p(alpha), int(bool(want_alpha)), _p(out), _p(info), _stream()), "tgp_loglike")
+    if row_end is None:
+        check(_cabi.load().tgp_loglike(_p(X), _p(y), _p(yerr2), N, ctypes.byref(kdesc), _p(work), work.stride(0),
+                                       _p(alpha), int(bool(want_alpha)), _p(out), _p(info), _stream()), "tgp_loglike")
+    else:
+        check(_cabi.load().tgp_loglike_env(_p(X), _p(y), _p(yerr2), N, ctypes.byref(kdesc), _p(work), work.stride(0),
+                                           _p(alpha), int(bool(want_alpha)), _p(out), _p(info), _host_i64(row_end),
+                                           len(row_end), _stream()), "tgp_loglike_env")
     return out, info, alpha, work
 
 
@@ -195,7 +279,9 @@ def knn_mean(X0, y0, Xq, k):
     return outs[0] if y0.dim() == 1 else torch.stack(outs, dim=1)
 
 
-def predict_var(Xs, X, kdesc, L, chunk=None, out=None, work=None):
+def predict_var(Xs, X, kdesc, L, chunk=None, out=None, work=None, row_end=None):
+    """Diagonal predictive variance amp - |L^-1 k*|^2 (tgp_predict_var); row_end: the factor's envelope, X in the
+    factor's (sorted) order (tgp_predict_var_env)."""
     Xs, X = as_points(Xs), as_points(X)
     _check_dims(kdesc, X, Xs)
     M, N = Xs.shape[0], X.shape[0]
@@ -207,8 +293,13 @@ def predict_var(Xs, X, kdesc, L, chunk=None, out=None, work=None):
         work = torch.empty(chunk * (N + 1), dtype=F64, device=X.device)
     if out is None:
         out = torch.empty(M, dtype=F64, device=X.device)
-    check(_cabi.load().tgp_predict_var(_p(Xs), M, _p(X), N, ctypes.byref(kdesc), _p(L), L.stride(0), _p(work),
-                                       chunk, _p(out), _stream()), "tgp_predict_var")
+    if row_end is None:
+        check(_cabi.load().tgp_predict_var(_p(Xs), M, _p(X), N, ctypes.byref(kdesc), _p(L), L.stride(0), _p(work),
+                                           chunk, _p(out), _stream()), "tgp_predict_var")
+    else:
+        check(_cabi.load().tgp_predict_var_env(_p(Xs), M, _p(X), N, ctypes.byref(kdesc), _p(L), L.stride(0),
+                                               _host_i64(row_end), len(row_end), _p(work), chunk, _p(out), _stream()),
+              "tgp_predict_var_env")
     return out
 
 
@@ -220,12 +311,25 @@ def var_chunk(N, M):
 
 def support_cutoffs(kdesc):
     """Per axis, the coordinate difference beyond which the kernel is below 1e-40 of its amplitude whatever the
-    other coordinate: q = d^T M d >= d_a^2 / (M^-1)_aa, and f(q) <= 1e-40 for q >= tgp_profile_qcut(family)."""
+    other coordinate: q = d^T M d >= d_a^2 / (M^-1)_aa, and f(q) <= 1e-40 for q >= tgp_profile_qcut(family).
+    NaN / inf for a metric that is not positive definite (callers then keep the dense path)."""
     qcut = float(_cabi.load().tgp_profile_qcut(int(kdesc.family)))
-    if kdesc.ndim == 1:
-        return [np.sqrt(qcut / kdesc.m00)]
-    det = kdesc.m00 * kdesc.m11 - kdesc.m01 * kdesc.m01
-    return [np.sqrt(qcut * kdesc.m11 / det), np.sqrt(qcut * kdesc.m00 / det)]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        if kdesc.ndim == 1:
+            return [float(np.sqrt(np.float64(qcut) / kdesc.m00))]
+        det = np.float64(kdesc.m00 * kdesc.m11 - kdesc.m01 * kdesc.m01)
+        if not det > 0:
+            return [float("nan"), float("nan")]
+        return [float(np.sqrt(qcut * kdesc.m11 / det)), float(np.sqrt(qcut * kdesc.m00 / det))]
+
+
+def envelope_trsm_flops(row_end, n):
+    """Flops per right-hand side of tgp_trsm_rows_env for that envelope."""
+    ob = envelope_block()
+    k = np.arange(0, n, ob, dtype=np.float64)
+    w = np.minimum(ob, n - k)
+    below = np.maximum.accumulate(np.clip(np.asarray(row_end, dtype=np.float64), k + w, n)) - (k + w)
+    return float(np.sum(w * w + 2.0 * w * below))
 
 
 def plan_var_windows(x_train_sorted, a, b, dcut, chunk_sizes, align=64):
@@ -285,11 +389,22 @@ def predict_var_windowed(Xs, X, kdesc, yerr2, chunk=None, min_gain=1.25, stats=N
     xt = X[order_t, axis].cpu().numpy()
     skip_asc, skip_desc, use_desc, f_win, f_full = plan_var_windows(xt, a, b, dcut[axis], sizes)
     need_asc, need_desc = bool(np.any(~use_desc)), bool(np.any(use_desc))
-    f_factor = (need_asc + need_desc) * float(N) ** 3 / 3.0
+    # the two factors are Cholesky factors of matrices sorted along the axis: they live inside an envelope
+    # (tgp_potrf_env), and so does the forward substitution of every window (tgp_predict_var_env)
+    coords = {False: xt, True: np.ascontiguousarray(-xt[::-1])}
+    env_full = envelope_rows(xt, dcut[axis])
+    use_env = N >= ENVELOPE_MIN_N and envelope_flops(env_full, N) * ENVELOPE_MIN_GAIN <= float(N) ** 3 / 3.0
+    f_factor = (need_asc + need_desc) * (envelope_flops(env_full, N) if use_env else float(N) ** 3 / 3.0)
+    envs = None
+    if use_env:
+        envs = [envelope_rows(coords[bool(use_desc[c])], dcut[axis], start=int(skip_desc[c] if use_desc[c] else skip_asc[c]))
+                for c in range(len(a))]
+        f_win = float(sum(sizes[c] * envelope_trsm_flops(envs[c], N - int(skip_desc[c] if use_desc[c] else skip_asc[c]))
+                          for c in range(len(a))))
     if stats is not None:
         stats.update({"axis": axis, "dcut": float(dcut[axis]), "extent": float(extent[axis]), "chunks": int(len(a)),
                       "flops_windowed": f_win, "flops_full": f_full, "flops_factors": f_factor,
-                      "chunks_descending": int(np.sum(use_desc)), "used": False})
+                      "chunks_descending": int(np.sum(use_desc)), "envelope": bool(use_env), "used": False})
     if (f_win + f_factor) * min_gain > f_full:
         return None
     ld = even(N)
@@ -304,7 +419,7 @@ def predict_var_windowed(Xs, X, kdesc, yerr2, chunk=None, min_gain=1.25, stats=N
         Xo = Xa.flip(0).contiguous() if desc_order else Xa
         eo = None if e2 is None else (e2.flip(0).contiguous() if desc_order else e2)
         L = kmat_sym(Xo, kdesc, eo, lower_only=True)
-        info = int(potrf(L, N).item())
+        info = int(potrf(L, N, row_end=envelope_rows(coords[desc_order], dcut[axis]) if use_env else None).item())
         if info < 0:
             raise _cabi.TgpError("tgp_potrf: internal synchronisation timed out (info = %d)" % info)
         if info != 0:
@@ -318,7 +433,8 @@ def predict_var_windowed(Xs, X, kdesc, yerr2, chunk=None, min_gain=1.25, stats=N
         d = bool(use_desc[c])
         s = int(skip_desc[c] if d else skip_asc[c])
         Xo, L = factors[d]
-        predict_var(Xss[c0:c1], Xo[s:], kdesc, L[s:, s:], chunk=chunk, out=out_sorted[c0:c1], work=work)
+        predict_var(Xss[c0:c1], Xo[s:], kdesc, L[s:, s:], chunk=chunk, out=out_sorted[c0:c1], work=work,
+                    row_end=None if envs is None else envs[c])
     var = torch.empty(M, dtype=F64, device=X.device)
     var[order_s] = out_sorted
     if stats is not None:

@@ -1051,6 +1051,108 @@ extern "C" int tgp_potrf_rows(double* A, int64_t N, int64_t ld, int64_t nrows, i
   return potrf_with_rows(A, N, ld, nrows, info, (cudaStream_t)stream);
 }
 
+// --------------------------------------------------------------------------------------------
+// Envelope (variable-band) Cholesky.  With the points sorted along one axis, a kernel that is below 1e-40 of its
+// amplitude beyond a coordinate difference d_cut gives a matrix whose row i starts (to 1e-40) at the first point
+// within d_cut of point i; a Cholesky factor keeps the envelope of its matrix.  Per OB-wide block column b the caller
+// states row_end[b]: the rows [row_end[b], N) of that block column are (numerically) zero in K and therefore in L, so
+// the panel solve and the trailing update stop there: N bw^2 flop instead of N^3 / 3 for a band of bw rows.  Rows
+// outside the envelope are neither read nor written (they keep whatever the K build left there: entries below
+// 1e-40 amp).  `extra` right-hand-side rows below the matrix are carried through as in potrf_rec.
+// --------------------------------------------------------------------------------------------
+static int potrf_envelope(double* A, int64_t n, int64_t ld, const int64_t* row_end, int32_t* info, cudaStream_t st,
+                          int64_t extra) {
+  int64_t prev_end = 0;
+  for (int64_t k = 0, b = 0; k < n; k += OB, ++b) {
+    const int64_t w = (n - k < OB) ? (n - k) : OB;
+    const int64_t c1 = k + w;
+    int64_t re = row_end[b];
+    if (re < prev_end) re = prev_end;   // an envelope never shrinks from one block column to the next
+    if (re < c1) re = c1;
+    if (re > n) re = n;
+    prev_end = re;
+    const int64_t below = re - c1;
+    double* Akk = A + k * ld + k;
+    double* Ark = A + c1 * ld + k;      // the rows of this block column inside the envelope
+    double* Aek = A + n * ld + k;       // the extra rows
+    int rc;
+    if (g_fused_panel) {
+      rc = panel_factor(Akk, w, ld, below, info, k, st);
+      if (rc) return rc;
+    } else {
+      rc = potrf_rec(Akk, w, ld, NB, info, k, st);
+      if (rc) return rc;
+      if (below > 0) {
+        rc = trsm_rows_rec(Akk, w, ld, Ark, below, ld, NB, st);
+        if (rc) return rc;
+      }
+    }
+    if (extra > 0) {
+      rc = trsm_rows_rec(Akk, w, ld, Aek, extra, ld, NB, st);
+      if (rc) return rc;
+    }
+    if (below > 0) {
+      rc = gemm_nt_sub_launch(A + c1 * ld + c1, below, below, ld, Ark, ld, Ark, ld, w, 1, st);
+      if (rc) return rc;
+      if (extra > 0) {
+        rc = gemm_nt_sub_launch(A + n * ld + c1, extra, below, ld, Aek, ld, Ark, ld, w, 0, st);
+        if (rc) return rc;
+      }
+    }
+  }
+  return TGP_OK;
+}
+
+static int check_envelope(const int64_t* row_end, int64_t nblocks, int64_t N) {
+  return row_end == nullptr || nblocks != tgp_cdiv(N, (int64_t)OB);
+}
+
+extern "C" int tgp_envelope_block(void) { return OB; }
+
+extern "C" int tgp_potrf_env(double* A, int64_t N, int64_t ld, const int64_t* row_end, int64_t nblocks,
+                             int64_t nrows, int32_t* info, void* stream) {
+  TGP_CHECK_ARG(!check_mat(A, N, ld), "A must be 16-byte aligned with even ld >= N");
+  TGP_CHECK_ARG(info != nullptr && nrows >= 0, "info/nrows");
+  TGP_CHECK_ARG(!check_envelope(row_end, nblocks, N), "row_end must hold one entry per tgp_envelope_block() columns");
+  cudaStream_t st = (cudaStream_t)stream;
+  TGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
+  if (N == 0) return TGP_OK;
+  return potrf_envelope(A, N, ld, row_end, info, st, nrows);
+}
+
+// B <- B L^-T for a factor with the envelope row_end: after the block of unknowns [k, c1) is solved it only enters
+// the unknowns [c1, row_end[b]) -- 2 M N bw flop instead of M N^2.
+static int trsm_rows_envelope(const double* L, int64_t n, int64_t ld, const int64_t* row_end, double* B, int64_t M,
+                              int64_t ldb, cudaStream_t st) {
+  int64_t prev_end = 0;
+  for (int64_t k = 0, b = 0; k < n; k += OB, ++b) {
+    const int64_t w = (n - k < OB) ? (n - k) : OB;
+    const int64_t c1 = k + w;
+    int64_t re = row_end[b];
+    if (re < prev_end) re = prev_end;
+    if (re < c1) re = c1;
+    if (re > n) re = n;
+    prev_end = re;
+    int rc = trsm_rows_rec(L + k * ld + k, w, ld, B + k, M, ldb, NB, st);
+    if (rc) return rc;
+    if (re > c1) {
+      rc = gemm_nt_sub_launch(B + c1, M, re - c1, ldb, B + k, ldb, L + c1 * ld + k, ld, w, 0, st);
+      if (rc) return rc;
+    }
+  }
+  return TGP_OK;
+}
+
+extern "C" int tgp_trsm_rows_env(const double* L, int64_t N, int64_t ld, const int64_t* row_end, int64_t nblocks,
+                                 double* B, int64_t M, int64_t ldb, void* stream) {
+  TGP_CHECK_ARG(!check_mat(L, N, ld), "L must be 16-byte aligned with even ld >= N");
+  TGP_CHECK_ARG(M >= 0 && ldb >= N, "M/ldb");
+  TGP_CHECK_ARG(!check_envelope(row_end, nblocks, N), "row_end must hold one entry per tgp_envelope_block() columns");
+  if (M == 0 || N == 0) return TGP_OK;
+  TGP_CHECK_ARG(B && (ldb % 2 == 0) && ((uintptr_t)B % 16 == 0), "B must be 16-byte aligned with even ldb");
+  return trsm_rows_envelope(L, N, ld, row_end, B, M, ldb, (cudaStream_t)stream);
+}
+
 extern "C" int tgp_trsm_rows(const double* L, int64_t N, int64_t ld, double* B, int64_t M, int64_t ldb,
                              void* stream) {
   TGP_CHECK_ARG(!check_mat(L, N, ld), "L must be 16-byte aligned with even ld >= N");
@@ -1161,24 +1263,38 @@ sumsq_kernel(const double* __restrict__ w, int64_t N, double* __restrict__ out1)
   }
 }
 
-extern "C" int tgp_loglike(const double* X, const double* y, const double* yerr2, int64_t N,
-                           const tgp_kernel* k, double* work, int64_t ld, double* alpha, int want_alpha,
-                           double* out, int32_t* info, void* stream) {
+static int loglike_impl(const double* X, const double* y, const double* yerr2, int64_t N,
+                        const tgp_kernel* k, double* work, int64_t ld, double* alpha, int want_alpha,
+                        double* out, int32_t* info, const int64_t* row_end, int64_t nblocks, void* stream) {
   TGP_CHECK_ARG(N > 0 && X && y && work && alpha && out && info, "null pointer / N");
+  TGP_CHECK_ARG(row_end == nullptr || !check_envelope(row_end, nblocks, N),
+                "row_end must hold one entry per tgp_envelope_block() columns");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = tgp_kmat_sym(X, N, k, yerr2, work, ld, /*lower_only=*/1, stream);
   if (rc) return rc;
-  // y rides along as row N of the workspace: the factorisation's panel solves turn it into w = L^-1 y
-  double* wrow = work + N * ld;
-  TGP_CUDA(cudaMemcpyAsync(wrow, y, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
-  rc = tgp_potrf_rows(work, N, ld, 1, info, stream);
-  if (rc) return rc;
-  TGP_CUDA(cudaMemcpyAsync(alpha, wrow, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
   // out[1], out[2] double as scratch {logdet, chi2} until the finishing kernel reorders them
   double* tmp = out + 1;
-  if (want_alpha) {
-    rc = trsv_backward(work, N, ld, alpha, st);   // alpha = L^-T w
+  if (row_end) {
+    // Envelope: a row riding through the factorisation would cost two more (one-row) launches chains per block column;
+    // the persistent sweep kernels read the factor once instead (w = L^-1 y, and alpha = L^-T w in the same call).
+    rc = tgp_potrf_env(work, N, ld, row_end, nblocks, 0, info, stream);
     if (rc) return rc;
+    TGP_CUDA(cudaMemcpyAsync(alpha, y, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    rc = tgp_trsv_sweeps(work, N, ld, alpha, want_alpha ? 3 : 1, st);
+    if (rc) return rc;
+  } else {
+    // y rides along as row N of the workspace: the factorisation's panel solves turn it into w = L^-1 y
+    double* wrow = work + N * ld;
+    TGP_CUDA(cudaMemcpyAsync(wrow, y, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    rc = tgp_potrf_rows(work, N, ld, 1, info, stream);
+    if (rc) return rc;
+    TGP_CUDA(cudaMemcpyAsync(alpha, wrow, N * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (want_alpha) {
+      rc = trsv_backward(work, N, ld, alpha, st);   // alpha = L^-T w
+      if (rc) return rc;
+    }
+  }
+  if (want_alpha) {
     logdet_chi2_kernel<<<1, 1024, 0, st>>>(work, N, ld, y, alpha, tmp);  // chi2 = y . alpha
     TGP_LAUNCH_CHECK();
   } else {
@@ -1191,4 +1307,17 @@ extern "C" int tgp_loglike(const double* X, const double* y, const double* yerr2
   loglike_finish_kernel<<<1, 1, 0, st>>>(tmp, N, info, out);
   TGP_LAUNCH_CHECK();
   return TGP_OK;
+}
+
+extern "C" int tgp_loglike(const double* X, const double* y, const double* yerr2, int64_t N,
+                           const tgp_kernel* k, double* work, int64_t ld, double* alpha, int want_alpha,
+                           double* out, int32_t* info, void* stream) {
+  return loglike_impl(X, y, yerr2, N, k, work, ld, alpha, want_alpha, out, info, nullptr, 0, stream);
+}
+
+extern "C" int tgp_loglike_env(const double* X, const double* y, const double* yerr2, int64_t N,
+                               const tgp_kernel* k, double* work, int64_t ld, double* alpha, int want_alpha,
+                               double* out, int32_t* info, const int64_t* row_end, int64_t nblocks, void* stream) {
+  TGP_CHECK_ARG(row_end != nullptr, "row_end");
+  return loglike_impl(X, y, yerr2, N, k, work, ld, alpha, want_alpha, out, info, row_end, nblocks, stream);
 }

@@ -274,9 +274,9 @@ var_from_rows_kernel(const double* __restrict__ V, int64_t M, int64_t N, int64_t
   if (lane == 0) var[m] = amp - s;
 }
 
-extern "C" int tgp_predict_var(const double* Xs, int64_t M, const double* X, int64_t N,
-                               const tgp_kernel* k, const double* L, int64_t ld, double* work,
-                               int64_t chunk, double* var, void* stream) {
+static int predict_var_impl(const double* Xs, int64_t M, const double* X, int64_t N,
+                            const tgp_kernel* k, const double* L, int64_t ld, const int64_t* row_end,
+                            int64_t nblocks, double* work, int64_t chunk, double* var, void* stream) {
   TGP_CHECK_ARG(kdesc_ok(k), "kernel descriptor");
   TGP_CHECK_ARG(M >= 0 && N > 0 && ld >= N && chunk > 0, "shape");
   if (M == 0) return TGP_OK;
@@ -287,13 +287,29 @@ extern "C" int tgp_predict_var(const double* Xs, int64_t M, const double* X, int
     const int64_t mc = (M - m0 < chunk) ? (M - m0) : chunk;
     int rc = tgp_kmat_cross(Xs + m0 * k->ndim, mc, X, N, k, work, ldw, stream);
     if (rc) return rc;
-    rc = tgp_trsm_rows(L, N, ld, work, mc, ldw, stream);
+    rc = row_end ? tgp_trsm_rows_env(L, N, ld, row_end, nblocks, work, mc, ldw, stream)
+                 : tgp_trsm_rows(L, N, ld, work, mc, ldw, stream);
     if (rc) return rc;
     var_from_rows_kernel<<<(unsigned)tgp_cdiv(mc, 8), 256, 0, (cudaStream_t)stream>>>(work, mc, N, ldw, k->amp,
                                                                                       var + m0);
     TGP_LAUNCH_CHECK();
   }
   return TGP_OK;
+}
+
+extern "C" int tgp_predict_var(const double* Xs, int64_t M, const double* X, int64_t N,
+                               const tgp_kernel* k, const double* L, int64_t ld, double* work,
+                               int64_t chunk, double* var, void* stream) {
+  return predict_var_impl(Xs, M, X, N, k, L, ld, nullptr, 0, work, chunk, var, stream);
+}
+
+// The same with a factor whose envelope is known (tgp_potrf_env): the multi-right-hand-side forward substitution
+// only propagates every solved block of unknowns to the rows inside the envelope.
+extern "C" int tgp_predict_var_env(const double* Xs, int64_t M, const double* X, int64_t N,
+                                   const tgp_kernel* k, const double* L, int64_t ld, const int64_t* row_end,
+                                   int64_t nblocks, double* work, int64_t chunk, double* var, void* stream) {
+  TGP_CHECK_ARG(row_end != nullptr, "row_end");
+  return predict_var_impl(Xs, M, X, N, k, L, ld, row_end, nblocks, work, chunk, var, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

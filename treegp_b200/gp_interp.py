@@ -125,6 +125,11 @@ class GPInterpolation(object):
             return y_interp, y_cov
         return y_interp
 
+    # K + diag(y_err^2) is factorised inside its envelope when the kernel's support is short against the field
+    # (backend.plan_envelope); False: always the dense factorisation
+    BANDED_SOLVE = True
+    _envelope = None
+
     # predict_var: solve only the trailing sub-system that a chunk of neighbouring test points can be correlated with
     # (backend.predict_var_windowed) whenever that is cheaper than the plain solves on the cached factor
     WINDOWED_VARIANCE = True
@@ -140,10 +145,10 @@ class GPInterpolation(object):
         mean = backend.predict_mean(Xs, Xd, desc, self._alpha_dev)
         var, self._var_plan = None, {}
         if self.WINDOWED_VARIANCE:
-            e2 = backend.to_device(np.asarray(self._y_err, dtype=np.float64).reshape(-1) ** 2)
-            var = backend.predict_var_windowed(Xs, Xd, desc, e2, chunk=self.VAR_CHUNK, stats=self._var_plan)
+            var = backend.predict_var_windowed(Xs, Xd, desc, self._e2_dev, chunk=self.VAR_CHUNK, stats=self._var_plan)
         if var is None:
-            var = backend.predict_var(Xs, Xd, desc, ws, chunk=self.VAR_CHUNK)
+            var = backend.predict_var(Xs, Xd, desc, ws, chunk=self.VAR_CHUNK,
+                                      row_end=None if self._envelope is None else self._envelope["row_end"])
         y = mean.cpu().numpy() + self._mean + self._build_average_meanify(X)
         return y, var.cpu().numpy()
 
@@ -155,10 +160,17 @@ class GPInterpolation(object):
         n = Xd.shape[0]
         desc = lower_kernel(kernel, Xd.shape[1])
         e2 = backend.to_device(np.asarray(y_err, dtype=np.float64).reshape(-1) ** 2)
+        yd = backend.to_device(np.asarray(y, dtype=np.float64).reshape(-1))
+        # A kernel whose support is short against the field: with the points sorted along one axis K is zero (below
+        # 1e-40 amp) outside an envelope that its Cholesky factor keeps -- factorise inside it (N bw^2 flop instead of
+        # N^3 / 3).  The factor, X and alpha are then held in the sorted order; `_alpha` (host) in the caller's.
+        env = backend.plan_envelope(Xd, desc) if self.BANDED_SOLVE else None
+        if env is not None:
+            Xd, yd, e2 = Xd[env["order"]].contiguous(), yd[env["order"]].contiguous(), e2[env["order"]].contiguous()
         # one call: K (lower) -> L with y riding through the factorisation as an extra row (forward substitution
         # for free), then the backward sweep (tgp_loglike, want_alpha)
-        yd = backend.to_device(np.asarray(y, dtype=np.float64).reshape(-1))
-        _, info, alpha, ws = backend.loglike(Xd, yd, e2, desc, want_alpha=True)
+        _, info, alpha, ws = backend.loglike(Xd, yd, e2, desc, want_alpha=True,
+                                             row_end=None if env is None else env["row_end"])
         bad = int(info.item())
         if bad < 0:
             raise _cabi.TgpError("tgp_loglike: internal synchronisation timed out (info = %d)" % bad)
@@ -166,8 +178,15 @@ class GPInterpolation(object):
             # scipy.linalg.cholesky raises LinAlgError here (gp_interp.py:181)
             raise np.linalg.LinAlgError("%d-th leading minor of the array is not positive definite" % bad)
         self._factor = (Xd, desc, ws)
+        self._e2_dev = e2        # y_err^2 in the order of Xd
+        self._envelope = env
         self._alpha_dev = alpha
-        self._alpha = alpha.cpu().numpy()
+        if env is None:
+            self._alpha = alpha.cpu().numpy()
+        else:
+            a = alpha.new_empty(alpha.shape)
+            a[env["order"]] = alpha
+            self._alpha = a.cpu().numpy()
 
     def return_gp_predict(self, y, X1, X2, kernel, y_err, return_cov=False):
         """GP algebra for residuals y at X1 with errors y_err, evaluated at X2 with `kernel`
@@ -182,7 +201,7 @@ class GPInterpolation(object):
             return y_predict, None
         # y_cov = K** - K* (K + s^2 I)^-1 K*^T = K** - V V^T,  V = K* L^-T  (gp_interp.py:187-191)
         V = backend.kmat_cross(Xs, Xd, desc)
-        backend.trsm_rows(ws, n, V, m)
+        backend.trsm_rows(ws, n, V, m, row_end=None if self._envelope is None else self._envelope["row_end"])
         cov = backend.kmat_sym(Xs, desc)
         backend.gemm_nt_sub(cov, m, m, V, V, n)
         return y_predict, cov[:, :m].cpu().numpy()
