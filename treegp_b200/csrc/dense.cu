@@ -164,6 +164,7 @@ gemm_nt_sub_kernel(double* __restrict__ C, int64_t M, int64_t Nc, int64_t ldc,
 static int g_lookahead = 1;  // 0 disables the two-stream look-ahead Cholesky driver
 static int g_ob_large = 0;   // outer block of the look-ahead driver: 0 = automatic, else a multiple of 512 (option "potrf_ob")
 static int g_fused_panel = 1;   // option "potrf_fused": 0 = the potf2 / trsm_panel / gemm chain per 64 columns
+static int g_env_lookahead = 1;   // option "potrf_env_lookahead": 0 = the sequential envelope driver
 static int g_gemm_config = -1;  // -1: pick by shape; 0: 128x128; 1: 128x64 (tgp_set_option for experiments)
 
 template <int BN_, int WARPS_M, int WARPS_N, int MIN_CTAS>
@@ -206,6 +207,7 @@ extern "C" int tgp_set_option(const char* name, int value) {
   if (name && !strcmp(name, "gemm_config")) { g_gemm_config = value; return TGP_OK; }
   if (name && !strcmp(name, "potrf_lookahead")) { g_lookahead = value; return TGP_OK; }
   if (name && !strcmp(name, "potrf_fused")) { g_fused_panel = value; return TGP_OK; }
+  if (name && !strcmp(name, "potrf_env_lookahead")) { g_env_lookahead = value; return TGP_OK; }
   if (name && !strcmp(name, "pairbin_block_sums")) return tgp_pairbin_set_block_sums(value);
   if (name && !strcmp(name, "pairbin_fast_paths")) return tgp_pairbin_set_fast_paths(value);
   if (name && !strcmp(name, "bootbin_paths")) return tgp_bootbin_set_paths(value);
@@ -1103,6 +1105,70 @@ static int potrf_envelope(double* A, int64_t n, int64_t ld, const int64_t* row_e
   return TGP_OK;
 }
 
+// The same factorisation on two streams, as potrf_lookahead does for the dense matrix: the panel of block column b+1
+// (a chain of 8 latency-bound launches) runs on the high-priority stream P while the caller's stream U still applies
+// block column b's update to everything right of that panel.
+//   P: panel(b) .. wait U2(b-1) .. U1(b) = update of the next panel's columns (rows inside the envelope) .. panel(b+1)
+//   U: wait panel(b) .. U2(b) = update of the columns right of the next panel
+// U1(b) and U2(b) write disjoint column ranges; U1(b+1) is ordered after U2(b) (both touch the columns right of panel
+// b+2's left edge).  No extra right-hand-side rows here (tgp_loglike_env uses the sweeps).
+static int potrf_envelope_lookahead(double* A, int64_t n, int64_t ld, const int64_t* row_end, int32_t* info,
+                                    cudaStream_t U) {
+  LookaheadCtx* Lp = lookahead_ctx();
+  if (!Lp) {
+    tgp_set_error("potrf_env: could not create the look-ahead stream: %s", cudaGetErrorString(cudaGetLastError()));
+    return TGP_ERR_CUDA;
+  }
+  LookaheadCtx& L = *Lp;
+  cudaStream_t P = L.panel;
+  const int64_t nblk = tgp_cdiv(n, (int64_t)OB);
+  if (!L.ensure((size_t)(4 + 2 * nblk))) {
+    tgp_set_error("potrf_env: cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return TGP_ERR_CUDA;
+  }
+  TGP_CUDA(cudaEventRecord(L.get(0), U));
+  TGP_CUDA(cudaStreamWaitEvent(P, L.get(0), 0));
+  int64_t prev_end = 0;
+  // event slots: 1 + 2 b = panel(b) done (on P), 2 + 2 b = U2(b) done (on U)
+  for (int64_t b = 0; b < nblk; ++b) {
+    const int64_t k = b * OB;
+    const int64_t w = (n - k < OB) ? (n - k) : OB;
+    const int64_t c1 = k + w;
+    int64_t re = row_end[b];
+    if (re < prev_end) re = prev_end;
+    if (re < c1) re = c1;
+    if (re > n) re = n;
+    prev_end = re;
+    const int64_t below = re - c1;
+    double* Akk = A + k * ld + k;
+    double* Ark = A + c1 * ld + k;
+    int rc = panel_factor(Akk, w, ld, below, info, k, P);
+    if (rc) return rc;
+    cudaEvent_t e_panel = L.get(1 + 2 * b);
+    TGP_CUDA(cudaEventRecord(e_panel, P));
+    TGP_CUDA(cudaStreamWaitEvent(U, e_panel, 0));
+    // everything the next panel reads must be final: the U2 updates up to block b-1 (stream order on U covers the
+    // earlier ones)
+    if (b >= 1) TGP_CUDA(cudaStreamWaitEvent(P, L.get(2 + 2 * (b - 1)), 0));
+    if (below > 0) {
+      const int64_t w2 = (below < OB) ? below : OB;
+      rc = gemm_nt_sub_launch(A + c1 * ld + c1, below, w2, ld, Ark, ld, Ark, ld, w, 1, P);            // U1(b)
+      if (rc) return rc;
+      const int64_t rest2 = below - w2;
+      if (rest2 > 0) {
+        rc = gemm_nt_sub_launch(A + (c1 + w2) * ld + (c1 + w2), rest2, rest2, ld, Ark + w2 * ld, ld, Ark + w2 * ld,
+                                ld, w, 1, U);                                                         // U2(b)
+        if (rc) return rc;
+      }
+    }
+    TGP_CUDA(cudaEventRecord(L.get(2 + 2 * b), U));
+  }
+  // join: the caller's stream continues after the last panel-stream work
+  TGP_CUDA(cudaEventRecord(L.get(3 + 2 * nblk), P));
+  TGP_CUDA(cudaStreamWaitEvent(U, L.get(3 + 2 * nblk), 0));
+  return TGP_OK;
+}
+
 static int check_envelope(const int64_t* row_end, int64_t nblocks, int64_t N) {
   return row_end == nullptr || nblocks != tgp_cdiv(N, (int64_t)OB);
 }
@@ -1117,6 +1183,8 @@ extern "C" int tgp_potrf_env(double* A, int64_t N, int64_t ld, const int64_t* ro
   cudaStream_t st = (cudaStream_t)stream;
   TGP_CUDA(cudaMemsetAsync(info, 0, sizeof(int32_t), st));
   if (N == 0) return TGP_OK;
+  if (g_env_lookahead && g_fused_panel && nrows == 0 && N >= 3 * OB)
+    return potrf_envelope_lookahead(A, N, ld, row_end, info, st);
   return potrf_envelope(A, N, ld, row_end, info, st, nrows);
 }
 
