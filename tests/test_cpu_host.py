@@ -450,3 +450,68 @@ def test_variance_window_plan_only_skips_uncorrelated_points(ndim):
                 assert q.min() >= qcut
         left += sizes[c] * float(n - (sd[c] if use_desc[c] else sa[c])) ** 2
     assert f_win == left and f_full == float(m) * n * n
+
+
+# ---- envelope factorisation: host-side plan ---------------------------------------------------------------
+@pytest.mark.parametrize("n,dcut", [(5000, 7.0), (1537, 0.5), (4096, 1000.0), (700, 3.0)])
+def test_envelope_rows_bound_every_correlated_pair(n, dcut):
+    """backend.envelope_rows / envelope_flops / envelope_trsm_flops (pure host logic behind tgp_potrf_env): a row at or
+    beyond row_end[b] is at least d_cut away from EVERY column of block b and of all earlier blocks (so K is below
+    1e-40 amp there and the factor stays zero), the bound is tight to one row, ends are non-decreasing and reach N,
+    sub-systems (start > 0) get the same envelope shifted, and the flop counts are the sums they claim to be."""
+    from treegp_b200 import backend
+
+    ob = backend.envelope_block()
+    assert ob == 512
+    rng = np.random.default_rng(n)
+    x = np.sort(np.concatenate([rng.uniform(0, 100, n - n // 5), rng.normal(50, 2, n // 5)]))   # with a dense clump
+    re = backend.envelope_rows(x, dcut)
+    nb = (n + ob - 1) // ob
+    assert re.dtype == np.int64 and len(re) == nb and re[-1] == n and np.all(np.diff(re) >= 0)
+    for b in range(nb):
+        c1 = min(n, (b + 1) * ob)
+        assert c1 <= re[b] <= n
+        if re[b] < n:
+            assert x[re[b]] - x[c1 - 1] >= dcut           # first row outside: far from the block's last column ...
+            assert np.all(x[re[b]:] - x[c1 - 1] >= dcut)  # ... and so is every later row, from every earlier column
+        if re[b] > c1:
+            assert x[re[b] - 1] - x[c1 - 1] < dcut * (1 + 2e-9)   # tight: the last row inside is within reach
+    # a trailing sub-system has the same envelope, shifted
+    s = 192
+    if n > s + ob:
+        re_s = backend.envelope_rows(x, dcut, start=s)
+        np.testing.assert_array_equal(re_s, backend.envelope_rows(x[s:], dcut))
+    # flop counts
+    k = np.arange(0, n, ob)
+    w = np.minimum(ob, n - k)
+    below = re - (k + w)
+    assert backend.envelope_flops(re, n) == pytest.approx(float(np.sum(w ** 3 / 3 + w * w * below + w * below * below)))
+    assert backend.envelope_trsm_flops(re, n) == pytest.approx(float(np.sum(w * w + 2 * w * below)))
+    if dcut >= 1000.0:   # support wider than the data: the envelope is the whole triangle
+        assert np.all(re == n)
+        assert backend.envelope_flops(re, n) == pytest.approx(n ** 3 / 3, rel=0.3)
+
+
+def test_plan_envelope_declines_small_and_wide_problems():
+    """backend.plan_envelope returns None before touching the device for N < ENVELOPE_MIN_N (the reference's tests and
+    the golden vectors never take the envelope path)."""
+    import torch
+    from treegp_b200 import backend, eval_kernel
+    from treegp_b200.kernels import lower_kernel
+
+    desc = lower_kernel(eval_kernel("1.0 * AnisotropicRBF(invLam=array([[400.0, 0.0], [0.0, 400.0]]))"), 2)
+    X = torch.rand((backend.ENVELOPE_MIN_N - 1, 2), dtype=torch.float64)
+    assert backend.plan_envelope(X, desc) is None
+    # wide support: declined from the cut-offs alone (CPU tensors are enough for the extent)
+    wide = lower_kernel(eval_kernel("1.0 * AnisotropicRBF(invLam=array([[0.5, 0.0], [0.0, 0.5]]))"), 2)
+    assert backend.plan_envelope(torch.rand((5000, 2), dtype=torch.float64) * 10.0, wide) is None
+    # a metric that is not positive definite has no cut-off: dense path
+    bad = lower_kernel(eval_kernel("1.0 * AnisotropicRBF(invLam=array([[1.0, 0.0], [0.0, 1.0]]))"), 2)
+    bad.m01 = 5.0
+    assert not np.all(np.isfinite(backend.support_cutoffs(bad)))
+    assert backend.plan_envelope(torch.rand((5000, 2), dtype=torch.float64) * 100.0, bad) is None
+    # and a short support on CPU tensors gives a plan (host logic only: sort, searchsorted, flop model)
+    narrow = lower_kernel(eval_kernel("1.0 * AnisotropicRBF(invLam=array([[4.0, 0.0], [0.0, 1.0]]))"), 2)
+    plan = backend.plan_envelope(torch.rand((6000, 2), dtype=torch.float64) * 300.0, narrow)
+    assert plan is not None and plan["axis"] == 0 and plan["flops"] * 2 <= plan["flops_dense"]
+    assert np.all(np.diff(plan["x"]) >= 0) and len(plan["row_end"]) == 12
