@@ -70,3 +70,34 @@ def test_gp_solve_full_size_satisfies_its_defining_equation(gpu_ready):
     np.testing.assert_allclose(float(out_b[0].item()), float(out_a[0].item()), rtol=1e-12)
     np.testing.assert_allclose(float(out_b[1].item()), float(out_a[1].item()), rtol=1e-9)   # chi2 two ways
     np.testing.assert_allclose(float(out_b[2].item()), float(out_a[2].item()), rtol=0, atol=0)  # same factor
+
+
+def test_envelope_solve_full_size_satisfies_its_defining_equation(gpu_ready):
+    """configs[2] through the envelope factorisation (tgp_loglike_env, what GPInterpolation runs at this size): the
+    solve satisfies (K + diag(s^2)) alpha = y with K applied by the fused predict kernel, and logL / chi2 / log-det
+    equal the dense evaluation of the same sorted system."""
+    from treegp_b200 import backend, eval_kernel
+    from treegp_b200.kernels import lower_kernel
+
+    n = 40_000
+    rng = np.random.default_rng(7)
+    Lf = 160.0
+    X = backend.as_points(rng.uniform(-Lf / 2, Lf / 2, size=(n, 2)))
+    y = backend.to_device(rng.normal(size=n))
+    noise2 = backend.to_device(rng.uniform(0.03, 0.07, size=n) ** 2)
+    desc = lower_kernel(eval_kernel("4.0 * AnisotropicVonKarman(invLam=array([[0.46, -0.09], [-0.09, 0.55]]))"), 2)
+    plan = backend.plan_envelope(X, desc)
+    assert plan is not None and plan["flops"] * 10 < plan["flops_dense"]
+    o = plan["order"]
+    Xs, ys, es = X[o].contiguous(), y[o].contiguous(), noise2[o].contiguous()
+    work = backend.alloc_matrix(n + 1, n)
+    out_e, info_e, alpha, _ = backend.loglike(Xs, ys, es, desc, work=work, want_alpha=True, row_end=plan["row_end"])
+    assert int(info_e.item()) == 0
+    resid = backend.predict_mean(Xs, Xs, desc, alpha, truncate=False) + es * alpha - ys
+    assert float(resid.abs().max().item()) <= 1e-8 * float(ys.abs().max().item())
+    out_f, info_f, _, _ = backend.loglike(Xs, ys, es, desc, work=work, want_alpha=False, row_end=plan["row_end"])
+    np.testing.assert_allclose(float(out_f[0].item()), float(out_e[0].item()), rtol=1e-12)
+    out_d, info_d, alpha_d, _ = backend.loglike(Xs, ys, es, desc, work=work, want_alpha=True)
+    assert int(info_d.item()) == 0
+    np.testing.assert_allclose(out_e.cpu().numpy(), out_d.cpu().numpy(), rtol=1e-11)
+    assert float((alpha - alpha_d).abs().max().item()) <= 1e-9 * float(alpha_d.abs().max().item())
