@@ -520,6 +520,13 @@ def run_ours(args):
                     "(roofline.timed); traffic / issue-active / warps-active are read from the committed ncu summaries.",
         "vs_reference": "the reference arm is an O(N^2) CPU port on a row sample, not TreeCorr: its ratio is a stated "
                         "baseline, not a speed-up over treegp",
+        "gp": "gp.wall_s is the public GPInterpolation path, which factorises K inside its envelope when the kernel's "
+              "support (correlation >= 1e-40 amp) is short against the field (points sorted along one axis; "
+              "gp.potrf_envelope_s, flops = gp.potrf_envelope_flops_frac of N^3/3; same logL / alpha / mean to "
+              "rounding, tests/test_gpu_envelope.py).  gp.potrf_s / potrf_tflops / potrf_frac_dmma are the DENSE "
+              "factorisation of the same matrix (what the reference's scipy call and cuSOLVER do), kept as the "
+              "tensor-pipe roofline figure.  gp.var_all_M_s uses windows + envelopes (gp_fit_predict.variance.*plan), "
+              "gp.var_plain_* are the plain solves on the cached factor, timed on a subset and extrapolated.",
     }
     if rank == 0:
         print(json.dumps(line), flush=True)
