@@ -108,3 +108,25 @@ def predictive_variance(K_noisy, K_star, amp):
     Lc = cholesky(K_noisy, lower=True)
     V = solve_triangular(Lc, K_star.T, lower=True)
     return amp - np.sum(V * V, axis=0)
+
+
+def cholesky_envelope(K, row_end, block=512):
+    """Restatement (numpy, small cases) of the ENVELOPE form of the factorisation the reference takes at
+    gp_interp.py:181 / log_likelihood.py:30 -- not an algorithm of the reference, which always factorises the dense
+    matrix, but the statement the device path (tgp_potrf_env) makes: a right-looking blocked Cholesky whose panel
+    solve and trailing update of block column b only touch the rows [end of block, row_end[b]).  Everything outside
+    is neither read nor written (it keeps the entries of K).  Used by the CPU tests to show that this equals the dense
+    factor whenever K is (numerically) zero outside the envelope."""
+    A = np.array(K, dtype=float, copy=True)
+    n = A.shape[0]
+    prev = 0
+    for b, k in enumerate(range(0, n, block)):
+        c1 = min(n, k + block)
+        re = min(n, max(int(row_end[b]), prev, c1))
+        prev = re
+        A[k:c1, k:c1] = cholesky(np.tril(A[k:c1, k:c1]) + np.tril(A[k:c1, k:c1], -1).T, lower=True)
+        if re > c1:
+            A[c1:re, k:c1] = solve_triangular(A[k:c1, k:c1], A[c1:re, k:c1].T, lower=True).T
+            upd = A[c1:re, k:c1] @ A[c1:re, k:c1].T
+            A[c1:re, c1:re] -= np.tril(upd)
+    return A

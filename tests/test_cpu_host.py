@@ -515,3 +515,49 @@ def test_plan_envelope_declines_small_and_wide_problems():
     plan = backend.plan_envelope(torch.rand((6000, 2), dtype=torch.float64) * 300.0, narrow)
     assert plan is not None and plan["axis"] == 0 and plan["flops"] * 2 <= plan["flops_dense"]
     assert np.all(np.diff(plan["x"]) >= 0) and len(plan["row_end"]) == 12
+
+
+@pytest.mark.parametrize("family,ndim", [("rbf", 2), ("vonkarman", 2), ("rbf", 1)])
+def test_envelope_factorisation_equals_the_dense_one_on_the_oracle(family, ndim):
+    """The algorithm of tgp_potrf_env restated in numpy (oracle.gp_oracle.cholesky_envelope) with the envelope the
+    host plans (backend.support_cutoffs / envelope_rows, 64-column blocks here so that a small case has many block
+    columns): same factor as scipy's dense Cholesky of the same sorted matrix, K below 1e-40 amp outside the envelope,
+    and the likelihood of log_likelihood.py:29-37 from either factor agrees to rounding."""
+    from oracle import gp_oracle as go
+    from treegp_b200 import backend, eval_kernel
+    from treegp_b200.kernels import lower_kernel
+
+    rng = np.random.default_rng(3 + ndim)
+    n, field, blk = 900, 400.0, 64
+    Mi = np.array([[0.9, -0.35], [-0.35, 0.6]]) if ndim == 2 else np.array([[1.0 / 0.64]])
+    name = {"rbf": "AnisotropicRBF", "vonkarman": "AnisotropicVonKarman"}[family]
+    kstr = ("2.0 * %s(invLam=array([[0.9, -0.35], [-0.35, 0.6]]))" % name) if ndim == 2 else "2.0 * RBF(0.8)"
+    desc = lower_kernel(eval_kernel(kstr), ndim)
+    X = rng.uniform(0, field, size=(n, ndim))
+    dcut = backend.support_cutoffs(desc)
+    axis = int(np.argmin(dcut))
+    X = X[np.argsort(X[:, axis], kind="stable")]
+    x = X[:, axis]
+    # envelope_rows with the product's block width, restated for 64-column blocks
+    c1 = np.minimum(np.arange(blk, n + blk, blk), n)
+    row_end = np.maximum(np.searchsorted(x, x[c1 - 1] + dcut[axis] * (1 + 1e-9), side="left"), c1)
+    assert row_end[0] < n // 2 and row_end[-1] == n          # a real envelope, many block columns
+    e2 = rng.uniform(0.005, 0.02, size=n)
+    K = go.kmat(family, X, amp=2.0, invLam=Mi) + np.diag(e2)
+    outside = np.zeros((n, n), dtype=bool)
+    for b, r in enumerate(row_end):
+        outside[r:, blk * b:blk * (b + 1)] = True
+    assert outside.sum() > 0.5 * n * n / 2 and np.max(np.abs(K[outside])) <= 1e-40 * 2.0
+    from scipy.linalg import cholesky
+    Ld = cholesky(K, lower=True)
+    Le = np.tril(go.cholesky_envelope(K, row_end, block=blk))
+    assert np.max(np.abs(Ld[outside])) < 1e-35
+    np.testing.assert_allclose(Le[~outside], Ld[~outside], rtol=0, atol=1e-13 * np.max(np.abs(Ld)))
+    np.testing.assert_array_equal(Le[outside], np.tril(K)[outside])   # never touched
+    y = rng.normal(size=n)
+    logl_d, alpha_d = go.log_likelihood(K, y)
+    from scipy.linalg import cho_solve
+    alpha_e = cho_solve((Le, True), y)
+    logl_e = -0.5 * y @ alpha_e - np.sum(np.log(np.diag(Le))) - 0.5 * n * np.log(2 * np.pi)
+    assert abs(logl_e - logl_d) <= 1e-12 * abs(logl_d)
+    np.testing.assert_allclose(alpha_e, alpha_d, rtol=0, atol=1e-10 * np.max(np.abs(alpha_d)))
