@@ -41,6 +41,18 @@ def test_invalid_arguments_are_rejected_without_a_gpu():
     ok = _cabi.TgpKernel(0, 2, 1.0, 1.0, 0.0, 1.0)
     assert lib.tgp_kmat_sym(None, 10, ctypes.byref(ok), None, None, 4, 0, None) == -1  # ld < N
     assert lib.tgp_potrf(ctypes.c_void_p(16), 10, 11, ctypes.c_void_p(16), None) == -1  # odd ld
+    # envelope forms: one row_end entry per tgp_envelope_block() columns, no NULL envelope
+    import numpy as np
+    assert lib.tgp_envelope_block() == 512
+    re2 = np.array([1000, 1000], dtype=np.int64)
+    A16, i16 = ctypes.c_void_p(16), ctypes.c_void_p(16)
+    assert lib.tgp_potrf_env(A16, 1000, 1000, None, 2, 0, i16, None) == -1
+    assert b"row_end" in lib.tgp_last_error()
+    assert lib.tgp_potrf_env(A16, 1000, 1000, ctypes.c_void_p(re2.ctypes.data), 3, 0, i16, None) == -1   # 2 blocks, not 3
+    assert lib.tgp_potrf_env(A16, 1000, 1001, ctypes.c_void_p(re2.ctypes.data), 2, 0, i16, None) == -1   # odd ld
+    assert lib.tgp_trsm_rows_env(A16, 1000, 1000, ctypes.c_void_p(re2.ctypes.data), 1, A16, 4, 1000, None) == -1
+    assert lib.tgp_loglike_env(A16, A16, A16, 1000, ctypes.byref(ok), A16, 1000, A16, 0, A16, i16, None, 2, None) == -1
+    assert lib.tgp_predict_var_env(A16, 4, A16, 1000, ctypes.byref(ok), A16, 1000, None, 2, A16, 128, A16, None) == -1
 
 
 def test_product_path_does_not_import_the_oracle():
