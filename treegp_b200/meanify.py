@@ -33,10 +33,35 @@ def knn_average(X0, y0, X, n_neighbors):
 def _bin_index(v, edges):
     """Bin of each value for edges e_0 < ... < e_m: [e_k, e_k+1), last bin closed on the right; -1 if
     outside (the convention of scipy.stats.binned_statistic_2d used at meanify.py:79-111)."""
-    idx = np.searchsorted(edges, v, side="right") - 1
-    idx[v == edges[-1]] = len(edges) - 2
-    idx[(v < edges[0]) | (v > edges[-1])] = -1
-    return idx
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    edges = np.asarray(edges, dtype=np.float64)
+
+    def by_search(x):
+        idx = np.searchsorted(edges, x, side="right") - 1
+        idx[x == edges[-1]] = len(edges) - 2
+        idx[(x < edges[0]) | (x > edges[-1])] = -1
+        return idx
+
+    # The edges come from np.linspace: guess the bin arithmetically, keep the guess where the defining inequality
+    # e_k <= v < e_k+1 holds for the ACTUAL edge values, and settle the rest (points outside, on the last edge, or
+    # one bin off through rounding) by the binary search -- the same bins in every case, without a binary search per
+    # point (2 x 1.2 million of them are 2/3 of a 6-exposure meanify at N = 200 000).
+    m = len(edges) - 1
+    span = edges[-1] - edges[0] if m >= 1 else 0.0
+    if not (m >= 1 and span > 0 and np.isfinite(span)):
+        return by_search(v)
+    with np.errstate(invalid="ignore", over="ignore"):
+        t = v - edges[0]
+        t *= m / span
+        np.clip(t, 0, m - 1, out=t)
+        t[np.isnan(t)] = 0
+        k = t.astype(np.intp)
+    good = edges.take(k) <= v
+    good &= v < edges.take(k + 1)
+    bad = np.flatnonzero(~good)
+    if len(bad):
+        k[bad] = by_search(v[bad])
+    return k
 
 
 class meanify(object):
